@@ -1,0 +1,702 @@
+// C ABI of the engine (include/hac_index.h): shard storage, add / reset, the search driver that
+// chains scan -> refresh -> rescore -> select, and the merge / gather entry points.
+#include <float.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "../../include/hac_index.h"
+#include "hac_common.cuh"
+#include "hac_kernels.cuh"
+
+using namespace hac;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const std::string& msg) {
+    g_err = msg;
+    return code;
+}
+int fail_cuda(cudaError_t e, const char* what) {
+    g_err = std::string(what) + ": " + cudaGetErrorString(e);
+    cudaGetLastError();
+    return (e == cudaErrorMemoryAllocation) ? HAC_E_NOMEM : HAC_E_CUDA;
+}
+#define CU(call)                                              \
+    do {                                                      \
+        cudaError_t e__ = (call);                             \
+        if (e__ != cudaSuccess) return fail_cuda(e__, #call); \
+    } while (0)
+
+constexpr int64_t kRowAlign = 256;          // scan tile width: segment capacities and chunk edges
+constexpr int kMaxQueryBatch = 16384;
+constexpr int kMaxEvents = 96;
+
+int64_t round_up(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
+
+struct Segment {
+    float* rows = nullptr;        // [cap_rows][d] fp32
+    uint8_t* shadow = nullptr;    // f16 tiled image of the same rows
+    OperandStats* stats = nullptr;
+    int64_t cap_rows = 0;
+    int64_t n_rows = 0;
+    uint32_t base = 0;            // index-local row of rows[0]
+    bool closed = false;          // no further appends (a larger segment follows)
+};
+
+struct Workspace {
+    int nq_pad = 0;
+    uint32_t cap = 0;
+    int d = 0;
+    float* q = nullptr;           // device copy of host queries
+    uint8_t* q_shadow = nullptr;
+    OperandStats* q_stats = nullptr;
+    float *q_norm = nullptr, *q_err = nullptr, *margin = nullptr, *tau = nullptr, *thr = nullptr;
+    float* scalars = nullptr;     // [0] absmax scratch, [1] margin_max, [2] screen_err_max
+    unsigned long long* counters = nullptr;  // [0] emitted, [1] rescored
+    CandBuf cb{};
+    float* D = nullptr;
+    int64_t* I = nullptr;
+    int64_t out_elems = 0;
+    void* host_pinned = nullptr;  // 64 B: overflow flag + statistics read-back
+};
+
+}  // namespace
+
+struct hac_index {
+    int d = 0, device = 0, sm_count = 148;
+    cudaStream_t stream = nullptr;
+    std::vector<Segment> segs;
+    int64_t ntotal = 0;
+    int64_t id_base = 0;
+    int64_t* id_table = nullptr;
+    int64_t id_table_n = 0;
+    OperandStats* corpus_stats = nullptr;   // index-wide maxima (device)
+    float* add_scratch = nullptr;           // absmax scratch for add
+    Workspace ws;
+    hac_stats stats{};
+    cudaEvent_t ev[kMaxEvents] = {};
+    bool events_ready = false;
+    bool mma_configured = false;
+};
+
+namespace {
+
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) {
+        cudaGetDevice(&prev);
+        if (prev != dev) cudaSetDevice(dev);
+    }
+    ~DeviceGuard() {
+        int cur = -1;
+        cudaGetDevice(&cur);
+        if (prev >= 0 && cur != prev) cudaSetDevice(prev);
+    }
+};
+
+__global__ void merge_stats_kernel(OperandStats* dst, const OperandStats* src) {
+    dst->absmax = fmaxf(dst->absmax, src->absmax);
+    dst->norm_max = fmaxf(dst->norm_max, src->norm_max);
+    dst->hat_norm_max = fmaxf(dst->hat_norm_max, src->hat_norm_max);
+    dst->err_norm_max = fmaxf(dst->err_norm_max, src->err_norm_max);
+}
+
+void free_segment(Segment& s) {
+    if (s.rows) cudaFree(s.rows);
+    if (s.shadow) cudaFree(s.shadow);
+    if (s.stats) cudaFree(s.stats);
+    s = Segment{};
+}
+
+int alloc_segment(hac_index* idx, int64_t cap_rows, Segment* out) {
+    Segment s;
+    s.cap_rows = round_up(std::max<int64_t>(cap_rows, kRowAlign), kRowAlign);
+    cudaError_t e = cudaMalloc(&s.rows, (size_t)s.cap_rows * idx->d * sizeof(float));
+    if (e == cudaSuccess) e = cudaMalloc(&s.shadow, (size_t)shadow_bytes(s.cap_rows, idx->d));
+    if (e == cudaSuccess) e = cudaMalloc(&s.stats, sizeof(OperandStats));
+    if (e != cudaSuccess) {
+        free_segment(s);
+        return fail_cuda(e, "segment allocation");
+    }
+    cudaMemsetAsync(s.shadow, 0, (size_t)shadow_bytes(s.cap_rows, idx->d), idx->stream);
+    cudaMemsetAsync(s.stats, 0, sizeof(OperandStats), idx->stream);
+    *out = s;
+    return HAC_OK;
+}
+
+// returns the segment the next rows go to, allocating when the last one is full
+int writable_segment(hac_index* idx, int64_t want_rows, Segment** out) {
+    if (!idx->segs.empty()) {
+        Segment& last = idx->segs.back();
+        if (!last.closed && last.n_rows < last.cap_rows) {
+            *out = &last;
+            return HAC_OK;
+        }
+    }
+    if ((int)idx->segs.size() >= kMaxSegments) return fail(HAC_E_STATE, "too many segments; call hac_reserve first");
+    Segment s;
+    const int64_t cap = std::max<int64_t>(want_rows, idx->ntotal);   // at least doubles the shard
+    int rc = alloc_segment(idx, cap, &s);
+    if (rc != HAC_OK) return rc;
+    s.base = (uint32_t)idx->ntotal;
+    idx->segs.push_back(s);
+    *out = &idx->segs.back();
+    return HAC_OK;
+}
+
+enum class RowSource { Host, Device, Synthetic };
+
+int add_rows(hac_index* idx, int64_t n, const float* src, RowSource kind, cudaStream_t user_stream, uint64_t seed,
+             int64_t row0_global, int dist) {
+    if (n < 0) return fail(HAC_E_INVALID, "add: negative row count");
+    if (n == 0) return HAC_OK;
+    if (kind != RowSource::Synthetic && src == nullptr) return fail(HAC_E_INVALID, "add: null row pointer");
+    if (idx->ntotal + n > 0xFFFFFF00ll) return fail(HAC_E_INVALID, "add: shard would exceed 2^32 rows");
+    if (idx->id_table != nullptr && idx->ntotal + n > idx->id_table_n) {
+        // a stale table from a previous block must not silently translate new rows
+        cudaFree(idx->id_table);
+        idx->id_table = nullptr;
+        idx->id_table_n = 0;
+    }
+    DeviceGuard guard(idx->device);
+    cudaStream_t s = idx->stream;
+    if (kind == RowSource::Device && user_stream != nullptr && user_stream != s) {
+        // rows were produced on the caller's stream: order our stream after it
+        cudaEvent_t e;
+        CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        cudaEventRecord(e, user_stream);
+        cudaStreamWaitEvent(s, e, 0);
+        cudaEventDestroy(e);
+    }
+    const int d = idx->d;
+    int64_t done = 0;
+    while (done < n) {
+        Segment* seg = nullptr;
+        int rc = writable_segment(idx, n - done, &seg);
+        if (rc != HAC_OK) return rc;
+        const int64_t m = std::min(n - done, seg->cap_rows - seg->n_rows);
+        float* dst = seg->rows + (size_t)seg->n_rows * d;
+        if (kind == RowSource::Host) {
+            // chunked so that the convert kernel of one chunk overlaps the copy of the next
+            const int64_t chunk_rows = std::max<int64_t>(1, (64ll << 20) / (d * (int64_t)sizeof(float)));
+            for (int64_t o = 0; o < m; o += chunk_rows) {
+                const int64_t c = std::min(chunk_rows, m - o);
+                CU(cudaMemcpyAsync(dst + (size_t)o * d, src + (size_t)(done + o) * d, (size_t)c * d * sizeof(float),
+                                   cudaMemcpyHostToDevice, s));
+            }
+        } else if (kind == RowSource::Device) {
+            CU(cudaMemcpyAsync(dst, src + (size_t)done * d, (size_t)m * d * sizeof(float), cudaMemcpyDeviceToDevice, s));
+        } else {
+            launch_synth(dst, m, d, seed, row0_global + done, dist, s);
+        }
+        launch_absmax(dst, m * d, idx->add_scratch, s);
+        launch_pick_scale(seg->stats, idx->add_scratch, /*keep_scale=*/seg->n_rows > 0 ? 1 : 0, s);
+        const int64_t end = seg->n_rows + m;
+        const int64_t n_pad = std::min(round_up(end, kRowAlign), seg->cap_rows) - seg->n_rows;
+        launch_convert_rows(dst, m, n_pad, d, seg->shadow, seg->n_rows, seg->stats, nullptr, nullptr, s);
+        merge_stats_kernel<<<1, 1, 0, s>>>(idx->corpus_stats, seg->stats);
+        CU(cudaGetLastError());
+        seg->n_rows = end;
+        idx->ntotal += m;
+        done += m;
+    }
+    // faiss copies on add: the caller may free / overwrite its buffer as soon as we return
+    CU(cudaStreamSynchronize(s));
+    return HAC_OK;
+}
+
+uint32_t cap_for_k(int k, int level) {
+    uint32_t cap = k <= 128 ? 4096u : (k <= 512 ? 8192u : 16384u);
+    if (level >= 1 && cap < 16384u) cap *= 2;
+    return cap;
+}
+
+void free_workspace(Workspace& w) {
+    void* ptrs[] = {w.q, w.q_shadow, w.q_stats, w.q_norm, w.q_err, w.margin, w.tau, w.thr, w.scalars, w.counters,
+                    w.cb.score, w.cb.row, w.cb.exact, w.cb.count, w.cb.sorted, w.cb.overflow, w.D, w.I};
+    for (void* p : ptrs)
+        if (p) cudaFree(p);
+    if (w.host_pinned) cudaFreeHost(w.host_pinned);
+    w = Workspace{};
+}
+
+int ensure_workspace(hac_index* idx, int nq_pad, uint32_t cap, int64_t out_elems) {
+    Workspace& w = idx->ws;
+    if (w.host_pinned == nullptr) CU(cudaMallocHost(&w.host_pinned, 64));
+    if (w.scalars == nullptr) {
+        CU(cudaMalloc(&w.scalars, 8 * sizeof(float)));
+        CU(cudaMalloc(&w.counters, 2 * sizeof(unsigned long long)));
+        CU(cudaMalloc(&w.q_stats, sizeof(OperandStats)));
+        CU(cudaMalloc(&w.cb.overflow, sizeof(uint32_t)));
+    }
+    if (nq_pad > w.nq_pad || idx->d != w.d) {
+        // per-query arrays
+        void* ptrs[] = {w.q, w.q_shadow, w.q_norm, w.q_err, w.margin, w.tau, w.thr, w.cb.count, w.cb.sorted,
+                        w.cb.score, w.cb.row, w.cb.exact};
+        for (void* p : ptrs)
+            if (p) cudaFree(p);
+        w.q = nullptr; w.q_shadow = nullptr; w.q_norm = w.q_err = w.margin = w.tau = w.thr = nullptr;
+        w.cb.score = w.cb.exact = nullptr; w.cb.row = w.cb.count = w.cb.sorted = nullptr;
+        const int np = std::max(nq_pad, w.nq_pad);
+        w.nq_pad = 0; w.cap = 0;
+        CU(cudaMalloc(&w.q, (size_t)np * idx->d * sizeof(float)));
+        CU(cudaMalloc(&w.q_shadow, (size_t)shadow_bytes(np, idx->d)));
+        CU(cudaMalloc(&w.q_norm, np * sizeof(float)));
+        CU(cudaMalloc(&w.q_err, np * sizeof(float)));
+        CU(cudaMalloc(&w.margin, np * sizeof(float)));
+        CU(cudaMalloc(&w.tau, np * sizeof(float)));
+        CU(cudaMalloc(&w.thr, np * sizeof(float)));
+        CU(cudaMalloc(&w.cb.count, np * sizeof(uint32_t)));
+        CU(cudaMalloc(&w.cb.sorted, np * sizeof(uint32_t)));
+        w.nq_pad = np; w.d = idx->d;
+    }
+    if (cap > w.cap) {
+        // per-(query, slot) arrays; the per-query arrays above are left alone
+        void* ptrs[] = {w.cb.score, w.cb.row, w.cb.exact};
+        for (void* p : ptrs)
+            if (p) cudaFree(p);
+        w.cb.score = w.cb.exact = nullptr; w.cb.row = nullptr;
+        w.cap = 0;
+        CU(cudaMalloc(&w.cb.score, (size_t)w.nq_pad * cap * sizeof(float)));
+        CU(cudaMalloc(&w.cb.row, (size_t)w.nq_pad * cap * sizeof(uint32_t)));
+        CU(cudaMalloc(&w.cb.exact, (size_t)w.nq_pad * cap * sizeof(float)));
+        w.cap = cap;
+    }
+    if (out_elems > w.out_elems) {
+        if (w.D) cudaFree(w.D);
+        if (w.I) cudaFree(w.I);
+        w.D = nullptr; w.I = nullptr; w.out_elems = 0;
+        CU(cudaMalloc(&w.D, out_elems * sizeof(float)));
+        CU(cudaMalloc(&w.I, out_elems * sizeof(int64_t)));
+        w.out_elems = out_elems;
+    }
+    w.cb.emitted = w.counters;
+    return HAC_OK;
+}
+
+struct HostReadback {
+    uint32_t overflow;
+    uint32_t pad;
+    unsigned long long emitted;
+    unsigned long long rescored;
+    float margin_max;
+    float screen_err_max;
+};
+
+// One query batch (nq <= kMaxQueryBatch) over the whole shard; all buffers on the device.
+int search_batch(hac_index* idx, int nq, const float* q_dev, int k, float* D_dev, int64_t* I_dev, cudaStream_t s,
+                 int path) {
+    const int d = idx->d;
+    const int nq_pad = (int)round_up(nq, kTileRows);
+    if (path == HAC_PATH_AUTO) path = nq <= 4 ? HAC_PATH_GEMV : HAC_PATH_MMA;
+    if (path == HAC_PATH_GEMV && nq > 4) return fail(HAC_E_INVALID, "GEMV path takes at most 4 queries per batch");
+    if (!idx->events_ready) {
+        for (auto& e : idx->ev) CU(cudaEventCreate(&e));
+        idx->events_ready = true;
+    }
+    if (path == HAC_PATH_MMA && !idx->mma_configured) {
+        CU(scan_mma_configure());
+        idx->mma_configured = true;
+    }
+    hac_stats& st = idx->stats;
+    st.path = path;
+    st.retries = 0;
+
+    for (int level = 0; level < 3; ++level) {
+        const uint32_t cap = cap_for_k(k, level);
+        int rc = ensure_workspace(idx, nq_pad, cap, 0);
+        if (rc != HAC_OK) return rc;
+        Workspace& w = idx->ws;
+        CandBuf cb = w.cb;
+        cb.cap = cap;   // rows of the candidate arrays are cap entries apart (may be below the allocation)
+        int launches = 0, n_chunks = 0, n_ev = 2;
+        cudaEventRecord(idx->ev[0], s);
+        launch_init_search(cb, w.tau, w.thr, nq, nq_pad, s);
+        ++launches;
+        if (path == HAC_PATH_MMA) {
+            cudaMemsetAsync(w.q_stats, 0, sizeof(OperandStats), s);
+            launch_absmax(q_dev, (int64_t)nq * d, w.scalars + 0, s);
+            launch_pick_scale(w.q_stats, w.scalars + 0, 0, s);
+            launch_convert_rows(q_dev, nq, nq_pad, d, w.q_shadow, 0, w.q_stats, w.q_norm, w.q_err, s);
+            launch_margins(w.q_norm, w.q_err, idx->corpus_stats, d, w.margin, w.scalars + 1, nq, s);
+            launches += 4;
+        } else {
+            launch_margins(nullptr, nullptr, nullptr, d, w.margin, w.scalars + 1, nq, s);
+            ++launches;
+        }
+        // chunk schedule: the first chunk is emitted unfiltered (it must fit the shortlist), later
+        // chunks grow geometrically with the rows already seen, so every chunk is expected to add
+        // about growth * k * (margin factor) candidates per query.
+        double growth = std::min(4.0, std::max(1.0, (double)cap / (8.0 * k)));
+        if (level == 1) growth = std::max(0.5, growth / 4.0);
+        int64_t rows_done = 0;
+        for (size_t si = 0; si < idx->segs.size(); ++si) {
+            const Segment& seg = idx->segs[si];
+            int64_t r = 0;
+            while (r < seg.n_rows) {
+                int64_t size;
+                if (level == 2) size = cap / 4;
+                else if (rows_done == 0) size = cap / 2;
+                else size = (int64_t)(growth * (double)rows_done);
+                size = std::max<int64_t>(kRowAlign, size / kRowAlign * kRowAlign);
+                const int64_t r1 = std::min(seg.n_rows, r + size);
+                const bool timed = n_ev + 2 <= kMaxEvents;
+                if (timed) cudaEventRecord(idx->ev[n_ev], s);
+                if (path == HAC_PATH_MMA) {
+                    MmaScanArgs a;
+                    a.q_shadow = w.q_shadow;
+                    a.x_shadow = seg.shadow;
+                    a.q_stats = w.q_stats;
+                    a.x_stats = seg.stats;
+                    a.thr = w.thr;
+                    a.d = d;
+                    a.n_qtiles = nq_pad / kTileRows;
+                    a.ct0 = r / kRowAlign;
+                    a.ct1 = (r1 + kRowAlign - 1) / kRowAlign;
+                    a.seg_rows = seg.n_rows;
+                    a.row_id_base = seg.base;
+                    a.cb = cb;
+                    CU(launch_scan_mma(a, idx->sm_count, s));
+                } else {
+                    launch_scan_gemv(seg.rows, r, r1, d, q_dev, nq, w.thr, cb, seg.base, idx->sm_count, s);
+                }
+                if (timed) {
+                    cudaEventRecord(idx->ev[n_ev + 1], s);
+                    n_ev += 2;
+                }
+                launch_refresh(cb, k, w.margin, w.tau, w.thr, nq, s);
+                launches += 2;
+                ++n_chunks;
+                rows_done += r1 - r;
+                r = r1;
+            }
+        }
+        SegTable segs;
+        segs.n = (int)idx->segs.size();
+        for (int i = 0; i < segs.n; ++i) {
+            segs.base[i] = idx->segs[i].base;
+            segs.rows[i] = idx->segs[i].rows;
+        }
+        launch_rescore(cb, q_dev, d, segs, nq, w.scalars + 2, w.counters + 1, s);
+        launch_final_select(cb, k, nq, idx->id_table, idx->id_base, D_dev, I_dev, s);
+        launches += 2;
+        cudaEventRecord(idx->ev[1], s);
+        CU(cudaGetLastError());
+        // read back the overflow flag and the statistics (56 bytes)
+        HostReadback* hr = static_cast<HostReadback*>(w.host_pinned);
+        CU(cudaMemcpyAsync(&hr->overflow, cb.overflow, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+        CU(cudaMemcpyAsync(&hr->emitted, w.counters, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+        CU(cudaMemcpyAsync(&hr->margin_max, w.scalars + 1, 2 * sizeof(float), cudaMemcpyDeviceToHost, s));
+        CU(cudaStreamSynchronize(s));
+        st.n_chunks = n_chunks;
+        st.kernel_launches = launches;
+        st.candidates_emitted = (int64_t)hr->emitted;
+        st.candidates_rescored = (int64_t)hr->rescored;
+        st.margin_max = hr->margin_max;
+        st.screen_err_max = hr->screen_err_max;
+        float ms = 0.f, scan_ms = 0.f;
+        cudaEventElapsedTime(&ms, idx->ev[0], idx->ev[1]);
+        for (int i = 2; i + 1 < n_ev; i += 2) {
+            float t = 0.f;
+            cudaEventElapsedTime(&t, idx->ev[i], idx->ev[i + 1]);
+            scan_ms += t;
+        }
+        st.total_ms = ms;
+        st.scan_ms = scan_ms;
+        if (!hr->overflow) return HAC_OK;
+        st.retries = level + 1;
+    }
+    return fail(HAC_E_OVERFLOW,
+                "candidate shortlist overflowed in every retry mode (pathological near-duplicate corpus?)");
+}
+
+int search_common(hac_index* idx, int64_t nq, const float* q, bool q_on_host, int k, float* D, int64_t* I,
+                  bool out_on_host, cudaStream_t user_stream, int path) {
+    if (idx == nullptr) return fail(HAC_E_INVALID, "search: null index");
+    if (nq < 0 || (nq > 0 && (q == nullptr || D == nullptr || I == nullptr)))
+        return fail(HAC_E_INVALID, "search: null buffer");
+    if (k <= 0 || k > HAC_MAX_K) {
+        char buf[96];
+        snprintf(buf, sizeof buf, "search: k=%d outside [1, %d]", k, HAC_MAX_K);
+        return fail(HAC_E_INVALID, buf);
+    }
+    if (path != HAC_PATH_AUTO && path != HAC_PATH_GEMV && path != HAC_PATH_MMA)
+        return fail(HAC_E_INVALID, "search: unknown path");
+    if (nq == 0) return HAC_OK;
+    DeviceGuard guard(idx->device);
+    cudaStream_t s = user_stream ? user_stream : idx->stream;
+    idx->stats.ntotal = idx->ntotal;
+    const int64_t max_batch = (path == HAC_PATH_GEMV) ? 4 : kMaxQueryBatch;
+    if (idx->ntotal == 0) {
+        // faiss: empty index -> every slot unfilled
+        if (out_on_host) {
+            for (int64_t i = 0; i < nq * k; ++i) { D[i] = -FLT_MAX; I[i] = -1; }
+        } else {
+            launch_fill_empty(D, I, nq * k, s);
+            CU(cudaStreamSynchronize(s));
+        }
+        return HAC_OK;
+    }
+    float total_ms = 0.f, scan_ms = 0.f;
+    int64_t emitted = 0, rescored = 0;
+    int launches = 0, retries = 0;
+    float margin_max = 0.f, err_max = 0.f;
+    for (int64_t q0 = 0; q0 < nq; q0 += max_batch) {
+        const int nb = (int)std::min<int64_t>(max_batch, nq - q0);
+        const int nb_pad = (int)round_up(nb, kTileRows);
+        int rc = ensure_workspace(idx, nb_pad, cap_for_k(k, 0), (q_on_host || out_on_host) ? (int64_t)nb * k : 0);
+        if (rc != HAC_OK) return rc;
+        const float* qd = q + (size_t)q0 * idx->d;
+        if (q_on_host) {
+            CU(cudaMemcpyAsync(idx->ws.q, qd, (size_t)nb * idx->d * sizeof(float), cudaMemcpyHostToDevice, s));
+            qd = idx->ws.q;
+        }
+        float* Dd = out_on_host ? idx->ws.D : D + (size_t)q0 * k;
+        int64_t* Id = out_on_host ? idx->ws.I : I + (size_t)q0 * k;
+        rc = search_batch(idx, nb, qd, k, Dd, Id, s, path);
+        if (rc != HAC_OK) return rc;
+        if (out_on_host) {
+            CU(cudaMemcpyAsync(D + (size_t)q0 * k, Dd, (size_t)nb * k * sizeof(float), cudaMemcpyDeviceToHost, s));
+            CU(cudaMemcpyAsync(I + (size_t)q0 * k, Id, (size_t)nb * k * sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+            CU(cudaStreamSynchronize(s));
+        }
+        total_ms += idx->stats.total_ms; scan_ms += idx->stats.scan_ms;
+        emitted += idx->stats.candidates_emitted; rescored += idx->stats.candidates_rescored;
+        launches += idx->stats.kernel_launches; retries += idx->stats.retries;
+        margin_max = std::max(margin_max, idx->stats.margin_max);
+        err_max = std::max(err_max, idx->stats.screen_err_max);
+    }
+    idx->stats.total_ms = total_ms; idx->stats.scan_ms = scan_ms;
+    idx->stats.candidates_emitted = emitted; idx->stats.candidates_rescored = rescored;
+    idx->stats.kernel_launches = launches; idx->stats.retries = retries;
+    idx->stats.margin_max = margin_max; idx->stats.screen_err_max = err_max;
+    return HAC_OK;
+}
+
+}  // namespace
+
+// =============================================================================================
+extern "C" {
+
+int hac_abi_version(void) { return HAC_ABI_VERSION; }
+const char* hac_last_error(void) { return g_err.c_str(); }
+
+int hac_create(int d, int device, hac_index** out) {
+    if (out == nullptr) return fail(HAC_E_INVALID, "create: null out pointer");
+    *out = nullptr;
+    if (d <= 0 || d % 64 != 0 || d > 1024) return fail(HAC_E_INVALID, "create: d must be a multiple of 64 in [64, 1024]");
+    int n_dev = 0;
+    CU(cudaGetDeviceCount(&n_dev));
+    if (device < 0 || device >= n_dev) return fail(HAC_E_INVALID, "create: no such CUDA device");
+    DeviceGuard guard(device);
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) return fail(HAC_E_STATE, "this engine is built for sm_100a (B200) only");
+    hac_index* idx = new hac_index();
+    idx->d = d;
+    idx->device = device;
+    idx->sm_count = prop.multiProcessorCount;
+    cudaError_t e = cudaStreamCreateWithFlags(&idx->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaMalloc(&idx->corpus_stats, sizeof(OperandStats));
+    if (e == cudaSuccess) e = cudaMalloc(&idx->add_scratch, 4 * sizeof(float));
+    if (e == cudaSuccess) e = cudaMemset(idx->corpus_stats, 0, sizeof(OperandStats));
+    if (e != cudaSuccess) {
+        hac_destroy(idx);
+        return fail_cuda(e, "create");
+    }
+    *out = idx;
+    return HAC_OK;
+}
+
+int hac_destroy(hac_index* idx) {
+    if (idx == nullptr) return HAC_OK;
+    DeviceGuard guard(idx->device);
+    cudaDeviceSynchronize();
+    for (auto& s : idx->segs) free_segment(s);
+    free_workspace(idx->ws);
+    if (idx->id_table) cudaFree(idx->id_table);
+    if (idx->corpus_stats) cudaFree(idx->corpus_stats);
+    if (idx->add_scratch) cudaFree(idx->add_scratch);
+    if (idx->events_ready)
+        for (auto& e : idx->ev) cudaEventDestroy(e);
+    if (idx->stream) cudaStreamDestroy(idx->stream);
+    delete idx;
+    return HAC_OK;
+}
+
+int hac_reserve(hac_index* idx, int64_t n_rows) {
+    if (idx == nullptr || n_rows < 0) return fail(HAC_E_INVALID, "reserve: bad argument");
+    DeviceGuard guard(idx->device);
+    const int64_t need = n_rows - idx->ntotal;
+    if (!idx->segs.empty()) {
+        Segment& last = idx->segs.back();
+        if (!last.closed && last.cap_rows - last.n_rows >= need) return HAC_OK;
+        if (last.n_rows == 0) {            // replace an empty tail segment
+            free_segment(last);
+            idx->segs.pop_back();
+        } else {
+            last.closed = true;            // its spare capacity stays unused
+        }
+    }
+    if (need <= 0) return HAC_OK;
+    if ((int)idx->segs.size() >= kMaxSegments) return fail(HAC_E_STATE, "reserve: too many segments");
+    Segment s;
+    int rc = alloc_segment(idx, need, &s);
+    if (rc != HAC_OK) return rc;
+    s.base = (uint32_t)idx->ntotal;
+    idx->segs.push_back(s);
+    CU(cudaStreamSynchronize(idx->stream));
+    return HAC_OK;
+}
+
+int hac_add(hac_index* idx, int64_t n, const float* x_host) {
+    if (idx == nullptr) return fail(HAC_E_INVALID, "add: null index");
+    return add_rows(idx, n, x_host, RowSource::Host, nullptr, 0, 0, 0);
+}
+int hac_add_device(hac_index* idx, int64_t n, const float* x_dev, void* stream) {
+    if (idx == nullptr) return fail(HAC_E_INVALID, "add: null index");
+    return add_rows(idx, n, x_dev, RowSource::Device, static_cast<cudaStream_t>(stream), 0, 0, 0);
+}
+int hac_add_synthetic(hac_index* idx, int64_t n, uint64_t seed, int64_t row0, int dist) {
+    if (idx == nullptr) return fail(HAC_E_INVALID, "add: null index");
+    if (dist != 0 && dist != 1) return fail(HAC_E_INVALID, "add_synthetic: dist must be 0 or 1");
+    return add_rows(idx, n, nullptr, RowSource::Synthetic, nullptr, seed, row0, dist);
+}
+int hac_synth_fill_device(int device, float* out_dev, int64_t n, int d, uint64_t seed, int64_t row0, int dist,
+                          void* stream) {
+    if (out_dev == nullptr || n < 0 || d <= 0 || d % 2) return fail(HAC_E_INVALID, "synth_fill: bad argument");
+    DeviceGuard guard(device);
+    launch_synth(out_dev, n, d, seed, row0, dist, static_cast<cudaStream_t>(stream));
+    CU(cudaGetLastError());
+    return HAC_OK;
+}
+
+int hac_reset(hac_index* idx) {
+    if (idx == nullptr) return fail(HAC_E_INVALID, "reset: null index");
+    DeviceGuard guard(idx->device);
+    CU(cudaStreamSynchronize(idx->stream));
+    // keep the largest segment (capacity for the next block), drop the rest
+    if (idx->segs.size() > 1) {
+        size_t best = 0;
+        for (size_t i = 1; i < idx->segs.size(); ++i)
+            if (idx->segs[i].cap_rows > idx->segs[best].cap_rows) best = i;
+        Segment keep = idx->segs[best];
+        for (size_t i = 0; i < idx->segs.size(); ++i)
+            if (i != best) free_segment(idx->segs[i]);
+        idx->segs.assign(1, keep);
+    }
+    for (auto& s : idx->segs) {
+        s.n_rows = 0;
+        s.base = 0;
+        s.closed = false;
+        CU(cudaMemsetAsync(s.stats, 0, sizeof(OperandStats), idx->stream));
+    }
+    CU(cudaMemsetAsync(idx->corpus_stats, 0, sizeof(OperandStats), idx->stream));
+    if (idx->id_table) {
+        cudaFree(idx->id_table);
+        idx->id_table = nullptr;
+        idx->id_table_n = 0;
+    }
+    idx->ntotal = 0;
+    CU(cudaStreamSynchronize(idx->stream));
+    return HAC_OK;
+}
+
+int hac_set_id_base(hac_index* idx, int64_t id_base) {
+    if (idx == nullptr) return fail(HAC_E_INVALID, "set_id_base: null index");
+    idx->id_base = id_base;
+    return HAC_OK;
+}
+
+int hac_set_id_table(hac_index* idx, const int64_t* ids_host, int64_t n) {
+    if (idx == nullptr) return fail(HAC_E_INVALID, "set_id_table: null index");
+    DeviceGuard guard(idx->device);
+    if (idx->id_table) {
+        CU(cudaStreamSynchronize(idx->stream));
+        cudaFree(idx->id_table);
+        idx->id_table = nullptr;
+        idx->id_table_n = 0;
+    }
+    if (ids_host == nullptr || n == 0) return HAC_OK;
+    if (n < idx->ntotal) return fail(HAC_E_INVALID, "set_id_table: table shorter than ntotal");
+    CU(cudaMalloc(&idx->id_table, n * sizeof(int64_t)));
+    CU(cudaMemcpy(idx->id_table, ids_host, n * sizeof(int64_t), cudaMemcpyHostToDevice));
+    idx->id_table_n = n;
+    return HAC_OK;
+}
+
+int hac_search(hac_index* idx, int64_t nq, const float* q_host, int k, float* D_host, int64_t* I_host) {
+    return search_common(idx, nq, q_host, true, k, D_host, I_host, true, nullptr, HAC_PATH_AUTO);
+}
+int hac_search_ex(hac_index* idx, int64_t nq, const float* q_host, int k, float* D_host, int64_t* I_host,
+                  int path) {
+    return search_common(idx, nq, q_host, true, k, D_host, I_host, true, nullptr, path);
+}
+int hac_search_device(hac_index* idx, int64_t nq, const float* q_dev, int k, float* D_dev, int64_t* I_dev,
+                      void* stream) {
+    return search_common(idx, nq, q_dev, false, k, D_dev, I_dev, false, static_cast<cudaStream_t>(stream),
+                         HAC_PATH_AUTO);
+}
+int hac_search_device_ex(hac_index* idx, int64_t nq, const float* q_dev, int k, float* D_dev, int64_t* I_dev,
+                         void* stream, int path) {
+    return search_common(idx, nq, q_dev, false, k, D_dev, I_dev, false, static_cast<cudaStream_t>(stream), path);
+}
+
+int hac_merge_topk_device(int device, int n_lists, int64_t nq, int k, const float* D_lists_dev,
+                          const int64_t* I_lists_dev, int k_out, float* D_out_dev, int64_t* I_out_dev,
+                          void* stream) {
+    if (n_lists <= 0 || nq < 0 || k <= 0 || k_out <= 0 || !D_lists_dev || !I_lists_dev || !D_out_dev || !I_out_dev)
+        return fail(HAC_E_INVALID, "merge: bad argument");
+    if ((int64_t)n_lists * k > 16384) return fail(HAC_E_INVALID, "merge: n_lists * k exceeds 16384");
+    if (nq == 0) return HAC_OK;
+    DeviceGuard guard(device);
+    CU(launch_merge_topk(n_lists, nq, k, D_lists_dev, I_lists_dev, k_out, D_out_dev, I_out_dev,
+                         static_cast<cudaStream_t>(stream)));
+    return HAC_OK;
+}
+
+int hac_gather_ids_device(int device, const int64_t* table_dev, int64_t table_n, const int64_t* ids_dev, int64_t n,
+                          int64_t* out_dev, void* stream) {
+    if (!table_dev || !ids_dev || !out_dev || n < 0) return fail(HAC_E_INVALID, "gather: bad argument");
+    DeviceGuard guard(device);
+    launch_gather_ids(table_dev, table_n, ids_dev, n, out_dev, static_cast<cudaStream_t>(stream));
+    CU(cudaGetLastError());
+    return HAC_OK;
+}
+
+int hac_pinned_alloc(size_t bytes, void** out_host) {
+    if (out_host == nullptr) return fail(HAC_E_INVALID, "pinned_alloc: null out pointer");
+    *out_host = nullptr;
+    cudaError_t e = cudaMallocHost(out_host, bytes ? bytes : 1);
+    if (e != cudaSuccess) return fail_cuda(e, "cudaMallocHost");
+    return HAC_OK;
+}
+int hac_pinned_free(void* host) {
+    if (host) cudaFreeHost(host);
+    return HAC_OK;
+}
+
+int64_t hac_ntotal(const hac_index* idx) { return idx ? idx->ntotal : -1; }
+int hac_dim(const hac_index* idx) { return idx ? idx->d : -1; }
+int hac_device(const hac_index* idx) { return idx ? idx->device : -1; }
+int hac_get_stats(const hac_index* idx, hac_stats* out) {
+    if (idx == nullptr || out == nullptr) return fail(HAC_E_INVALID, "get_stats: null argument");
+    *out = idx->stats;
+    out->ntotal = idx->ntotal;
+    int64_t b32 = 0, bsh = 0;
+    for (const auto& s : idx->segs) {
+        b32 += s.cap_rows * (int64_t)idx->d * 4;
+        bsh += shadow_bytes(s.cap_rows, idx->d);
+    }
+    out->bytes_fp32 = b32;
+    out->bytes_shadow = bsh;
+    return HAC_OK;
+}
+
+}  // extern "C"

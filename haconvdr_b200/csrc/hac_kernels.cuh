@@ -1,0 +1,92 @@
+// Declarations shared by the kernel translation units and the C-ABI layer.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace hac {
+
+constexpr int kMaxSegments = 32;
+
+// Per-operand statistics kept on the device (written by the convert kernels, read by the
+// margin / scan kernels), so a search never has to synchronise with the host.
+struct OperandStats {
+    float absmax;        // max |x| over the rows converted so far
+    float scale;         // power-of-two factor applied before rounding to f16
+    float inv_scale;     // 1 / scale
+    float norm_max;      // max_j ||x_j||_2            (fp32 rows)
+    float hat_norm_max;  // max_j ||f16(x_j*scale)/scale||_2
+    float err_norm_max;  // max_j ||x_j - f16(x_j*scale)/scale||_2
+    float pad0, pad1;
+};
+
+// Candidate shortlist: per query a list of (screen score, index-local row) pairs.
+struct CandBuf {
+    float* score;        // [nq_pad][cap]  screen (approximate) score, unscaled units
+    uint32_t* row;       // [nq_pad][cap]  index-local row
+    float* exact;        // [nq_pad][cap]  exact fp32 score (filled by the rescore kernel)
+    uint32_t* count;     // [nq_pad]       entries appended (may exceed cap -> overflow)
+    uint32_t* sorted;    // [nq_pad]       entries already sorted/compacted by the last refresh
+    uint32_t* overflow;  // [1]
+    unsigned long long* emitted;  // [1] total pairs that passed the filter (statistics)
+    uint32_t cap;
+};
+
+struct SegTable {
+    int n;
+    uint32_t base[kMaxSegments];     // index-local row of the segment's first row
+    const float* rows[kMaxSegments]; // fp32 rows of the segment
+};
+
+// ---- prep ----------------------------------------------------------------------------------
+void launch_absmax(const float* x, int64_t n_elems, float* absmax_out, cudaStream_t s);
+// scale <- 2^(12 - ceil(log2(absmax))) unless *stats already holds a scale and keep_scale != 0
+void launch_pick_scale(OperandStats* stats, const float* absmax_in, int keep_scale, cudaStream_t s);
+// rows [0,n) of x -> shadow rows [row0, row0+n); rows [n, n_pad) are written as zeros.
+void launch_convert_rows(const float* x, int64_t n, int64_t n_pad, int d, uint8_t* shadow, int64_t row0,
+                         OperandStats* stats, float* row_norm, float* row_err, cudaStream_t s);
+void launch_synth(float* out, int64_t n, int d, uint64_t seed, int64_t row0, int dist, cudaStream_t s);
+
+// ---- search state --------------------------------------------------------------------------
+void launch_init_search(CandBuf cb, float* tau, float* thr, int nq, int nq_pad, cudaStream_t s);
+// margin[q] = ||e_q|| * Xhat_max + ||q|| * Ex_max + slack   (0 when corpus==nullptr: exact scan)
+void launch_margins(const float* q_norm, const float* q_err, const OperandStats* corpus, int d, float* margin,
+                    float* margin_max, int nq, cudaStream_t s);
+// per query: sort the shortlist, raise tau to the k-th best screen score, drop entries below tau - 2m
+void launch_refresh(CandBuf cb, int k, const float* margin, float* tau, float* thr, int nq, cudaStream_t s);
+// exact fp32 scores of every shortlisted pair
+void launch_rescore(CandBuf cb, const float* q, int d, SegTable segs, int nq, float* screen_err_max,
+                    unsigned long long* rescored, cudaStream_t s);
+// final top-k by (exact score desc, id asc) with id translation
+void launch_final_select(CandBuf cb, int k, int nq, const int64_t* id_table, int64_t id_base, float* D,
+                         int64_t* I, cudaStream_t s);
+void launch_fill_empty(float* D, int64_t* I, int64_t n, cudaStream_t s);
+
+// ---- scans ---------------------------------------------------------------------------------
+// exact fp32 streaming scan of rows [r0, r1) of one segment, 1..4 queries
+void launch_scan_gemv(const float* rows, int64_t r0, int64_t r1, int d, const float* q, int nq,
+                      const float* thr, CandBuf cb, uint32_t row_id_base, int sm_count, cudaStream_t s);
+// tcgen05 f16 screen of 256-row column tiles [ct0, ct1) of one segment against all query tiles
+struct MmaScanArgs {
+    const uint8_t* q_shadow;
+    const uint8_t* x_shadow;
+    const OperandStats* q_stats;
+    const OperandStats* x_stats;
+    const float* thr;       // [n_qtiles*128] unscaled emission thresholds
+    int d;
+    int n_qtiles;
+    int64_t ct0, ct1;       // 256-row tiles of the segment
+    int64_t seg_rows;       // valid rows of the segment
+    uint32_t row_id_base;
+    CandBuf cb;
+};
+cudaError_t launch_scan_mma(const MmaScanArgs& a, int sm_count, cudaStream_t s);
+cudaError_t scan_mma_configure();
+
+// ---- merge / gather ---------------------------------------------------------------------------
+cudaError_t launch_merge_topk(int n_lists, int64_t nq, int k, const float* D_lists, const int64_t* I_lists,
+                              int k_out, float* D_out, int64_t* I_out, cudaStream_t s);
+void launch_gather_ids(const int64_t* table, int64_t table_n, const int64_t* ids, int64_t n, int64_t* out,
+                       cudaStream_t s);
+
+}  // namespace hac

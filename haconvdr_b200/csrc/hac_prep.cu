@@ -1,0 +1,168 @@
+// Operand preparation: fp32 rows -> f16 tiled/swizzled shadow (+ error norms for the rigorous
+// screen margin), synthetic corpus generator.  All HBM-bound, 128-bit vectorised, one warp per row.
+#include "hac_common.cuh"
+#include "hac_kernels.cuh"
+
+namespace hac {
+
+// ---------------------------------------------------------------------------------------------
+__global__ void absmax_kernel(const float4* __restrict__ x, int64_t n4, float* __restrict__ out) {
+    float m = 0.f;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+        const float4 v = __ldg(x + i);
+        m = fmaxf(m, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    // non-negative floats order like their bit patterns
+    if ((threadIdx.x & 31) == 0) atomicMax(reinterpret_cast<int*>(out), __float_as_int(m));
+}
+
+void launch_absmax(const float* x, int64_t n_elems, float* absmax_out, cudaStream_t s) {
+    cudaMemsetAsync(absmax_out, 0, sizeof(float), s);
+    const int64_t n4 = n_elems / 4;
+    if (n4 == 0) return;
+    int blocks = (int)((n4 + 255) / 256);
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    absmax_kernel<<<blocks, 256, 0, s>>>(reinterpret_cast<const float4*>(x), n4, absmax_out);
+}
+
+// scale = 2^(12 - ceil(log2(absmax))): |x*scale| <= 4096, three octaves of headroom below the
+// f16 maximum for later appends to the same segment; values that still overflow saturate in the
+// convert kernel and show up in err_norm_max (the margin stays rigorous).
+__global__ void pick_scale_kernel(OperandStats* st, const float* absmax_in, int keep_scale) {
+    const float am = *absmax_in;
+    st->absmax = fmaxf(st->absmax, am);
+    if (keep_scale && st->scale != 0.f) return;
+    int e = 0;
+    float scale = 1.f;
+    if (am > 0.f && isfinite(am)) {
+        frexpf(am, &e);                 // am = f * 2^e, f in [0.5, 1)  ->  am <= 2^e
+        int p = 12 - e;
+        p = max(-100, min(100, p));
+        scale = ldexpf(1.f, p);
+    }
+    st->scale = scale;
+    st->inv_scale = 1.f / scale;
+}
+
+void launch_pick_scale(OperandStats* stats, const float* absmax_in, int keep_scale, cudaStream_t s) {
+    pick_scale_kernel<<<1, 1, 0, s>>>(stats, absmax_in, keep_scale);
+}
+
+// ---------------------------------------------------------------------------------------------
+// One warp per row.  Each lane converts 16-byte output chunks (8 elements): two float4 loads,
+// scale, round-to-nearest f16 (saturating), one 16 B store into the swizzled tile image.
+// Per-row sums of x^2, xhat^2 and (x - xhat)^2 feed the screen margin.
+__global__ void __launch_bounds__(256) convert_rows_kernel(const float* __restrict__ x, int64_t n, int64_t n_pad,
+                                                           int d, uint8_t* __restrict__ shadow, int64_t row0,
+                                                           OperandStats* __restrict__ stats,
+                                                           float* __restrict__ row_norm,
+                                                           float* __restrict__ row_err) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const float scale = stats->scale, inv_scale = stats->inv_scale;
+    const int chunks = d >> 3;
+    float w_norm = 0.f, w_hat = 0.f, w_err = 0.f;
+    for (int64_t r = warp; r < n_pad; r += n_warps) {
+        float s_x = 0.f, s_h = 0.f, s_e = 0.f;
+        for (int c = lane; c < chunks; c += 32) {
+            uint4 packed = make_uint4(0u, 0u, 0u, 0u);
+            if (r < n) {
+                const float4* src = reinterpret_cast<const float4*>(x + r * d + c * 8);
+                const float4 a = __ldg(src), b = __ldg(src + 1);
+                const float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+                __half h[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    float t = v[i] * scale;
+                    t = fminf(fmaxf(t, -65504.f), 65504.f);
+                    h[i] = __float2half_rn(t);
+                    const float back = __half2float(h[i]) * inv_scale;
+                    const float e = v[i] - back;
+                    s_x = fmaf(v[i], v[i], s_x);
+                    s_h = fmaf(back, back, s_h);
+                    s_e = fmaf(e, e, s_e);
+                }
+                packed = *reinterpret_cast<uint4*>(h);
+            }
+            *reinterpret_cast<uint4*>(shadow + shadow_chunk_offset(row0 + r, c, d)) = packed;
+        }
+        if (r < n) {
+            s_x = warp_sum(s_x);
+            s_h = warp_sum(s_h);
+            s_e = warp_sum(s_e);
+            // round the norms up a little: they are used as upper bounds
+            const float nx = sqrtf(s_x) * 1.0001f, nh = sqrtf(s_h) * 1.0001f, ne = sqrtf(s_e) * 1.0001f;
+            if (row_norm != nullptr && lane == 0) {
+                row_norm[r] = nx;
+                row_err[r] = ne;
+            }
+            w_norm = fmaxf(w_norm, nx);
+            w_hat = fmaxf(w_hat, nh);
+            w_err = fmaxf(w_err, ne);
+        } else if (row_norm != nullptr && lane == 0) {
+            row_norm[r] = 0.f;
+            row_err[r] = 0.f;
+        }
+    }
+    if (lane == 0 && w_norm > 0.f) {
+        atomicMax(reinterpret_cast<int*>(&stats->norm_max), __float_as_int(w_norm));
+        atomicMax(reinterpret_cast<int*>(&stats->hat_norm_max), __float_as_int(w_hat));
+        atomicMax(reinterpret_cast<int*>(&stats->err_norm_max), __float_as_int(w_err));
+    }
+}
+
+void launch_convert_rows(const float* x, int64_t n, int64_t n_pad, int d, uint8_t* shadow, int64_t row0,
+                         OperandStats* stats, float* row_norm, float* row_err, cudaStream_t s) {
+    if (n_pad <= 0) return;
+    int64_t blocks = (n_pad + 7) / 8;  // 8 warps per block, one row per warp per pass
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    convert_rows_kernel<<<(int)blocks, 256, 0, s>>>(x, n, n_pad, d, shadow, row0, stats, row_norm, row_err);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Synthetic rows: element (r, c) is a pure function of (seed, r, c) - counter-based, so shards
+// of any size reproduce the same global corpus.  splitmix64 -> two 24-bit uniforms -> Box-Muller.
+__device__ __forceinline__ uint64_t splitmix64(uint64_t z) {
+    z += 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+__device__ __forceinline__ float2 normal_pair(uint64_t seed, uint64_t counter) {
+    const uint64_t h = splitmix64(splitmix64(seed) ^ (counter * 0xD1342543DE82EF95ull + 0x632BE59BD9B4E019ull));
+    const float u1 = ((float)(uint32_t)(h >> 40) + 1.0f) * (1.0f / 16777216.0f);   // (0, 1]
+    const float u2 = (float)(uint32_t)((h >> 8) & 0xFFFFFFu) * (1.0f / 16777216.0f);  // [0, 1)
+    const float rad = sqrtf(-2.0f * logf(u1));
+    float sn, cs;
+    sincospif(2.0f * u2, &sn, &cs);
+    return make_float2(rad * cs, rad * sn);
+}
+
+__global__ void synth_kernel(float2* __restrict__ out, int64_t n_pairs, int d2, uint64_t seed, int64_t row0,
+                             int dist) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n_pairs;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = i / d2;
+        const int c2 = (int)(i - r * d2);
+        float2 z = normal_pair(seed, (uint64_t)((row0 + r) * d2 + c2));
+        if (dist == 1) {
+            const float2 mu = normal_pair(seed ^ 0x5DEECE66Dull, 0xFFFFFFFF00000000ull + (uint64_t)c2);
+            z.x = mu.x + 0.3f * z.x;
+            z.y = mu.y + 0.3f * z.y;
+        }
+        out[i] = z;
+    }
+}
+
+void launch_synth(float* out, int64_t n, int d, uint64_t seed, int64_t row0, int dist, cudaStream_t s) {
+    const int64_t n_pairs = n * (d / 2);
+    if (n_pairs <= 0) return;
+    int64_t blocks = (n_pairs + 255) / 256;
+    if (blocks > 148 * 32) blocks = 148 * 32;
+    synth_kernel<<<(int)blocks, 256, 0, s>>>(reinterpret_cast<float2*>(out), n_pairs, d / 2, seed, row0, dist);
+}
+
+}  // namespace hac

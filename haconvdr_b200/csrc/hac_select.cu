@@ -1,0 +1,319 @@
+// Selection side of the search: per-query shortlist refresh (k-th best screen score -> new
+// emission threshold), exact fp32 rescore of the shortlist, final top-k, cross-shard merge.
+// The full score matrix never exists: these kernels only ever see the few hundred candidates
+// per query that passed the fused filter of the scan kernels.
+#include <float.h>
+
+#include <algorithm>
+
+#include "hac_common.cuh"
+#include "hac_kernels.cuh"
+
+namespace hac {
+
+// ---------------------------------------------------------------------------------------------
+// shared-memory bitonic sort, descending, P a power of two
+template <typename K>
+__device__ __forceinline__ void bitonic_sort_desc(K* a, int P) {
+    for (int size = 2; size <= P; size <<= 1) {
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            __syncthreads();
+            for (int t = threadIdx.x; t < (P >> 1); t += blockDim.x) {
+                const int lo = 2 * t - (t & (stride - 1));
+                const int hi = lo + stride;
+                const bool desc = (lo & size) == 0;
+                const K x = a[lo], y = a[hi];
+                if ((x < y) == desc) {
+                    a[lo] = y;
+                    a[hi] = x;
+                }
+            }
+        }
+    }
+    __syncthreads();
+}
+
+__device__ __forceinline__ int next_pow2(int v) {
+    int p = 2;
+    while (p < v) p <<= 1;
+    return p;
+}
+
+__device__ __forceinline__ uint64_t cand_key(float score, uint32_t row) {
+    return ((uint64_t)float_key(score) << 32) | (uint64_t)(0xFFFFFFFFu - row);
+}
+
+// ---------------------------------------------------------------------------------------------
+__global__ void init_search_kernel(CandBuf cb, float* tau, float* thr, int nq, int nq_pad) {
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q == 0) {
+        *cb.overflow = 0u;
+        *cb.emitted = 0ull;
+    }
+    if (q >= nq_pad) return;
+    cb.count[q] = 0u;
+    cb.sorted[q] = 0u;
+    tau[q] = -INFINITY;
+    thr[q] = q < nq ? -INFINITY : INFINITY;   // padded queries never emit
+}
+
+void launch_init_search(CandBuf cb, float* tau, float* thr, int nq, int nq_pad, cudaStream_t s) {
+    init_search_kernel<<<(nq_pad + 255) / 256, 256, 0, s>>>(cb, tau, thr, nq, nq_pad);
+}
+
+// m_q bounds |screen score - exact fp32 score| for every row of the index:
+//   |sum qhat*xhat - sum q*x| <= ||q - qhat||*||xhat|| + ||q||*||x - xhat||        (Cauchy-Schwarz)
+//   + accumulation slack d * 2^-21 * ||q|| * ||x||  (covers truncating fp32 accumulation in the
+//     tensor core and the rounding of the exact fp32 dot product, each <= d * 2^-23 * ||q||*||x||).
+__global__ void margins_kernel(const float* q_norm, const float* q_err, const OperandStats* corpus, int d,
+                               float* margin, float* margin_max, int nq) {
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= nq) return;
+    float m = 0.f;
+    if (corpus != nullptr) {
+        const float qn = q_norm[q], qe = q_err[q];
+        const float xn = fmaxf(corpus->norm_max, corpus->hat_norm_max);
+        m = qe * corpus->hat_norm_max + qn * corpus->err_norm_max + (float)d * 4.76837158e-7f * (qn + qe) * xn;
+        m *= 1.001f;
+    }
+    margin[q] = m;
+    atomicMax(reinterpret_cast<int*>(margin_max), __float_as_int(m));
+}
+
+void launch_margins(const float* q_norm, const float* q_err, const OperandStats* corpus, int d, float* margin,
+                    float* margin_max, int nq, cudaStream_t s) {
+    cudaMemsetAsync(margin_max, 0, sizeof(float), s);
+    margins_kernel<<<(nq + 127) / 128, 128, 0, s>>>(q_norm, q_err, corpus, d, margin, margin_max, nq);
+}
+
+// ---------------------------------------------------------------------------------------------
+// One CTA per query.  Sorts the shortlist by (screen score desc, row asc); if it holds >= k
+// entries, tau becomes the k-th best screen score seen so far (a valid lower bound on the final
+// k-th best screen score), every true top-k row then has screen score >= tau - 2m, so entries
+// below thr = tau - 2m are dropped and later chunks only emit rows with score >= thr.
+__global__ void __launch_bounds__(512) refresh_kernel(CandBuf cb, int k, const float* __restrict__ margin,
+                                                      float* __restrict__ tau, float* __restrict__ thr) {
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    uint64_t* keys = reinterpret_cast<uint64_t*>(smem_raw);
+    __shared__ int s_keep;
+    const int q = blockIdx.x;
+    const uint32_t raw = cb.count[q];
+    const int cnt = (int)min(raw, cb.cap);
+    if (raw > cb.cap && threadIdx.x == 0) *cb.overflow = 1u;
+    if ((uint32_t)cnt == cb.sorted[q]) return;   // nothing new since the last refresh
+    const int P = next_pow2(cnt);
+    const float* sc = cb.score + (size_t)q * cb.cap;
+    const uint32_t* rw = cb.row + (size_t)q * cb.cap;
+    for (int i = threadIdx.x; i < P; i += blockDim.x) keys[i] = i < cnt ? cand_key(sc[i], rw[i]) : 0ull;
+    bitonic_sort_desc(keys, P);
+    float tau_new = tau[q];
+    if (cnt >= k) tau_new = fmaxf(tau_new, key_float((uint32_t)(keys[k - 1] >> 32)));
+    float thr_new = -INFINITY;
+    if (tau_new > -INFINITY) {
+        thr_new = tau_new - 2.f * margin[q];
+        thr_new -= fabsf(thr_new) * 1e-6f;       // keep the cut conservative under fp32 rounding
+    }
+    if (threadIdx.x == 0) {
+        // entries are sorted: binary search for the first one below thr_new
+        int lo = 0, hi = cnt;
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (key_float((uint32_t)(keys[mid] >> 32)) >= thr_new) lo = mid + 1; else hi = mid;
+        }
+        s_keep = lo;
+    }
+    __syncthreads();
+    const int keep = s_keep;
+    float* sc_w = cb.score + (size_t)q * cb.cap;
+    uint32_t* rw_w = cb.row + (size_t)q * cb.cap;
+    for (int i = threadIdx.x; i < keep; i += blockDim.x) {
+        const uint64_t kk = keys[i];
+        sc_w[i] = key_float((uint32_t)(kk >> 32));
+        rw_w[i] = 0xFFFFFFFFu - (uint32_t)kk;
+    }
+    if (threadIdx.x == 0) {
+        cb.count[q] = (uint32_t)keep;
+        cb.sorted[q] = (uint32_t)keep;
+        tau[q] = tau_new;
+        thr[q] = thr_new;
+    }
+}
+
+void launch_refresh(CandBuf cb, int k, const float* margin, float* tau, float* thr, int nq, cudaStream_t s) {
+    const size_t smem = (size_t)cb.cap * sizeof(uint64_t);
+    static size_t configured = 0;
+    if (smem > 48 * 1024 && smem > configured) {
+        cudaFuncSetAttribute(refresh_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        configured = smem;
+    }
+    refresh_kernel<<<nq, 512, smem, s>>>(cb, k, margin, tau, thr);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Exact fp32 score of every shortlisted (query,row) pair: one warp per pair, the same per-lane
+// FMA order and butterfly as the GEMV scan (hac_common.cuh), so both paths agree bitwise.
+__device__ __forceinline__ const float* seg_row_ptr(const SegTable& segs, uint32_t row, int d) {
+    int s = 0;
+#pragma unroll 1
+    for (int i = 1; i < segs.n; ++i)
+        if (row >= segs.base[i]) s = i;
+    return segs.rows[s] + (size_t)(row - segs.base[s]) * d;
+}
+
+__global__ void __launch_bounds__(256) rescore_kernel(CandBuf cb, const float* __restrict__ qmat, int d,
+                                                      SegTable segs, float* __restrict__ screen_err_max,
+                                                      unsigned long long* __restrict__ rescored) {
+    const int q = blockIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
+    const int cnt = (int)min(cb.count[q], cb.cap);
+    const int d4 = d >> 2;
+    const float4* qrow = reinterpret_cast<const float4*>(qmat + (size_t)q * d);
+    float worst = 0.f;
+    for (int slot = warp; slot < cnt; slot += n_warps) {
+        const uint32_t row = cb.row[(size_t)q * cb.cap + slot];
+        const float4* xrow = reinterpret_cast<const float4*>(seg_row_ptr(segs, row, d));
+        float acc = 0.f;
+        for (int i = lane; i < d4; i += 32) acc = lane_fma4(acc, __ldg(qrow + i), __ldg(xrow + i));
+        acc = warp_sum(acc);
+        if (lane == 0) {
+            cb.exact[(size_t)q * cb.cap + slot] = acc;
+            worst = fmaxf(worst, fabsf(acc - cb.score[(size_t)q * cb.cap + slot]));
+        }
+    }
+    if (lane == 0) {
+        if (worst > 0.f) atomicMax(reinterpret_cast<int*>(screen_err_max), __float_as_int(worst));
+        if (warp == 0) atomicAdd(rescored, (unsigned long long)cnt);
+    }
+}
+
+void launch_rescore(CandBuf cb, const float* q, int d, SegTable segs, int nq, float* screen_err_max,
+                    unsigned long long* rescored, cudaStream_t s) {
+    cudaMemsetAsync(screen_err_max, 0, sizeof(float), s);
+    cudaMemsetAsync(rescored, 0, sizeof(unsigned long long), s);
+    rescore_kernel<<<nq, 256, 0, s>>>(cb, q, d, segs, screen_err_max, rescored);
+}
+
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(512) final_select_kernel(CandBuf cb, int k, const int64_t* __restrict__ id_table,
+                                                           int64_t id_base, float* __restrict__ D,
+                                                           int64_t* __restrict__ I) {
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    uint64_t* keys = reinterpret_cast<uint64_t*>(smem_raw);
+    const int q = blockIdx.x;
+    const int cnt = (int)min(cb.count[q], cb.cap);
+    const int P = next_pow2(cnt);
+    const float* ex = cb.exact + (size_t)q * cb.cap;
+    const uint32_t* rw = cb.row + (size_t)q * cb.cap;
+    for (int i = threadIdx.x; i < P; i += blockDim.x) keys[i] = i < cnt ? cand_key(ex[i], rw[i]) : 0ull;
+    bitonic_sort_desc(keys, P);
+    for (int j = threadIdx.x; j < k; j += blockDim.x) {
+        float score = -FLT_MAX;
+        int64_t id = -1;
+        if (j < cnt) {
+            const uint64_t kk = keys[j];
+            const uint32_t row = 0xFFFFFFFFu - (uint32_t)kk;
+            score = key_float((uint32_t)(kk >> 32));
+            id = id_table != nullptr ? id_table[row] : id_base + (int64_t)row;
+        }
+        D[(size_t)q * k + j] = score;
+        I[(size_t)q * k + j] = id;
+    }
+}
+
+void launch_final_select(CandBuf cb, int k, int nq, const int64_t* id_table, int64_t id_base, float* D,
+                         int64_t* I, cudaStream_t s) {
+    const size_t smem = (size_t)cb.cap * sizeof(uint64_t);
+    static size_t configured = 0;
+    if (smem > 48 * 1024 && smem > configured) {
+        cudaFuncSetAttribute(final_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        configured = smem;
+    }
+    final_select_kernel<<<nq, 512, smem, s>>>(cb, k, id_table, id_base, D, I);
+}
+
+__global__ void fill_empty_kernel(float* D, int64_t* I, int64_t n) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        D[i] = -FLT_MAX;
+        I[i] = -1;
+    }
+}
+void launch_fill_empty(float* D, int64_t* I, int64_t n, cudaStream_t s) {
+    if (n <= 0) return;
+    fill_empty_kernel<<<(int)std::min<int64_t>((n + 255) / 256, 1184), 256, 0, s>>>(D, I, n);
+}
+
+// ---------------------------------------------------------------------------------------------
+// k-way merge of n_lists sorted lists per query (shards or corpus blocks) on the device.
+struct MergeItem {
+    uint32_t key;
+    uint32_t pad;
+    uint64_t id;   // int64 id viewed unsigned: fillers (-1) sort last among equal scores
+    __device__ bool operator<(const MergeItem& o) const {   // "ranks after"
+        return key < o.key || (key == o.key && id > o.id);
+    }
+};
+
+__global__ void __launch_bounds__(512) merge_topk_kernel(int n_lists, int64_t nq, int k,
+                                                         const float* __restrict__ D_lists,
+                                                         const int64_t* __restrict__ I_lists, int k_out,
+                                                         float* __restrict__ D_out, int64_t* __restrict__ I_out) {
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    MergeItem* items = reinterpret_cast<MergeItem*>(smem_raw);
+    const int64_t q = blockIdx.x;
+    const int total = n_lists * k;
+    const int P = next_pow2(total);
+    for (int i = threadIdx.x; i < P; i += blockDim.x) {
+        MergeItem it;
+        it.key = 0u;
+        it.pad = 0u;
+        it.id = ~0ull;
+        if (i < total) {
+            const int l = i / k, j = i - l * k;
+            const size_t src = ((size_t)l * nq + q) * k + j;
+            it.key = float_key(D_lists[src]);
+            it.id = (uint64_t)I_lists[src];
+        }
+        items[i] = it;
+    }
+    bitonic_sort_desc(items, P);
+    for (int j = threadIdx.x; j < k_out; j += blockDim.x) {
+        float score = -FLT_MAX;
+        int64_t id = -1;
+        if (j < total) {
+            score = key_float(items[j].key);
+            id = (int64_t)items[j].id;
+            if (id < 0) score = -FLT_MAX;
+        }
+        D_out[q * k_out + j] = score;
+        I_out[q * k_out + j] = id;
+    }
+}
+
+cudaError_t launch_merge_topk(int n_lists, int64_t nq, int k, const float* D_lists, const int64_t* I_lists,
+                              int k_out, float* D_out, int64_t* I_out, cudaStream_t s) {
+    int P = 2;
+    while (P < n_lists * k) P <<= 1;
+    const size_t smem = (size_t)P * sizeof(MergeItem);
+    if (smem > 200 * 1024) return cudaErrorInvalidValue;
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(merge_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+    }
+    merge_topk_kernel<<<(unsigned)nq, 512, smem, s>>>(n_lists, nq, k, D_lists, I_lists, k_out, D_out, I_out);
+    return cudaGetLastError();
+}
+
+__global__ void gather_ids_kernel(const int64_t* __restrict__ table, int64_t table_n,
+                                  const int64_t* __restrict__ ids, int64_t n, int64_t* __restrict__ out) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t v = ids[i];
+        out[i] = (v >= 0 && v < table_n) ? table[v] : -1;
+    }
+}
+void launch_gather_ids(const int64_t* table, int64_t table_n, const int64_t* ids, int64_t n, int64_t* out,
+                       cudaStream_t s) {
+    if (n <= 0) return;
+    gather_ids_kernel<<<(int)std::min<int64_t>((n + 255) / 256, 1184), 256, 0, s>>>(table, table_n, ids, n, out);
+}
+
+}  // namespace hac

@@ -1,0 +1,154 @@
+"""``FlatIPIndex`` - the reference-facing shim over the C-ABI CUDA library.
+
+Mirrors the part of ``faiss.IndexFlatIP`` / ``GpuIndexFlatIP`` the reference relies on
+(`/root/reference/src/test_HAConvDR_topiocqa.py:52` ctor, `:98` ``add``, `:102`
+``search(q, k) -> (D, I)``, `:122` ``reset``; attributes ``d`` and ``ntotal``):
+
+* ``add`` copies the rows (caller may free its array afterwards, `:123-124`), ids are
+  insertion order;
+* ``search`` returns ``D`` float32 ``[nq, k]`` sorted descending and ``I`` int64 ``[nq, k]``;
+  unfilled slots are ``-3.4028235e38`` / ``-1``; ties are ordered by ascending id;
+* dimension mismatches raise ``AssertionError`` like the faiss Python wrapper
+  (``assert d == self.d``), a k outside ``[1, HAC_MAX_K]`` raises ``ValueError``.
+
+NumPy in -> NumPy out (host buffers, copies inside the call); CUDA torch tensors in ->
+CUDA torch tensors out (``data_ptr()`` handoff on the current stream, no host round trip).
+PyTorch is optional and only used for that tensor handoff.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import numpy as np
+
+from . import _lib
+from ._lib import HAC_MAX_K, HAC_PATH_AUTO, HacStats, check
+
+
+def _is_torch_tensor(x) -> bool:
+    return type(x).__module__.startswith("torch") and hasattr(x, "data_ptr")
+
+
+class FlatIPIndex:
+    def __init__(self, d: int = 768, device: int = 0, reserve: int = 0):
+        self._h = ctypes.c_void_p()
+        self._lib = _lib.lib()
+        check(self._lib.hac_create(int(d), int(device), ctypes.byref(self._h)), "hac_create")
+        self.d = int(d)
+        self.device = int(device)
+        self.is_trained = True
+        if reserve:
+            self.reserve(reserve)
+
+    # -- lifetime -----------------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self._lib.hac_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def ntotal(self) -> int:
+        return int(self._lib.hac_ntotal(self._h))
+
+    def reserve(self, n_rows: int):
+        check(self._lib.hac_reserve(self._h, int(n_rows)), "hac_reserve")
+
+    # -- add / reset --------------------------------------------------------------------------
+    def add(self, x):
+        if _is_torch_tensor(x) and x.is_cuda:
+            import torch
+            assert x.dim() == 2 and x.shape[1] == self.d, "add: expected [n, %d]" % self.d
+            if x.device.index != self.device:
+                raise ValueError("add: tensor lives on cuda:%s, index on cuda:%d" % (x.device.index, self.device))
+            x = x.contiguous().float()
+            stream = torch.cuda.current_stream(x.device).cuda_stream
+            check(self._lib.hac_add_device(self._h, x.shape[0], x.data_ptr(), stream), "hac_add_device")
+            return
+        if _is_torch_tensor(x):
+            x = x.detach().cpu().numpy()
+        x = np.ascontiguousarray(x, dtype=np.float32)
+        assert x.ndim == 2 and x.shape[1] == self.d, "add: expected [n, %d] float32" % self.d
+        check(self._lib.hac_add(self._h, x.shape[0], x.ctypes.data), "hac_add")
+
+    def add_synthetic(self, n: int, seed: int = 42, row0: int = 0, dist: int = 0):
+        """Append ``n`` device-generated rows; row ``row0 + i`` depends only on (seed, row0 + i)."""
+        check(self._lib.hac_add_synthetic(self._h, int(n), int(seed), int(row0), int(dist)), "hac_add_synthetic")
+
+    def reset(self):
+        check(self._lib.hac_reset(self._h), "hac_reset")
+
+    # -- id translation (replaces passage_embedding2id[I], reference :110) ---------------------------
+    def set_id_base(self, base: int):
+        check(self._lib.hac_set_id_base(self._h, int(base)), "hac_set_id_base")
+
+    def set_id_table(self, ids):
+        if ids is None:
+            check(self._lib.hac_set_id_table(self._h, None, 0), "hac_set_id_table")
+            return
+        ids = np.ascontiguousarray(ids, dtype=np.int64)
+        check(self._lib.hac_set_id_table(self._h, ids.ctypes.data, ids.shape[0]), "hac_set_id_table")
+
+    # -- search -------------------------------------------------------------------------------
+    def search(self, q, k: int, path: int = HAC_PATH_AUTO):
+        k = int(k)
+        if k <= 0 or k > HAC_MAX_K:
+            raise ValueError("search: k=%d outside [1, %d]" % (k, HAC_MAX_K))
+        if _is_torch_tensor(q) and q.is_cuda:
+            import torch
+            assert q.dim() == 2 and q.shape[1] == self.d, "search: expected [nq, %d]" % self.d
+            if q.device.index != self.device:
+                raise ValueError("search: tensor lives on cuda:%s, index on cuda:%d" % (q.device.index, self.device))
+            q = q.contiguous().float()
+            D = torch.empty((q.shape[0], k), dtype=torch.float32, device=q.device)
+            I = torch.empty((q.shape[0], k), dtype=torch.int64, device=q.device)
+            stream = torch.cuda.current_stream(q.device).cuda_stream
+            check(self._lib.hac_search_device_ex(self._h, q.shape[0], q.data_ptr(), k, D.data_ptr(), I.data_ptr(),
+                                                 stream, int(path)), "hac_search_device")
+            return D, I
+        if _is_torch_tensor(q):
+            q = q.detach().cpu().numpy()
+        q = np.ascontiguousarray(q, dtype=np.float32)
+        assert q.ndim == 2 and q.shape[1] == self.d, "search: expected [nq, %d] float32" % self.d
+        D = np.empty((q.shape[0], k), dtype=np.float32)
+        I = np.empty((q.shape[0], k), dtype=np.int64)
+        check(self._lib.hac_search_ex(self._h, q.shape[0], q.ctypes.data, k, D.ctypes.data, I.ctypes.data,
+                                      int(path)), "hac_search")
+        return D, I
+
+    def stats(self) -> dict:
+        st = HacStats()
+        check(self._lib.hac_get_stats(self._h, ctypes.byref(st)), "hac_get_stats")
+        return st.as_dict()
+
+
+def merge_topk_device(D_lists, I_lists, k_out: int):
+    """k-way merge on the device: ``D_lists`` float32 / ``I_lists`` int64 CUDA tensors of shape
+    ``[n_lists, nq, k]`` -> ``(D [nq, k_out], I [nq, k_out])`` by (score desc, id asc)."""
+    import torch
+    assert D_lists.is_cuda and I_lists.is_cuda and D_lists.shape == I_lists.shape and D_lists.dim() == 3
+    D_lists = D_lists.contiguous().float()
+    I_lists = I_lists.contiguous().long()
+    n_lists, nq, k = D_lists.shape
+    D = torch.empty((nq, k_out), dtype=torch.float32, device=D_lists.device)
+    I = torch.empty((nq, k_out), dtype=torch.int64, device=D_lists.device)
+    stream = torch.cuda.current_stream(D_lists.device).cuda_stream
+    check(_lib.lib().hac_merge_topk_device(D_lists.device.index, n_lists, nq, k, D_lists.data_ptr(),
+                                           I_lists.data_ptr(), int(k_out), D.data_ptr(), I.data_ptr(), stream),
+          "hac_merge_topk_device")
+    return D, I
+
+
+def synth_rows_device(n: int, d: int, seed: int, row0: int = 0, dist: int = 0, device: int = 0):
+    """Rows of the device generator as a CUDA tensor (queries, and read-back for parity tests)."""
+    import torch
+    out = torch.empty((n, d), dtype=torch.float32, device="cuda:%d" % device)
+    stream = torch.cuda.current_stream(out.device).cuda_stream
+    check(_lib.lib().hac_synth_fill_device(device, out.data_ptr(), n, d, int(seed), int(row0), int(dist), stream),
+          "hac_synth_fill_device")
+    return out

@@ -1,0 +1,146 @@
+/*
+ * hac_index.h - C ABI of the B200-native exact inner-product (IndexFlatIP) engine.
+ *
+ * Drop-in boundary for the retrieval hot path of fengranMark/HAConvDR.  Every entry
+ * point replaces one call the reference makes into faiss (SWIG Python binding) in
+ *   src/test_HAConvDR_topiocqa.py / src/test_HAConvDR_qrecc.py (identical line numbers)
+ *   src/test_PRJ_topiocqa.py / src/test_PRJ_qrecc.py (same code at :44-171)
+ * Plain pointers and sizes only; no torch / numpy types.  One handle owns one
+ * device shard (one process per GPU, or one handle per device inside a process).
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative HAC_E_* code on failure;
+ *     hac_last_error() returns the message of the calling thread's last failure.
+ *   - a handle is not re-entrant; different handles may be used from different threads.
+ *   - "host" pointers are ordinary or pinned host memory, "dev" pointers are device
+ *     memory on the handle's device; `stream` is a cudaStream_t passed as void*
+ *     (NULL = the handle's own stream).
+ *   - result order is the deterministic total order (score desc, id asc); unfilled
+ *     slots (k > ntotal) carry score -FLT_MAX and id -1, as faiss does.
+ */
+#ifndef HAC_INDEX_H_
+#define HAC_INDEX_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HAC_ABI_VERSION 1
+
+#define HAC_OK 0
+#define HAC_E_INVALID (-1)   /* bad argument (dimension mismatch, k out of range, null pointer) */
+#define HAC_E_CUDA (-2)      /* CUDA runtime error (message holds cudaGetErrorString) */
+#define HAC_E_NOMEM (-3)     /* device or pinned-host allocation failed */
+#define HAC_E_OVERFLOW (-4)  /* candidate shortlist overflowed in every retry mode */
+#define HAC_E_STATE (-5)     /* call not valid in the current state */
+
+#define HAC_MAX_K 1024       /* faiss-gpu caps k at 2048; BASELINE's sweep tops out at 1000 */
+
+/* scan paths (hac_search*_ex `path` argument / hac_stats.path) */
+#define HAC_PATH_AUTO 0
+#define HAC_PATH_GEMV 1      /* exact fp32 HBM-streaming scan, small query batches */
+#define HAC_PATH_MMA 2       /* tcgen05 f16 screen + exact fp32 rescore of the shortlist */
+
+typedef struct hac_index hac_index;
+
+typedef struct hac_stats {
+    int32_t path;                 /* HAC_PATH_* actually used by the last search */
+    int32_t retries;              /* shortlist-overflow retries taken by the last search */
+    int32_t n_chunks;             /* corpus chunks (threshold refresh points) of the last search */
+    int32_t kernel_launches;      /* kernels launched by the last search */
+    int64_t candidates_emitted;   /* (query,row) pairs that passed the fused filter */
+    int64_t candidates_rescored;  /* pairs whose exact fp32 score was recomputed */
+    float   margin_max;           /* largest per-query screen margin m_q (score units) */
+    float   screen_err_max;       /* largest |screen score - exact score| seen among rescored pairs */
+    float   scan_ms;              /* device time of the scan kernels of the last search (CUDA events) */
+    float   total_ms;             /* device time of the whole last search (CUDA events) */
+    int64_t ntotal;
+    int64_t bytes_fp32;           /* HBM held by the fp32 rows */
+    int64_t bytes_shadow;         /* HBM held by the f16 tiled shadow */
+} hac_stats;
+
+/* ---- lifetime ------------------------------------------------------------------------------
+ * hac_create  <- faiss.IndexFlatIP(768) + StandardGpuResources()/index_cpu_to_gpu_multiple
+ *                (src/test_HAConvDR_topiocqa.py:46-66).  d must be a multiple of 64, <= 1024.
+ * hac_destroy <- Python GC of the faiss index object. */
+int hac_create(int d, int device, hac_index** out);
+int hac_destroy(hac_index* idx);
+
+/* Optional: pre-size the shard so later adds do not allocate (HBM-resident corpus). */
+int hac_reserve(hac_index* idx, int64_t n_rows);
+
+/* ---- add / reset ---------------------------------------------------------------------------
+ * hac_add        <- index.add(passage_embedding) (src/test_HAConvDR_topiocqa.py:98):
+ *                   copies n rows of d fp32 from host memory; ids are insertion order.
+ * hac_add_device <- same, rows already on the device (loader / synthetic generator).
+ * hac_reset      <- index.reset() (src/test_HAConvDR_topiocqa.py:122): ntotal -> 0,
+ *                   capacity is kept for the next block. */
+int hac_add(hac_index* idx, int64_t n, const float* x_host);
+int hac_add_device(hac_index* idx, int64_t n, const float* x_dev, void* stream);
+int hac_reset(hac_index* idx);
+
+/* Synthetic corpus rows generated on the device: row r (global index row0 + i) is a pure
+ * function of (seed, r), so a shard is reproducible for any shard count.
+ * dist 0: i.i.d. N(0,1); dist 1: shared mean + 0.3*N(0,1) ("anisotropic", ANCE-like). */
+int hac_add_synthetic(hac_index* idx, int64_t n, uint64_t seed, int64_t row0, int dist);
+/* Same generator into caller memory (device pointer), for queries and for test read-back. */
+int hac_synth_fill_device(int device, float* out_dev, int64_t n, int d, uint64_t seed,
+                          int64_t row0, int dist, void* stream);
+
+/* ---- id translation ------------------------------------------------------------------------
+ * Returned ids are  id_base + local_row  unless an id table is set, in which case they are
+ * id_table[local_row].  Replaces  passage_embedding2id[I]  (src/test_HAConvDR_topiocqa.py:110)
+ * and the shard-base translation faiss IndexShards does on the host.
+ * The table is copied to the device; n must equal the rows it will cover. */
+int hac_set_id_base(hac_index* idx, int64_t id_base);
+int hac_set_id_table(hac_index* idx, const int64_t* ids_host, int64_t n);
+
+/* ---- search --------------------------------------------------------------------------------
+ * hac_search        <- D, I = index.search(query_embeddings, topN)
+ *                      (src/test_HAConvDR_topiocqa.py:102): host fp32 queries [nq,d] in,
+ *                      host D fp32 [nq,k] and I int64 [nq,k] out.
+ * hac_search_device <- same with device buffers (torch tensor handoff via data_ptr()).
+ * *_ex variants force a scan path (HAC_PATH_*); the plain ones pick by batch size. */
+int hac_search(hac_index* idx, int64_t nq, const float* q_host, int k, float* D_host, int64_t* I_host);
+int hac_search_device(hac_index* idx, int64_t nq, const float* q_dev, int k, float* D_dev,
+                      int64_t* I_dev, void* stream);
+int hac_search_ex(hac_index* idx, int64_t nq, const float* q_host, int k, float* D_host,
+                  int64_t* I_host, int path);
+int hac_search_device_ex(hac_index* idx, int64_t nq, const float* q_dev, int k, float* D_dev,
+                         int64_t* I_dev, void* stream, int path);
+
+/* ---- cross-shard / cross-block merge ----------------------------------------------------------
+ * Merges `n_lists` sorted top-k lists per query (laid out [n_lists][nq][k], device memory)
+ * into one top-k_out list per query by (score desc, id asc); earlier lists win exact ties on
+ * equal ids only through the id order.  Replaces faiss IndexShards' host merge and the
+ * reference's pure-Python pairwise merge (src/test_HAConvDR_topiocqa.py:126-149). */
+int hac_merge_topk_device(int device, int n_lists, int64_t nq, int k, const float* D_lists_dev,
+                          const int64_t* I_lists_dev, int k_out, float* D_out_dev,
+                          int64_t* I_out_dev, void* stream);
+
+/* offset -> pid gather on the device (src/test_HAConvDR_topiocqa.py:250): out[i] =
+ * table[ids[i]] for ids >= 0, -1 otherwise.  table/ids/out are device pointers. */
+int hac_gather_ids_device(int device, const int64_t* table_dev, int64_t table_n, const int64_t* ids_dev,
+                          int64_t n, int64_t* out_dev, void* stream);
+
+/* ---- pinned staging (loader) -----------------------------------------------------------------
+ * Page-locked host buffers the block-pickle loader reads file payloads into, so that
+ * hac_add runs H2D at full PCIe rate without an extra host copy. */
+int hac_pinned_alloc(size_t bytes, void** out_host);
+int hac_pinned_free(void* host);
+
+/* ---- introspection --------------------------------------------------------------------------- */
+int64_t hac_ntotal(const hac_index* idx);
+int hac_dim(const hac_index* idx);
+int hac_device(const hac_index* idx);
+int hac_get_stats(const hac_index* idx, hac_stats* out);
+int hac_abi_version(void);
+const char* hac_last_error(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HAC_INDEX_H_ */
