@@ -603,6 +603,7 @@ int hac_reset(hac_index* idx) {
         idx->id_table = nullptr;
         idx->id_table_n = 0;
     }
+    idx->id_base = 0;
     idx->ntotal = 0;
     CU(cudaStreamSynchronize(idx->stream));
     return HAC_OK;

@@ -1,0 +1,108 @@
+"""Corpus sharding across GPUs, one process per GPU (``torch.distributed``).
+
+The reference shards its index with faiss ``IndexShards`` (``co.shard = True``,
+`/root/reference/src/test_HAConvDR_topiocqa.py:55-66`): contiguous row ranges per device, a
+host-side merge of the per-shard top-k lists.  Here rank ``r`` of ``G`` owns global rows
+``[r*N/G, (r+1)*N/G)`` (ids = global offsets through ``set_id_base``), queries are replicated,
+and one search is: local exact top-k on every rank -> ONE all-gather of the ``Q x k``
+(score, id) candidates over NCCL/NVLink -> k-way merge kernel on the device.  The corpus rows
+never cross a link.
+
+The local index and the merge are injected so the partitioning / gather / ordering logic can be
+exercised under ``gloo`` on CPU with the oracle standing in (tests only); the defaults are the
+CUDA engine and the device merge kernel - there is no CPU path in the product.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+
+def shard_bounds(n_rows: int, world_size: int):
+    """Contiguous partition of ``n_rows`` global rows: bounds[r] .. bounds[r+1] belongs to rank r."""
+    return [(r * n_rows) // world_size for r in range(world_size + 1)]
+
+
+class ShardedFlatIPIndex:
+    def __init__(self, d: int, local_index=None, device=None, group=None, merge=None):
+        import torch
+        import torch.distributed as dist
+        self._torch, self._dist = torch, dist
+        self.d = int(d)
+        self.group = group
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.world_size = dist.get_world_size(group) if dist.is_initialized() else 1
+        if local_index is None:
+            from .index import FlatIPIndex
+            local_index = FlatIPIndex(self.d, device if device is not None else torch.cuda.current_device())
+        self.local = local_index
+        if merge is None:
+            from .index import merge_topk_device
+            merge = merge_topk_device
+        self._merge = merge
+        self.ntotal = 0            # global rows
+        self._lo = 0               # global offset of the next add's first row
+        self._bases = []           # (local_row_start, global_row_start, n) per add
+
+    # -- building the shard ---------------------------------------------------------------------
+    def _after_add(self, lo_global: int, n_local: int):
+        start_local = sum(b[2] for b in self._bases)
+        self._bases.append((start_local, lo_global, n_local))
+        if len(self._bases) == 1:
+            self.local.set_id_base(lo_global)
+        else:                                   # several adds: ids are no longer base + row
+            table = np.concatenate([np.arange(g, g + n, dtype=np.int64) for _, g, n in self._bases])
+            self.local.set_id_table(table)
+
+    def add(self, x):
+        """Every rank passes the same global block (as the reference's single process does);
+        each keeps its contiguous slice."""
+        n = int(x.shape[0])
+        b = shard_bounds(n, self.world_size)
+        lo, hi = b[self.rank], b[self.rank + 1]
+        if hi > lo:
+            self.local.add(x[lo:hi])
+            self._after_add(self._lo + lo, hi - lo)
+        self._lo += n
+        self.ntotal += n
+
+    def add_synthetic(self, n_global: int, seed: int = 42, dist_kind: int = 0):
+        b = shard_bounds(n_global, self.world_size)
+        lo, hi = b[self.rank], b[self.rank + 1]
+        if hasattr(self.local, "reserve"):
+            self.local.reserve(hi - lo)
+        self.local.add_synthetic(hi - lo, seed=seed, row0=self._lo + lo, dist=dist_kind)
+        self._after_add(self._lo + lo, hi - lo)
+        self._lo += n_global
+        self.ntotal += n_global
+
+    def reset(self):
+        self.local.reset()
+        self.ntotal, self._lo, self._bases = 0, 0, []
+
+    # -- search ---------------------------------------------------------------------------------
+    def search(self, q, k: int):
+        """``q``: the same queries on every rank (numpy -> numpy results, CUDA tensor -> CUDA tensors).
+        Returns the merged global (D [Q,k], I [Q,k]) on every rank."""
+        torch, dist = self._torch, self._dist
+        as_numpy = not (hasattr(q, "is_cuda") and q.is_cuda)
+        if as_numpy and self._on_gpu():
+            q = torch.from_numpy(np.ascontiguousarray(q, dtype=np.float32)).pin_memory().to(
+                self._device(), non_blocking=True)
+        D, I = self.local.search(q, k)
+        if self.world_size > 1:
+            if not torch.is_tensor(D):
+                D, I = torch.from_numpy(np.ascontiguousarray(D)), torch.from_numpy(np.ascontiguousarray(I))
+            Dg = torch.empty((self.world_size,) + tuple(D.shape), dtype=D.dtype, device=D.device)
+            Ig = torch.empty((self.world_size,) + tuple(I.shape), dtype=I.dtype, device=I.device)
+            dist.all_gather_into_tensor(Dg, D.contiguous(), group=self.group)
+            dist.all_gather_into_tensor(Ig, I.contiguous(), group=self.group)
+            D, I = self._merge(Dg, Ig, k)
+        if as_numpy and torch.is_tensor(D):
+            return D.cpu().numpy(), I.cpu().numpy()
+        return D, I
+
+    def _on_gpu(self) -> bool:
+        return hasattr(self.local, "device") and hasattr(self.local, "_h")
+
+    def _device(self):
+        return self._torch.device("cuda", self.local.device)

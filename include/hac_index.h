@@ -76,8 +76,8 @@ int hac_reserve(hac_index* idx, int64_t n_rows);
  * hac_add        <- index.add(passage_embedding) (src/test_HAConvDR_topiocqa.py:98):
  *                   copies n rows of d fp32 from host memory; ids are insertion order.
  * hac_add_device <- same, rows already on the device (loader / synthetic generator).
- * hac_reset      <- index.reset() (src/test_HAConvDR_topiocqa.py:122): ntotal -> 0,
- *                   capacity is kept for the next block. */
+ * hac_reset      <- index.reset() (src/test_HAConvDR_topiocqa.py:122): ntotal -> 0, id base and
+ *                   id table cleared, capacity is kept for the next block. */
 int hac_add(hac_index* idx, int64_t n, const float* x_host);
 int hac_add_device(hac_index* idx, int64_t n, const float* x_dev, void* stream);
 int hac_reset(hac_index* idx);

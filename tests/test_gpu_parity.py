@@ -29,12 +29,15 @@ def _scores_of(q, x):
 
 def _check(q, x, k, D, I, also_fp32_oracle=True):
     D64, I64 = brute_force_fp64(q, x, k)
-    rep = assert_parity(D64, I64, D, I, rtol=RTOL, ref_scores_of=_scores_of(q, x))
+    # when (nearly) the whole corpus is returned the tail scores pass through zero, where a relative
+    # bound is meaningless: allow 1e-5 of the score scale there (never the case at BASELINE sizes)
+    atol = RTOL * float(np.abs(D64[I64 >= 0]).max()) if 4 * k >= x.shape[0] else 0.0
+    rep = assert_parity(D64, I64, D, I, rtol=RTOL, ref_scores_of=_scores_of(q, x), atol=atol)
     if also_fp32_oracle:
         ref = FlatIP(x.shape[1])
         ref.add(x)
         Dr, Ir = ref.search(q, k)
-        assert_parity(Dr, Ir, D, I, rtol=RTOL, ref_scores_of=_scores_of(q, x))
+        assert_parity(Dr, Ir, D, I, rtol=RTOL, ref_scores_of=_scores_of(q, x), atol=atol)
     assert np.all(np.diff(D, axis=1) <= 0)
     return rep
 
@@ -66,7 +69,8 @@ def test_golden_fixtures_through_reference_loop(name):
         if "short" in name:
             # unfilled slots and the emb2id[-1] wrap must match exactly where the reference is deterministic
             assert np.array_equal(I, g["I"])
-            np.testing.assert_allclose(D, g["D"], rtol=RTOL)
+            # (k > rows and d = 64: scores pass through zero, hence the absolute term 1e-5 * max|score|)
+            np.testing.assert_allclose(D, g["D"], rtol=RTOL, atol=RTOL * float(np.abs(g["D"][g["D"] > -1e30]).max()))
         else:
             off = g["id_start"]
             assert_parity(g["D"][:, :valid_cols], g["I"][:, :valid_cols] - off, D[:, :valid_cols],
