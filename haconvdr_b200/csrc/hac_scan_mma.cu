@@ -26,6 +26,7 @@ constexpr int kABytes = kPieceBytes;                       // 16 KiB
 constexpr int kBBytes = 2 * kPieceBytes;                   // 32 KiB
 constexpr int kStageBytes = kABytes + kBBytes;             // 48 KiB
 constexpr int kThreads = 192;
+constexpr int kStash = 8;                                  // per-thread survivors kept until the TMEM buffer is released
 constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
 
 struct Barriers {
@@ -50,16 +51,6 @@ __device__ __forceinline__ void wait_or_trap(uint64_t* bar, uint32_t parity) {
         if (done) return;
     }
     __trap();
-}
-
-__device__ __forceinline__ void emit(const CandBuf& cb, int q, uint32_t row, float score) {
-    const uint32_t pos = atomicAdd(cb.count + q, 1u);
-    if (pos < cb.cap) {
-        cb.score[(size_t)q * cb.cap + pos] = score;
-        cb.row[(size_t)q * cb.cap + pos] = row;
-    } else {
-        *cb.overflow = 1u;
-    }
 }
 
 __global__ void __launch_bounds__(kThreads, 1) scan_mma_kernel(const MmaScanArgs a) {
@@ -146,6 +137,11 @@ __global__ void __launch_bounds__(kThreads, 1) scan_mma_kernel(const MmaScanArgs
         const float inv_scale = a.q_stats->inv_scale * a.x_stats->inv_scale;
         unsigned long long emitted = 0;
         uint32_t it = 0;
+        // Survivors are first stashed per thread (local memory) and appended to the shortlist only
+        // AFTER the accumulator buffer has been handed back to the MMA warp, so the round trip of the
+        // global atomic overlaps the next tile's MMAs instead of stalling the TMEM pipeline.
+        float stash_v[kStash];
+        uint32_t stash_r[kStash];
         for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
             const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
             const int64_t ct = a.ct0 + t / a.n_qtiles;
@@ -153,6 +149,7 @@ __global__ void __launch_bounds__(kThreads, 1) scan_mma_kernel(const MmaScanArgs
             const int q = qt * kTileM + quarter * 32 + lane;
             const float thr_s = a.thr[q] * scale;        // threshold in accumulator units (power-of-two scale)
             const int64_t row0 = ct * kTileN;
+            uint32_t stash_n = 0;
             wait_or_trap(&bars->tmem_full[acc], acc_phase);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * kTileN;
@@ -165,20 +162,52 @@ __global__ void __launch_bounds__(kThreads, 1) scan_mma_kernel(const MmaScanArgs
 #pragma unroll
                 for (int j = 0; j < 32; ++j) any |= (__uint_as_float(v[j]) >= thr_s);
                 if (any) {
+                    uint32_t mask = 0;
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        const float sv = __uint_as_float(v[j]);
-                        const int64_t row = row0 + c * 32 + j;
-                        if (sv >= thr_s && row < a.seg_rows) {
-                            emit(a.cb, q, a.row_id_base + (uint32_t)row, sv * inv_scale);
-                            ++emitted;
+                    for (int j = 0; j < 32; ++j) mask |= (__uint_as_float(v[j]) >= thr_s ? 1u : 0u) << j;
+                    const int64_t rem = a.seg_rows - (row0 + c * 32);      // rows past the segment end are padding
+                    if (rem < 32) mask &= rem <= 0 ? 0u : ((1u << rem) - 1u);
+                    const uint32_t n = __popc(mask);
+                    const uint32_t row_id = a.row_id_base + (uint32_t)(row0 + c * 32);
+                    if (n != 0 && stash_n + n <= (uint32_t)kStash) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            if ((mask >> j) & 1u) {
+                                stash_v[stash_n] = __uint_as_float(v[j]) * inv_scale;
+                                stash_r[stash_n] = row_id + j;
+                                ++stash_n;
+                            }
+                        }
+                    } else if (n != 0) {
+                        // loose-threshold phase (first chunks): one atomic per 32-column group
+                        const uint32_t base = atomicAdd(a.cb.count + q, n);
+                        if (base + n > a.cb.cap) *a.cb.overflow = 1u;
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            const uint32_t pos = base + __popc(mask & ((1u << j) - 1u));
+                            if (((mask >> j) & 1u) && pos < a.cb.cap) {
+                                a.cb.score[(size_t)q * a.cb.cap + pos] = __uint_as_float(v[j]) * inv_scale;
+                                a.cb.row[(size_t)q * a.cb.cap + pos] = row_id + j;
+                            }
                         }
                     }
+                    emitted += n;
                 }
                 __syncwarp();
             }
             tc_fence_before();
             mbar_arrive(&bars->tmem_empty[acc]);
+            if (stash_n != 0) {
+                const uint32_t base = atomicAdd(a.cb.count + q, stash_n);
+                if (base + stash_n > a.cb.cap) *a.cb.overflow = 1u;
+                for (uint32_t i = 0; i < stash_n; ++i) {
+                    if (base + i < a.cb.cap) {
+                        a.cb.score[(size_t)q * a.cb.cap + base + i] = stash_v[i];
+                        a.cb.row[(size_t)q * a.cb.cap + base + i] = stash_r[i];
+                    }
+                }
+            }
+            __syncwarp();
         }
         if (emitted) atomicAdd(a.cb.emitted, emitted);
     }

@@ -92,11 +92,12 @@ class ShardedFlatIPIndex:
         if self.world_size > 1:
             if not torch.is_tensor(D):
                 D, I = torch.from_numpy(np.ascontiguousarray(D)), torch.from_numpy(np.ascontiguousarray(I))
-            Dg = torch.empty((self.world_size,) + tuple(D.shape), dtype=D.dtype, device=D.device)
-            Ig = torch.empty((self.world_size,) + tuple(I.shape), dtype=I.dtype, device=I.device)
-            dist.all_gather_into_tensor(Dg, D.contiguous(), group=self.group)
+            nq = D.shape[0]
+            Dg = torch.empty((self.world_size * nq, k), dtype=D.dtype, device=D.device)
+            Ig = torch.empty((self.world_size * nq, k), dtype=I.dtype, device=I.device)
+            dist.all_gather_into_tensor(Dg, D.contiguous(), group=self.group)   # rank-major: [G][Q][k]
             dist.all_gather_into_tensor(Ig, I.contiguous(), group=self.group)
-            D, I = self._merge(Dg, Ig, k)
+            D, I = self._merge(Dg.view(self.world_size, nq, k), Ig.view(self.world_size, nq, k), k)
         if as_numpy and torch.is_tensor(D):
             return D.cpu().numpy(), I.cpu().numpy()
         return D, I

@@ -13,8 +13,10 @@
  *     hac_last_error() returns the message of the calling thread's last failure.
  *   - a handle is not re-entrant; different handles may be used from different threads.
  *   - "host" pointers are ordinary or pinned host memory, "dev" pointers are device
- *     memory on the handle's device; `stream` is a cudaStream_t passed as void*
- *     (NULL = the handle's own stream).
+ *     memory on the handle's device; `stream` is a cudaStream_t passed as void* and is used
+ *     as given (NULL = the CUDA legacy default stream, i.e. torch's default stream): device
+ *     entry points are stream-ordered with the caller's work and return after the stream
+ *     reached the end of the call.  Host entry points run on the handle's own stream.
  *   - result order is the deterministic total order (score desc, id asc); unfilled
  *     slots (k > ntotal) carry score -FLT_MAX and id -1, as faiss does.
  */

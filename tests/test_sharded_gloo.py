@@ -1,0 +1,106 @@
+"""CPU, world_size 2 over gloo: the N>1 host logic of haconvdr_b200.sharded (row partition, id bases,
+all-gather layout, merge order) with the oracle index and a NumPy merge injected in place of the
+CUDA engine.  The CUDA pieces themselves are covered by the -m gpu tests."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+class OracleShard:
+    """oracle FlatIP + the id-translation surface of FlatIPIndex (test stand-in for one GPU shard)."""
+
+    def __init__(self, d):
+        from oracle.flat_ip import FlatIP
+        self._ix, self.d, self._base, self._table = FlatIP(d), d, 0, None
+
+    @property
+    def ntotal(self):
+        return self._ix.ntotal
+
+    def add(self, x):
+        self._ix.add(x)
+
+    def reset(self):
+        self._ix.reset()
+        self._base, self._table = 0, None
+
+    def set_id_base(self, b):
+        self._base = int(b)
+
+    def set_id_table(self, t):
+        self._table = np.asarray(t, np.int64)
+
+    def search(self, q, k):
+        D, I = self._ix.search(np.asarray(q, np.float32), k)
+        valid = I >= 0
+        out = I.copy()
+        out[valid] = self._table[I[valid]] if self._table is not None else I[valid] + self._base
+        return D, out
+
+
+def numpy_merge(Dg, Ig, k):
+    """[G,Q,k] -> [Q,k] by (score desc, id asc), fillers (id -1) last."""
+    D = Dg.numpy().transpose(1, 0, 2).reshape(Dg.shape[1], -1)
+    I = Ig.numpy().transpose(1, 0, 2).reshape(Ig.shape[1], -1)
+    key_i = np.where(I < 0, np.iinfo(np.int64).max, I)
+    order = np.lexsort((key_i, -D.astype(np.float64)), axis=1)[:, :k]
+    return torch.from_numpy(np.take_along_axis(D, order, 1)), torch.from_numpy(np.take_along_axis(I, order, 1))
+
+
+def _worker(rank, world, port, tmp):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from haconvdr_b200.sharded import ShardedFlatIPIndex, shard_bounds
+        from oracle.flat_ip import brute_force_fp64
+        rng = np.random.default_rng(123)                      # same data on every rank
+        blocks = [rng.standard_normal((n, 64)).astype(np.float32) for n in (501, 333)]
+        q = rng.standard_normal((17, 64)).astype(np.float32)
+        x = np.concatenate(blocks, 0)
+        idx = ShardedFlatIPIndex(64, local_index=OracleShard(64), merge=numpy_merge)
+        for b in blocks:
+            idx.add(b)
+        assert idx.ntotal == 834
+        lo0, hi0 = shard_bounds(501, world)[rank], shard_bounds(501, world)[rank + 1]
+        lo1, hi1 = shard_bounds(333, world)[rank], shard_bounds(333, world)[rank + 1]
+        assert idx.local.ntotal == (hi0 - lo0) + (hi1 - lo1)
+        D, I = idx.search(q, 20)
+        D64, I64 = brute_force_fp64(q, x, 20)
+        assert np.array_equal(np.asarray(I), I64), (rank, np.asarray(I)[0], I64[0])
+        np.testing.assert_allclose(np.asarray(D), D64, rtol=1e-5, atol=1e-5)
+        # k larger than a shard and than the corpus: fillers must stay last after the merge
+        idx.reset()
+        idx.add(blocks[0][:5])
+        D, I = idx.search(q, 8)
+        D64, I64 = brute_force_fp64(q, blocks[0][:5], 8)
+        assert np.array_equal(np.asarray(I), I64)
+        np.save(os.path.join(tmp, "ok_%d.npy" % rank), np.asarray([1]))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_index_world_size_2_gloo(tmp_path):
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    assert all(os.path.exists(os.path.join(str(tmp_path), "ok_%d.npy" % r)) for r in range(2))
+
+
+def test_shard_bounds_cover_rows_exactly():
+    from haconvdr_b200.sharded import shard_bounds
+    for n in (0, 1, 7, 25_700_592, 54_573_064):
+        for g in (1, 2, 4, 8):
+            b = shard_bounds(n, g)
+            assert b[0] == 0 and b[-1] == n and all(b[i] <= b[i + 1] for i in range(g))
+            assert max(b[i + 1] - b[i] for i in range(g)) - min(b[i + 1] - b[i] for i in range(g)) <= 1
