@@ -2,6 +2,7 @@
 // chains scan -> refresh -> rescore -> select, and the merge / gather entry points.
 #include <float.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -83,6 +84,8 @@ struct hac_index {
     cudaEvent_t ev[kMaxEvents] = {};
     bool events_ready = false;
     bool mma_configured = false;
+    int mma_cta_group = 1;                  // 2 = CTA-pair variant (measured equal within noise; HAC_MMA_CTA_GROUP / hac_set_option)
+    double chunk_growth = 4.0;              // chunk i+1 = growth * rows seen so far
 };
 
 namespace {
@@ -335,7 +338,7 @@ int search_batch(hac_index* idx, int nq, const float* q_dev, int k, float* D_dev
         // chunk schedule: the first chunk is emitted unfiltered (it must fit the shortlist), later
         // chunks grow geometrically with the rows already seen, so every chunk is expected to add
         // about growth * k * (margin factor) candidates per query.
-        double growth = std::min(4.0, std::max(1.0, (double)cap / (8.0 * k)));
+        double growth = std::min(idx->chunk_growth, std::max(1.0, (double)cap / (8.0 * k)));
         if (level == 1) growth = std::max(0.5, growth / 4.0);
         int64_t rows_done = 0;
         for (size_t si = 0; si < idx->segs.size(); ++si) {
@@ -364,7 +367,7 @@ int search_batch(hac_index* idx, int nq, const float* q_dev, int k, float* D_dev
                     a.seg_rows = seg.n_rows;
                     a.row_id_base = seg.base;
                     a.cb = cb;
-                    CU(launch_scan_mma(a, idx->sm_count, s));
+                    CU(launch_scan_mma(a, idx->sm_count, idx->mma_cta_group, s));
                 } else {
                     launch_scan_gemv(seg.rows, r, r1, d, q_dev, nq, w.thr, cb, seg.base, idx->sm_count, s);
                 }
@@ -454,7 +457,7 @@ int search_common(hac_index* idx, int64_t nq, const float* q, bool q_on_host, in
     float margin_max = 0.f, err_max = 0.f;
     for (int64_t q0 = 0; q0 < nq; q0 += max_batch) {
         const int nb = (int)std::min<int64_t>(max_batch, nq - q0);
-        const int nb_pad = (int)round_up(nb, kTileRows);
+        const int nb_pad = (int)round_up(nb, kTileRows * idx->mma_cta_group);
         int rc = ensure_workspace(idx, nb_pad, cap_for_k(k, 0), (q_on_host || out_on_host) ? (int64_t)nb * k : 0);
         if (rc != HAC_OK) return rc;
         const float* qd = q + (size_t)q0 * idx->d;
@@ -507,6 +510,7 @@ int hac_create(int d, int device, hac_index** out) {
     idx->d = d;
     idx->device = device;
     idx->sm_count = prop.multiProcessorCount;
+    if (const char* cg = getenv("HAC_MMA_CTA_GROUP")) idx->mma_cta_group = atoi(cg) == 2 ? 2 : 1;
     cudaError_t e = cudaStreamCreateWithFlags(&idx->stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaMalloc(&idx->corpus_stats, sizeof(OperandStats));
     if (e == cudaSuccess) e = cudaMalloc(&idx->add_scratch, 4 * sizeof(float));
@@ -686,6 +690,21 @@ int hac_pinned_alloc(size_t bytes, void** out_host) {
 int hac_pinned_free(void* host) {
     if (host) cudaFreeHost(host);
     return HAC_OK;
+}
+
+int hac_set_option(hac_index* idx, const char* name, int64_t value) {
+    if (idx == nullptr || name == nullptr) return fail(HAC_E_INVALID, "set_option: null argument");
+    if (strcmp(name, "mma_cta_group") == 0) {
+        if (value != 1 && value != 2) return fail(HAC_E_INVALID, "mma_cta_group must be 1 or 2");
+        idx->mma_cta_group = (int)value;
+        return HAC_OK;
+    }
+    if (strcmp(name, "chunk_growth_x100") == 0) {
+        if (value < 110 || value > 1600) return fail(HAC_E_INVALID, "chunk_growth_x100 must be in [110, 1600]");
+        idx->chunk_growth = (double)value / 100.0;
+        return HAC_OK;
+    }
+    return fail(HAC_E_INVALID, std::string("set_option: unknown option ") + name);
 }
 
 int64_t hac_ntotal(const hac_index* idx) { return idx ? idx->ntotal : -1; }

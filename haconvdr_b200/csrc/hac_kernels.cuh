@@ -80,7 +80,8 @@ struct MmaScanArgs {
     uint32_t row_id_base;
     CandBuf cb;
 };
-cudaError_t launch_scan_mma(const MmaScanArgs& a, int sm_count, cudaStream_t s);
+// cta_group = 1: one CTA per tile; 2: CTA pairs (cluster of 2) sharing each MMA; needs an even n_qtiles
+cudaError_t launch_scan_mma(const MmaScanArgs& a, int sm_count, int cta_group, cudaStream_t s);
 cudaError_t scan_mma_configure();
 
 // ---- merge / gather ---------------------------------------------------------------------------

@@ -1,14 +1,22 @@
 // Large-batch scan: f16 screen scores on the 5th-gen tensor cores with a fused threshold filter.
 //
-//   D[128 queries x 256 rows] (fp32, TMEM) += Qhat[128 x 64] * Xhat[256 x 64]^T   per K block,
+//   D[queries x 256 rows] (fp32, TMEM) += Qhat[queries x 64] * Xhat[256 x 64]^T   per K block,
 //   12 K blocks for d = 768, operands staged global -> shared by 16 KiB bulk async copies of the
 //   pre-swizzled shadow tiles (hac_common.cuh), tcgen05.mma issued by one thread, accumulators
 //   double-buffered in TMEM (2 x 256 columns), epilogue warps read them back with tcgen05.ld and
 //   compare every score against the owning query's emission threshold - only the (rare) survivors
 //   are appended to the shortlist in HBM, the score tile itself never leaves the SM.
 //
-// Warp roles (192 threads, one persistent CTA per SM): warp 0 = copy producer, warp 1 = MMA issuer
-// (owns the TMEM allocation), warps 2..5 = epilogue (TMEM lane quarter = warp % 4, one query per thread).
+// Two variants of one kernel (template kCG):
+//   kCG = 1  one CTA per SM works alone: tile 128 queries x 256 rows, 4 stages of 48 KiB.
+//   kCG = 2  a CTA pair (cluster of 2, one TPC) shares each MMA (cta_group::2, M = 256): every CTA
+//            stages its own 128 queries and HALF of the 256 corpus rows, so shared-memory fills and
+//            operand reads per FLOP drop by a third; 6 stages of 32 KiB.  The pair's leader issues
+//            the MMAs; the peer forwards "my half has landed" to the leader through a remote
+//            mbarrier arrive; tcgen05.commit multicasts slot-free / accumulator-ready to both CTAs.
+// Warp roles (192 threads, persistent): warp 0 = copy producer, warp 1 = MMA issuer (leader) or
+// forwarder (peer) and owner of the TMEM allocation, warps 2..5 = epilogue (TMEM lane quarter =
+// warp % 4, one query per thread).
 // Tile order: consecutive CTAs take the query tiles of the same 256-row corpus tile, so a corpus
 // tile is pulled from HBM once and re-read from L2 by the other query tiles.
 // Roofline: tensor pipe; algorithmic FLOPs = 2 * queries * rows * d per launch.
@@ -19,21 +27,27 @@ namespace hac {
 
 namespace {
 
-constexpr int kStages = 4;
-constexpr int kTileM = 128;                                // queries per tile (TMEM lanes)
+constexpr int kTileM = 128;                                // queries per CTA tile (TMEM lanes)
 constexpr int kTileN = 256;                                // corpus rows per tile (TMEM columns)
-constexpr int kABytes = kPieceBytes;                       // 16 KiB
-constexpr int kBBytes = 2 * kPieceBytes;                   // 32 KiB
-constexpr int kStageBytes = kABytes + kBBytes;             // 48 KiB
 constexpr int kThreads = 192;
 constexpr int kStash = 8;                                  // per-thread survivors kept until the TMEM buffer is released
-constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int kMaxStages = 6;
+
+template <int kCG>
+struct Cfg {
+    static constexpr int kStages = kCG == 1 ? 4 : 6;
+    static constexpr int kABytes = kPieceBytes;                              // 128 queries x 64 k
+    static constexpr int kBBytes = kCG == 1 ? 2 * kPieceBytes : kPieceBytes; // 256 or 128 rows x 64 k
+    static constexpr int kStageBytes = kABytes + kBBytes;
+    static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+};
 
 struct Barriers {
-    uint64_t full[kStages];
-    uint64_t empty[kStages];
-    uint64_t tmem_full[2];
-    uint64_t tmem_empty[2];
+    uint64_t full[kMaxStages];       // this CTA's operand bytes of the stage have landed
+    uint64_t peer_full[kMaxStages];  // (leader only) the peer CTA's bytes have landed
+    uint64_t empty[kMaxStages];      // the MMAs reading the stage have retired
+    uint64_t tmem_full[2];           // accumulator buffer complete
+    uint64_t tmem_empty[2];          // (leader only when kCG = 2) accumulator buffer drained
     uint32_t tmem_base;
 };
 
@@ -53,30 +67,38 @@ __device__ __forceinline__ void wait_or_trap(uint64_t* bar, uint32_t parity) {
     __trap();
 }
 
+template <int kCG>
 __global__ void __launch_bounds__(kThreads, 1) scan_mma_kernel(const MmaScanArgs a) {
+    using C = Cfg<kCG>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    Barriers* bars = reinterpret_cast<Barriers*>(smem + kStages * kStageBytes);
+    Barriers* bars = reinterpret_cast<Barriers*>(smem + C::kStages * C::kStageBytes);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int kb_count = a.d / kBlockK;
-    const int64_t n_ctiles = a.ct1 - a.ct0;
-    const int64_t n_tiles = n_ctiles * a.n_qtiles;
+    const uint32_t cta_rank = kCG == 2 ? cluster_ctarank() : 0u;
+    const bool leader = cta_rank == 0;
+    // work unit: (corpus tile of 256 rows) x (query tile of 128*kCG queries); one unit per CTA group
+    const int n_qgroups = a.n_qtiles / kCG;
+    const int64_t n_units = (a.ct1 - a.ct0) * n_qgroups;
+    const int64_t unit0 = blockIdx.x / kCG, unit_step = gridDim.x / kCG;
 
+    if constexpr (kCG == 2) cluster_sync_all();          // both CTAs resident before any cross-CTA traffic
     if (threadIdx.x == 0) {
-        for (int i = 0; i < kStages; ++i) {
+        for (int i = 0; i < C::kStages; ++i) {
             mbar_init(&bars->full[i], 1);
+            mbar_init(&bars->peer_full[i], 1);
             mbar_init(&bars->empty[i], 1);
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&bars->tmem_full[i], 1);
-            mbar_init(&bars->tmem_empty[i], 128);
+            mbar_init(&bars->tmem_empty[i], 128 * kCG);
         }
         fence_barrier_init();
     }
-    if (warp == 1) tmem_alloc<1>(&bars->tmem_base, 512);
+    if (warp == 1) tmem_alloc<kCG>(&bars->tmem_base, 512);
     tc_fence_before();
-    __syncthreads();
+    if constexpr (kCG == 2) cluster_sync_all(); else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = bars->tmem_base;
 
@@ -84,49 +106,71 @@ __global__ void __launch_bounds__(kThreads, 1) scan_mma_kernel(const MmaScanArgs
         // ---------------- producer: shadow pieces -> shared memory ----------------
         if (elect_one()) {
             uint32_t stage = 0, phase = 0;
-            for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-                const int64_t ct = a.ct0 + t / a.n_qtiles;
-                const int qt = (int)(t % a.n_qtiles);
+            for (int64_t u = unit0; u < n_units; u += unit_step) {
+                const int64_t ct = a.ct0 + u / n_qgroups;
+                const int qt = (int)(u % n_qgroups) * kCG + (int)cta_rank;
                 const uint8_t* srcA = a.q_shadow + (size_t)qt * kb_count * kPieceBytes;
-                const uint8_t* srcB0 = a.x_shadow + (size_t)(2 * ct) * kb_count * kPieceBytes;
-                const uint8_t* srcB1 = srcB0 + (size_t)kb_count * kPieceBytes;
+                // kCG = 1: both 128-row halves of the corpus tile; kCG = 2: this CTA's half only
+                const uint8_t* srcB = a.x_shadow + (size_t)(2 * ct + (kCG == 2 ? cta_rank : 0)) * kb_count * kPieceBytes;
                 for (int kb = 0; kb < kb_count; ++kb) {
                     wait_or_trap(&bars->empty[stage], phase ^ 1);
-                    uint8_t* sA = smem + stage * kStageBytes;
-                    uint8_t* sB = sA + kABytes;
-                    mbar_arrive_expect_tx(&bars->full[stage], kStageBytes);
+                    uint8_t* sA = smem + stage * C::kStageBytes;
+                    uint8_t* sB = sA + C::kABytes;
+                    mbar_arrive_expect_tx(&bars->full[stage], C::kStageBytes);
                     bulk_g2s(sA, srcA + (size_t)kb * kPieceBytes, kPieceBytes, &bars->full[stage]);
-                    bulk_g2s(sB, srcB0 + (size_t)kb * kPieceBytes, kPieceBytes, &bars->full[stage]);
-                    bulk_g2s(sB + kPieceBytes, srcB1 + (size_t)kb * kPieceBytes, kPieceBytes, &bars->full[stage]);
-                    if (++stage == kStages) { stage = 0; phase ^= 1; }
+                    bulk_g2s(sB, srcB + (size_t)kb * kPieceBytes, kPieceBytes, &bars->full[stage]);
+                    if constexpr (kCG == 1)
+                        bulk_g2s(sB + kPieceBytes, srcB + (size_t)(kb_count + kb) * kPieceBytes, kPieceBytes,
+                                 &bars->full[stage]);
+                    if (++stage == C::kStages) { stage = 0; phase ^= 1; }
                 }
             }
         }
     } else if (warp == 1) {
-        // ---------------- MMA issuer ----------------
-        if (elect_one()) {
-            constexpr uint32_t idesc = umma_idesc_f16(kTileM, kTileN);
-            uint32_t stage = 0, phase = 0;
-            uint32_t it = 0;
-            for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
-                const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
-                wait_or_trap(&bars->tmem_empty[acc], acc_phase ^ 1);
-                tc_fence_after();
-                const uint32_t tmem_d = tmem_base + acc * kTileN;
-                for (int kb = 0; kb < kb_count; ++kb) {
-                    wait_or_trap(&bars->full[stage], phase);
+        if (leader) {
+            // ---------------- MMA issuer ----------------
+            if (elect_one()) {
+                constexpr uint32_t idesc = umma_idesc_f16(kTileM * kCG, kTileN);
+                uint32_t stage = 0, phase = 0, it = 0;
+                for (int64_t u = unit0; u < n_units; u += unit_step, ++it) {
+                    const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
+                    wait_or_trap(&bars->tmem_empty[acc], acc_phase ^ 1);
                     tc_fence_after();
-                    const uint32_t sA = smem_u32(smem + stage * kStageBytes);
-                    const uint64_t descA = umma_desc_k128(sA);
-                    const uint64_t descB = umma_desc_k128(sA + kABytes);
+                    const uint32_t tmem_d = tmem_base + acc * kTileN;
+                    for (int kb = 0; kb < kb_count; ++kb) {
+                        wait_or_trap(&bars->full[stage], phase);
+                        if constexpr (kCG == 2) wait_or_trap(&bars->peer_full[stage], phase);
+                        tc_fence_after();
+                        const uint32_t sA = smem_u32(smem + stage * C::kStageBytes);
+                        const uint64_t descA = umma_desc_k128(sA);
+                        const uint64_t descB = umma_desc_k128(sA + C::kABytes);
 #pragma unroll
-                    for (int k = 0; k < kBlockK / 16; ++k) {
-                        // advance 16 elements (32 B) along K inside the swizzle atom: +2 in the >>4 address field
-                        umma_f16<1>(tmem_d, descA + 2 * k, descB + 2 * k, idesc, (kb | k) != 0);
+                        for (int k = 0; k < kBlockK / 16; ++k) {
+                            // advance 16 elements (32 B) along K inside the swizzle atom: +2 in the >>4 address field
+                            umma_f16<kCG>(tmem_d, descA + 2 * k, descB + 2 * k, idesc, (kb | k) != 0);
+                        }
+                        // slot free / accumulator ready, signalled when the MMAs above retire
+                        if constexpr (kCG == 1) {
+                            umma_commit(&bars->empty[stage]);
+                            if (kb == kb_count - 1) umma_commit(&bars->tmem_full[acc]);
+                        } else {
+                            umma_commit_2cta(&bars->empty[stage], 0b11);
+                            if (kb == kb_count - 1) umma_commit_2cta(&bars->tmem_full[acc], 0b11);
+                        }
+                        if (++stage == C::kStages) { stage = 0; phase ^= 1; }
                     }
-                    umma_commit(&bars->empty[stage]);          // frees the smem stage when these MMAs retire
-                    if (kb == kb_count - 1) umma_commit(&bars->tmem_full[acc]);
-                    if (++stage == kStages) { stage = 0; phase ^= 1; }
+                }
+            }
+        } else {
+            // ---------------- peer forwarder: my half of the stage has landed ----------------
+            if (elect_one()) {
+                uint32_t stage = 0, phase = 0;
+                for (int64_t u = unit0; u < n_units; u += unit_step) {
+                    for (int kb = 0; kb < kb_count; ++kb) {
+                        wait_or_trap(&bars->full[stage], phase);
+                        mbar_arrive_cluster(&bars->peer_full[stage], 0);
+                        if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+                    }
                 }
             }
         }
@@ -142,10 +186,10 @@ __global__ void __launch_bounds__(kThreads, 1) scan_mma_kernel(const MmaScanArgs
         // global atomic overlaps the next tile's MMAs instead of stalling the TMEM pipeline.
         float stash_v[kStash];
         uint32_t stash_r[kStash];
-        for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
+        for (int64_t u = unit0; u < n_units; u += unit_step, ++it) {
             const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
-            const int64_t ct = a.ct0 + t / a.n_qtiles;
-            const int qt = (int)(t % a.n_qtiles);
+            const int64_t ct = a.ct0 + u / n_qgroups;
+            const int qt = (int)(u % n_qgroups) * kCG + (int)cta_rank;
             const int q = qt * kTileM + quarter * 32 + lane;
             const float thr_s = a.thr[q] * scale;        // threshold in accumulator units (power-of-two scale)
             const int64_t row0 = ct * kTileN;
@@ -196,7 +240,8 @@ __global__ void __launch_bounds__(kThreads, 1) scan_mma_kernel(const MmaScanArgs
                 __syncwarp();
             }
             tc_fence_before();
-            mbar_arrive(&bars->tmem_empty[acc]);
+            if constexpr (kCG == 1) mbar_arrive(&bars->tmem_empty[acc]);
+            else mbar_arrive_cluster(&bars->tmem_empty[acc], 0);       // the leader's barrier counts both CTAs
             if (stash_n != 0) {
                 const uint32_t base = atomicAdd(a.cb.count + q, stash_n);
                 if (base + stash_n > a.cb.cap) *a.cb.overflow = 1u;
@@ -213,21 +258,42 @@ __global__ void __launch_bounds__(kThreads, 1) scan_mma_kernel(const MmaScanArgs
     }
 
     tc_fence_before();
-    __syncthreads();
-    if (warp == 1) tmem_dealloc<1>(tmem_base, 512);
+    if constexpr (kCG == 2) cluster_sync_all(); else __syncthreads();
+    if (warp == 1) tmem_dealloc<kCG>(tmem_base, 512);
 }
 
 }  // namespace
 
 cudaError_t scan_mma_configure() {
-    return cudaFuncSetAttribute(scan_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+    cudaError_t e = cudaFuncSetAttribute(scan_mma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         Cfg<1>::kSmemBytes);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(scan_mma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<2>::kSmemBytes);
 }
 
-cudaError_t launch_scan_mma(const MmaScanArgs& a, int sm_count, cudaStream_t s) {
-    const int64_t n_tiles = (a.ct1 - a.ct0) * a.n_qtiles;
-    if (n_tiles <= 0) return cudaSuccess;
-    const int grid = (int)(n_tiles < sm_count ? n_tiles : sm_count);
-    scan_mma_kernel<<<grid, kThreads, kSmemBytes, s>>>(a);
+cudaError_t launch_scan_mma(const MmaScanArgs& a, int sm_count, int cta_group, cudaStream_t s) {
+    const int64_t n_ctiles = a.ct1 - a.ct0;
+    if (n_ctiles <= 0 || a.n_qtiles <= 0) return cudaSuccess;
+    if (cta_group == 2 && (a.n_qtiles % 2) == 0) {
+        const int64_t n_units = n_ctiles * (a.n_qtiles / 2);
+        const int pairs = (int)(n_units < sm_count / 2 ? n_units : sm_count / 2);
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(2 * pairs);
+        cfg.blockDim = dim3(kThreads);
+        cfg.dynamicSmemBytes = Cfg<2>::kSmemBytes;
+        cfg.stream = s;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        return cudaLaunchKernelEx(&cfg, scan_mma_kernel<2>, a);
+    }
+    const int64_t n_units = n_ctiles * a.n_qtiles;
+    const int grid = (int)(n_units < sm_count ? n_units : sm_count);
+    scan_mma_kernel<1><<<grid, kThreads, Cfg<1>::kSmemBytes, s>>>(a);
     return cudaGetLastError();
 }
 

@@ -87,66 +87,127 @@ void launch_margins(const float* q_norm, const float* q_err, const OperandStats*
 }
 
 // ---------------------------------------------------------------------------------------------
-// One CTA per query.  Sorts the shortlist by (screen score desc, row asc); if it holds >= k
-// entries, tau becomes the k-th best screen score seen so far (a valid lower bound on the final
-// k-th best screen score), every true top-k row then has screen score >= tau - 2m, so entries
-// below thr = tau - 2m are dropped and later chunks only emit rows with score >= thr.
-__global__ void __launch_bounds__(512) refresh_kernel(CandBuf cb, int k, const float* __restrict__ margin,
-                                                      float* __restrict__ tau, float* __restrict__ thr) {
+// One CTA per query.  tau <- the k-th best screen score seen so far (a valid lower bound on the final
+// k-th best screen score), found by an 8-bit MSB radix select over the order-preserving keys; every
+// true top-k row then has screen score >= tau - 2m, so entries below thr = tau - 2m are dropped
+// (block-wide stream compaction, in place) and later chunks only emit rows with score >= thr.
+// No sort: the shortlist stays unordered until the final select.
+constexpr int kRefreshThreads = 256;
+
+__global__ void __launch_bounds__(kRefreshThreads) refresh_kernel(CandBuf cb, int k,
+                                                                  const float* __restrict__ margin,
+                                                                  float* __restrict__ tau,
+                                                                  float* __restrict__ thr) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
-    uint64_t* keys = reinterpret_cast<uint64_t*>(smem_raw);
-    __shared__ int s_keep;
+    uint32_t* keys = reinterpret_cast<uint32_t*>(smem_raw);          // [cap]
+    __shared__ uint32_t hist[256];
+    __shared__ uint32_t s_prefix, s_want;
+    __shared__ uint32_t warp_cnt[kRefreshThreads / 32];
+    __shared__ uint32_t s_base;
     const int q = blockIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t raw = cb.count[q];
     const int cnt = (int)min(raw, cb.cap);
-    if (raw > cb.cap && threadIdx.x == 0) *cb.overflow = 1u;
-    if ((uint32_t)cnt == cb.sorted[q]) return;   // nothing new since the last refresh
-    const int P = next_pow2(cnt);
-    const float* sc = cb.score + (size_t)q * cb.cap;
-    const uint32_t* rw = cb.row + (size_t)q * cb.cap;
-    for (int i = threadIdx.x; i < P; i += blockDim.x) keys[i] = i < cnt ? cand_key(sc[i], rw[i]) : 0ull;
-    bitonic_sort_desc(keys, P);
+    if (raw > cb.cap && tid == 0) *cb.overflow = 1u;
+    if ((uint32_t)cnt == cb.sorted[q]) return;   // nothing new since the last refresh (uniform per block)
+    float* sc = cb.score + (size_t)q * cb.cap;
+    uint32_t* rw = cb.row + (size_t)q * cb.cap;
+    for (int i = tid; i < cnt; i += kRefreshThreads) keys[i] = float_key(sc[i]);
     float tau_new = tau[q];
-    if (cnt >= k) tau_new = fmaxf(tau_new, key_float((uint32_t)(keys[k - 1] >> 32)));
+    if (cnt >= k) {
+        if (tid == 0) { s_prefix = 0u; s_want = (uint32_t)k; }
+        uint32_t mask = 0u;
+#pragma unroll 1
+        for (int shift = 24; shift >= 0; shift -= 8) {
+            hist[tid] = 0u;                                           // kRefreshThreads == 256 bins
+            __syncthreads();
+            const uint32_t prefix = s_prefix;
+            for (int i = tid; i < cnt; i += kRefreshThreads) {
+                const uint32_t key = keys[i];
+                if ((key & mask) == prefix) atomicAdd(&hist[(key >> shift) & 255u], 1u);
+            }
+            __syncthreads();
+            if (warp == 0) {
+                // lane l owns bins [255-8l-7, 255-8l] (descending order across lanes)
+                uint32_t local[8], sum = 0;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) { local[j] = hist[255 - (lane * 8 + j)]; sum += local[j]; }
+                uint32_t incl = sum;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+                    if (lane >= o) incl += v;
+                }
+                const uint32_t excl = incl - sum, want = s_want;
+                if (excl < want && want <= incl) {                    // the k-th best falls into this lane's bins
+                    uint32_t cum = excl;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        if (cum < want && want <= cum + local[j]) {
+                            s_prefix = prefix | ((uint32_t)(255 - (lane * 8 + j)) << shift);
+                            s_want = want - cum;
+                        }
+                        cum += local[j];
+                    }
+                }
+            }
+            mask |= 0xFFu << shift;
+            __syncthreads();
+        }
+        tau_new = fmaxf(tau_new, key_float(s_prefix));
+    }
     float thr_new = -INFINITY;
     if (tau_new > -INFINITY) {
         thr_new = tau_new - 2.f * margin[q];
         thr_new -= fabsf(thr_new) * 1e-6f;       // keep the cut conservative under fp32 rounding
     }
-    if (threadIdx.x == 0) {
-        // entries are sorted: binary search for the first one below thr_new
-        int lo = 0, hi = cnt;
-        while (lo < hi) {
-            const int mid = (lo + hi) >> 1;
-            if (key_float((uint32_t)(keys[mid] >> 32)) >= thr_new) lo = mid + 1; else hi = mid;
-        }
-        s_keep = lo;
-    }
+    // in-place compaction of entries with score >= thr_new, one round of kRefreshThreads entries at a time
+    const uint32_t thr_key = float_key(thr_new);
+    if (tid == 0) s_base = 0u;
     __syncthreads();
-    const int keep = s_keep;
-    float* sc_w = cb.score + (size_t)q * cb.cap;
-    uint32_t* rw_w = cb.row + (size_t)q * cb.cap;
-    for (int i = threadIdx.x; i < keep; i += blockDim.x) {
-        const uint64_t kk = keys[i];
-        sc_w[i] = key_float((uint32_t)(kk >> 32));
-        rw_w[i] = 0xFFFFFFFFu - (uint32_t)kk;
+    for (int r0 = 0; r0 < cnt; r0 += kRefreshThreads) {
+        const int i = r0 + tid;
+        uint32_t key = 0u, row = 0u;
+        bool keep = false;
+        if (i < cnt) {
+            key = keys[i];
+            row = rw[i];
+            keep = thr_new == -INFINITY || key >= thr_key;
+        }
+        const uint32_t ballot = __ballot_sync(0xffffffffu, keep);
+        if (lane == 0) warp_cnt[warp] = __popc(ballot);
+        __syncthreads();                                   // all reads of this round done, counts visible
+        uint32_t off = s_base;
+        for (int w = 0; w < warp; ++w) off += warp_cnt[w];
+        if (keep) {
+            const uint32_t pos = off + __popc(ballot & ((1u << lane) - 1u));
+            sc[pos] = key_float(key);
+            rw[pos] = row;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            uint32_t t = 0;
+            for (int w = 0; w < kRefreshThreads / 32; ++w) t += warp_cnt[w];
+            s_base += t;
+        }
+        __syncthreads();
     }
-    if (threadIdx.x == 0) {
-        cb.count[q] = (uint32_t)keep;
-        cb.sorted[q] = (uint32_t)keep;
+    if (tid == 0) {
+        cb.count[q] = s_base;
+        cb.sorted[q] = s_base;
         tau[q] = tau_new;
         thr[q] = thr_new;
     }
 }
 
 void launch_refresh(CandBuf cb, int k, const float* margin, float* tau, float* thr, int nq, cudaStream_t s) {
-    const size_t smem = (size_t)cb.cap * sizeof(uint64_t);
+    const size_t smem = (size_t)cb.cap * sizeof(uint32_t);
     static size_t configured = 0;
-    if (smem > 48 * 1024 && smem > configured) {
+    if (smem > 40 * 1024 && smem > configured) {
         cudaFuncSetAttribute(refresh_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         configured = smem;
     }
-    refresh_kernel<<<nq, 512, smem, s>>>(cb, k, margin, tau, thr);
+    refresh_kernel<<<nq, kRefreshThreads, smem, s>>>(cb, k, margin, tau, thr);
 }
 
 // ---------------------------------------------------------------------------------------------

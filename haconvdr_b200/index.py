@@ -121,6 +121,9 @@ class FlatIPIndex:
                                       int(path)), "hac_search")
         return D, I
 
+    def set_option(self, name: str, value: int):
+        check(self._lib.hac_set_option(self._h, name.encode(), int(value)), "hac_set_option")
+
     def stats(self) -> dict:
         st = HacStats()
         check(self._lib.hac_get_stats(self._h, ctypes.byref(st)), "hac_get_stats")

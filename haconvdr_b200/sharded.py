@@ -42,6 +42,7 @@ class ShardedFlatIPIndex:
         self.ntotal = 0            # global rows
         self._lo = 0               # global offset of the next add's first row
         self._bases = []           # (local_row_start, global_row_start, n) per add
+        self._pinned_q = None      # page-locked staging for host queries
 
     # -- building the shard ---------------------------------------------------------------------
     def _after_add(self, lo_global: int, n_local: int):
@@ -86,8 +87,11 @@ class ShardedFlatIPIndex:
         torch, dist = self._torch, self._dist
         as_numpy = not (hasattr(q, "is_cuda") and q.is_cuda)
         if as_numpy and self._on_gpu():
-            q = torch.from_numpy(np.ascontiguousarray(q, dtype=np.float32)).pin_memory().to(
-                self._device(), non_blocking=True)
+            qh = torch.from_numpy(np.ascontiguousarray(q, dtype=np.float32))
+            if self._pinned_q is None or self._pinned_q.shape != qh.shape:
+                self._pinned_q = torch.empty(qh.shape, dtype=torch.float32).pin_memory()   # reused across calls
+            self._pinned_q.copy_(qh)
+            q = self._pinned_q.to(self._device(), non_blocking=True)
         D, I = self.local.search(q, k)
         if self.world_size > 1:
             if not torch.is_tensor(D):

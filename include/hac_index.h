@@ -134,6 +134,12 @@ int hac_gather_ids_device(int device, const int64_t* table_dev, int64_t table_n,
 int hac_pinned_alloc(size_t bytes, void** out_host);
 int hac_pinned_free(void* host);
 
+/* ---- tuning knobs ---------------------------------------------------------------------------
+ * Named integer options (unknown names -> HAC_E_INVALID):
+ *   "mma_cta_group"  1 = one CTA per scan tile, 2 = CTA pairs sharing each MMA (cta_group::2)
+ *   "chunk_growth_x100"  corpus-chunk growth factor of the threshold schedule, in percent (default 400) */
+int hac_set_option(hac_index* idx, const char* name, int64_t value);
+
 /* ---- introspection --------------------------------------------------------------------------- */
 int64_t hac_ntotal(const hac_index* idx);
 int hac_dim(const hac_index* idx);

@@ -1,0 +1,95 @@
+"""GPU (-m gpu), needs >= 2 devices (skipped otherwise): the real multi-GPU paths.
+  * torchrun, one process per GPU, NCCL all-gather of Q x k candidates + device merge
+    (haconvdr_b200.sharded.ShardedFlatIPIndex) against the fp64 arbiter;
+  * the in-process faiss IndexShards stand-in (faiss_compat.index_cpu_to_gpu_multiple, n_gpu = 2)."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+WORKER = r'''
+import os, sys
+import numpy as np, torch, torch.distributed as dist
+sys.path.insert(0, os.environ["HAC_ROOT"])
+from haconvdr_b200.sharded import ShardedFlatIPIndex
+from haconvdr_b200 import FlatIPIndex
+from oracle.flat_ip import brute_force_fp64
+from oracle.compare import assert_parity
+rank, local = int(os.environ["RANK"]), int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(local)
+dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+rng = np.random.default_rng(77)
+blocks = [rng.standard_normal((n, 768), dtype=np.float32) for n in (30001, 17777)]
+q = rng.standard_normal((150, 768), dtype=np.float32)
+x = np.concatenate(blocks, 0)
+idx = ShardedFlatIPIndex(768, FlatIPIndex(768, local))
+for b in blocks:
+    idx.add(b)
+D, I = idx.search(q, 100)
+D64, I64 = brute_force_fp64(q, x, 100)
+x64 = x.astype(np.float64)
+assert_parity(D64, I64, D, I, rtol=1e-5, ref_scores_of=lambda qi, ids: x64[ids] @ q[qi].astype(np.float64))
+Dd, Id = idx.search(torch.from_numpy(q).cuda(), 100)
+assert np.array_equal(Id.cpu().numpy(), I) and np.array_equal(Dd.cpu().numpy(), D)
+# synthetic shards reproduce the same global corpus for any world size
+idx.reset()
+idx.add_synthetic(100000, seed=42)
+from haconvdr_b200.index import synth_rows_device
+xs = synth_rows_device(100000, 768, seed=42, device=local).cpu().numpy()
+D, I = idx.search(q, 10)
+D64, I64 = brute_force_fp64(q, xs, 10)
+xs64 = xs.astype(np.float64)
+assert_parity(D64, I64, D, I, rtol=1e-5, ref_scores_of=lambda qi, ids: xs64[ids] @ q[qi].astype(np.float64))
+dist.barrier()
+if rank == 0:
+    print("MULTI_OK")
+dist.destroy_process_group()
+'''
+
+
+def _n_gpus():
+    import torch
+    return torch.cuda.device_count()
+
+
+def test_torchrun_nccl_sharded_search(tmp_path):
+    if _n_gpus() < 2:
+        pytest.skip("needs 2 GPUs")
+    script = tmp_path / "worker.py"
+    script.write_text(WORKER)
+    env = dict(os.environ, HAC_ROOT=ROOT)
+    res = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29577", str(script)],
+                         capture_output=True, text=True, env=env, timeout=600)
+    assert res.returncode == 0 and "MULTI_OK" in res.stdout, res.stdout[-3000:] + res.stderr[-3000:]
+
+
+def test_in_process_index_shards_two_devices():
+    if _n_gpus() < 2:
+        pytest.skip("needs 2 GPUs")
+    from haconvdr_b200 import faiss_compat as faiss
+    from oracle.compare import assert_parity
+    from oracle.flat_ip import brute_force_fp64
+    co = faiss.GpuMultipleClonerOptions()
+    co.shard = True
+    vres, vdev = faiss.GpuResourcesVector(), faiss.Int32Vector()
+    for i in range(2):
+        vdev.push_back(i)
+        vres.push_back(faiss.StandardGpuResources())
+    index = faiss.index_cpu_to_gpu_multiple(vres, vdev, faiss.IndexFlatIP(768), co)
+    rng = np.random.default_rng(5)
+    x = rng.standard_normal((25001, 768), dtype=np.float32)
+    q = rng.standard_normal((70, 768), dtype=np.float32)
+    index.add(x[:9000])
+    index.add(x[9000:])
+    D, I = index.search(q, 100)
+    D64, I64 = brute_force_fp64(q, x, 100)
+    x64 = x.astype(np.float64)
+    assert_parity(D64, I64, D, I, rtol=1e-5, ref_scores_of=lambda qi, ids: x64[ids] @ q[qi].astype(np.float64))
+    index.reset()
+    assert index.ntotal == 0
