@@ -166,21 +166,35 @@ def stream_block_into(index, emb_path: str, chunk_bytes: int = 64 << 20, buffers
     freed = [threading.Semaphore(1) for _ in bufs]
     err = []
 
+    n_readers = max(1, min(8, (os.cpu_count() or 2) // 2))
+
+    def read_slice(fd, mv, file_off):
+        got = 0
+        while got < len(mv):
+            r = os.preadv(fd, [mv[got:]], file_off + got)      # releases the GIL; slices read in parallel
+            if not r:
+                raise IOError("short read in %s" % emb_path)
+            got += r
+
     def reader():
         try:
-            with open(emb_path, "rb", buffering=0) as f:
-                f.seek(hdr.payload_offset)
-                for i, (_, nr) in enumerate(chunks):
-                    b = i % len(bufs)
-                    freed[b].acquire()
-                    mv = memoryview(bufs[b].view)[: nr * row_bytes]
-                    got = 0
-                    while got < len(mv):
-                        r = f.readinto(mv[got:])
-                        if not r:
-                            raise IOError("short read in %s" % emb_path)
-                        got += r
-                    filled[b].release()
+            from concurrent.futures import ThreadPoolExecutor
+            fd = os.open(emb_path, os.O_RDONLY)
+            try:
+                with ThreadPoolExecutor(n_readers) as pool:
+                    for i, (r0, nr) in enumerate(chunks):
+                        b = i % len(bufs)
+                        freed[b].acquire()
+                        mv = memoryview(bufs[b].view).cast("B")[: nr * row_bytes]
+                        base = hdr.payload_offset + r0 * row_bytes
+                        step = (len(mv) + n_readers - 1) // n_readers
+                        step = (step + 4095) // 4096 * 4096
+                        futs = [pool.submit(read_slice, fd, mv[o:o + step], base + o) for o in range(0, len(mv), step)]
+                        for f in futs:
+                            f.result()
+                        filled[b].release()
+            finally:
+                os.close(fd)
         except Exception as e:   # surfaced on the consumer side
             err.append(e)
             for s in filled:
