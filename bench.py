@@ -155,14 +155,29 @@ def run_ours(args):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        # NCCL prints its version banner on stdout at communicator creation; stdout must carry only the
+        # one JSON line, so fd 1 points at stderr until the first collective has run.
+        sys.stdout.flush()
+        saved_fd = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            warm = torch.zeros(1, device=dev)
+            dist.all_reduce(warm)
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_fd, 1)
+            os.close(saved_fd)
     t_setup = time.perf_counter()
 
     index = ShardedFlatIPIndex(DIM, FlatIPIndex(DIM, local_rank))
     index.add_synthetic(args.rows, seed=42)
     shard_rows = index.local.ntotal
     q_dev = synth_rows_device(args.queries, DIM, seed=4242, device=local_rank)
-    q_host = q_dev.cpu().numpy()
+    q_pinned = torch.empty(q_dev.shape, dtype=torch.float32).pin_memory()   # e2e inputs live in pinned host memory
+    q_pinned.copy_(q_dev)
+    q_host = q_pinned.numpy()
     torch.cuda.synchronize()
     setup_s = time.perf_counter() - t_setup
 

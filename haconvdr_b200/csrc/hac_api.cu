@@ -7,6 +7,7 @@
 
 #include <algorithm>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "../../include/hac_index.h"
@@ -313,13 +314,27 @@ int search_batch(hac_index* idx, int nq, const float* q_dev, int k, float* D_dev
     st.path = path;
     st.retries = 0;
 
-    for (int level = 0; level < 3; ++level) {
+    SegTable segs;
+    segs.n = (int)idx->segs.size();
+    for (int i = 0; i < segs.n; ++i) {
+        segs.base[i] = idx->segs[i].base;
+        segs.rows[i] = idx->segs[i].rows;
+    }
+    // level 0: fast mode - the whole search is enqueued without a host round trip; the overflow flag is
+    //          read once at the end.
+    // level 1: careful mode (only after level 0 overflowed: mass near-duplicates, adversarial data) -
+    //          larger shortlist, the flag is read after every chunk; an overflowing chunk is rolled back and
+    //          split in two; when a minimal chunk still overflows the carry-over is cut to its exact top-k
+    //          (rescore + exact compaction), which bounds it by k whatever the data.  Always terminates.
+    for (int level = 0; level < 2; ++level) {
+        const bool careful = level == 1;
         const uint32_t cap = cap_for_k(k, level);
         int rc = ensure_workspace(idx, nq_pad, cap, 0);
         if (rc != HAC_OK) return rc;
         Workspace& w = idx->ws;
         CandBuf cb = w.cb;
         cb.cap = cap;   // rows of the candidate arrays are cap entries apart (may be below the allocation)
+        HostReadback* hr = static_cast<HostReadback*>(w.host_pinned);
         int launches = 0, n_chunks = 0, n_ev = 2;
         cudaEventRecord(idx->ev[0], s);
         launch_init_search(cb, w.tau, w.thr, nq, nq_pad, s);
@@ -335,58 +350,91 @@ int search_batch(hac_index* idx, int nq, const float* q_dev, int k, float* D_dev
             launch_margins(nullptr, nullptr, nullptr, d, w.margin, w.scalars + 1, nq, s);
             ++launches;
         }
+        auto scan = [&](const Segment& seg, int64_t r, int64_t r1) -> int {
+            const bool timed = n_ev + 2 <= kMaxEvents;
+            if (timed) cudaEventRecord(idx->ev[n_ev], s);
+            if (path == HAC_PATH_MMA) {
+                MmaScanArgs a;
+                a.q_shadow = w.q_shadow;
+                a.x_shadow = seg.shadow;
+                a.q_stats = w.q_stats;
+                a.x_stats = seg.stats;
+                a.thr = w.thr;
+                a.d = d;
+                a.n_qtiles = nq_pad / kTileRows;
+                a.ct0 = r / kRowAlign;
+                a.ct1 = (r1 + kRowAlign - 1) / kRowAlign;
+                a.seg_rows = std::min(seg.n_rows, r1);     // rows past r1 belong to a later chunk
+                a.row_id_base = seg.base;
+                a.cb = cb;
+                CU(launch_scan_mma(a, idx->sm_count, idx->mma_cta_group, s));
+            } else {
+                launch_scan_gemv(seg.rows, r, r1, d, q_dev, nq, w.thr, cb, seg.base, idx->sm_count, s);
+            }
+            if (timed) {
+                cudaEventRecord(idx->ev[n_ev + 1], s);
+                n_ev += 2;
+            }
+            ++launches;
+            ++n_chunks;
+            return HAC_OK;
+        };
+        auto overflowed = [&](bool* flag) -> int {
+            CU(cudaMemcpyAsync(&hr->overflow, cb.overflow, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+            CU(cudaStreamSynchronize(s));
+            *flag = hr->overflow != 0;
+            return HAC_OK;
+        };
         // chunk schedule: the first chunk is emitted unfiltered (it must fit the shortlist), later
         // chunks grow geometrically with the rows already seen, so every chunk is expected to add
         // about growth * k * (margin factor) candidates per query.
-        double growth = std::min(idx->chunk_growth, std::max(1.0, (double)cap / (8.0 * k)));
-        if (level == 1) growth = std::max(0.5, growth / 4.0);
+        const double growth = std::min(idx->chunk_growth, std::max(1.0, (double)cap / (8.0 * k)));
         int64_t rows_done = 0;
         for (size_t si = 0; si < idx->segs.size(); ++si) {
             const Segment& seg = idx->segs[si];
             int64_t r = 0;
             while (r < seg.n_rows) {
-                int64_t size;
-                if (level == 2) size = cap / 4;
-                else if (rows_done == 0) size = cap / 2;
-                else size = (int64_t)(growth * (double)rows_done);
+                int64_t size = rows_done == 0 ? cap / 2 : (int64_t)(growth * (double)rows_done);
                 size = std::max<int64_t>(kRowAlign, size / kRowAlign * kRowAlign);
                 const int64_t r1 = std::min(seg.n_rows, r + size);
-                const bool timed = n_ev + 2 <= kMaxEvents;
-                if (timed) cudaEventRecord(idx->ev[n_ev], s);
-                if (path == HAC_PATH_MMA) {
-                    MmaScanArgs a;
-                    a.q_shadow = w.q_shadow;
-                    a.x_shadow = seg.shadow;
-                    a.q_stats = w.q_stats;
-                    a.x_stats = seg.stats;
-                    a.thr = w.thr;
-                    a.d = d;
-                    a.n_qtiles = nq_pad / kTileRows;
-                    a.ct0 = r / kRowAlign;
-                    a.ct1 = (r1 + kRowAlign - 1) / kRowAlign;
-                    a.seg_rows = seg.n_rows;
-                    a.row_id_base = seg.base;
-                    a.cb = cb;
-                    CU(launch_scan_mma(a, idx->sm_count, idx->mma_cta_group, s));
+                if (!careful) {
+                    rc = scan(seg, r, r1);
+                    if (rc != HAC_OK) return rc;
+                    launch_refresh(cb, k, w.margin, w.tau, w.thr, nq, s);
+                    ++launches;
                 } else {
-                    launch_scan_gemv(seg.rows, r, r1, d, q_dev, nq, w.thr, cb, seg.base, idx->sm_count, s);
+                    std::vector<std::pair<int64_t, int64_t>> todo{{r, r1}};
+                    while (!todo.empty()) {
+                        const auto [a0, b0] = todo.back();
+                        todo.pop_back();
+                        bool ovf = false;
+                        rc = scan(seg, a0, b0);
+                        if (rc == HAC_OK) rc = overflowed(&ovf);
+                        if (rc != HAC_OK) return rc;
+                        if (ovf) {
+                            launch_rollback(cb, nq, s);
+                            ++launches;
+                            if (b0 - a0 > 2 * kRowAlign) {
+                                const int64_t mid = a0 + ((b0 - a0) / 2 + kRowAlign - 1) / kRowAlign * kRowAlign;
+                                todo.push_back({mid, b0});     // LIFO: the lower half is scanned first
+                                todo.push_back({a0, mid});
+                                continue;
+                            }
+                            launch_rescore(cb, q_dev, d, segs, nq, w.scalars + 2, w.counters + 1, s);
+                            launch_exact_compact(cb, k, w.margin, w.tau, w.thr, nq, s);
+                            launches += 2;
+                            rc = scan(seg, a0, b0);
+                            if (rc == HAC_OK) rc = overflowed(&ovf);
+                            if (rc != HAC_OK) return rc;
+                            if (ovf) return fail(HAC_E_OVERFLOW, "shortlist overflow in a minimal chunk (k too close to the cap)");
+                        }
+                        launch_refresh(cb, k, w.margin, w.tau, w.thr, nq, s);
+                        ++launches;
+                    }
                 }
-                if (timed) {
-                    cudaEventRecord(idx->ev[n_ev + 1], s);
-                    n_ev += 2;
-                }
-                launch_refresh(cb, k, w.margin, w.tau, w.thr, nq, s);
-                launches += 2;
-                ++n_chunks;
                 rows_done += r1 - r;
                 r = r1;
             }
-        }
-        SegTable segs;
-        segs.n = (int)idx->segs.size();
-        for (int i = 0; i < segs.n; ++i) {
-            segs.base[i] = idx->segs[i].base;
-            segs.rows[i] = idx->segs[i].rows;
         }
         launch_rescore(cb, q_dev, d, segs, nq, w.scalars + 2, w.counters + 1, s);
         launch_final_select(cb, k, nq, idx->id_table, idx->id_base, D_dev, I_dev, s);
@@ -394,7 +442,6 @@ int search_batch(hac_index* idx, int nq, const float* q_dev, int k, float* D_dev
         cudaEventRecord(idx->ev[1], s);
         CU(cudaGetLastError());
         // read back the overflow flag and the statistics (56 bytes)
-        HostReadback* hr = static_cast<HostReadback*>(w.host_pinned);
         CU(cudaMemcpyAsync(&hr->overflow, cb.overflow, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
         CU(cudaMemcpyAsync(&hr->emitted, w.counters, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
         CU(cudaMemcpyAsync(&hr->margin_max, w.scalars + 1, 2 * sizeof(float), cudaMemcpyDeviceToHost, s));
@@ -417,8 +464,7 @@ int search_batch(hac_index* idx, int nq, const float* q_dev, int k, float* D_dev
         if (!hr->overflow) return HAC_OK;
         st.retries = level + 1;
     }
-    return fail(HAC_E_OVERFLOW,
-                "candidate shortlist overflowed in every retry mode (pathological near-duplicate corpus?)");
+    return fail(HAC_E_OVERFLOW, "candidate shortlist overflowed even in careful mode");
 }
 
 int search_common(hac_index* idx, int64_t nq, const float* q, bool q_on_host, int k, float* D, int64_t* I,

@@ -61,6 +61,9 @@ void launch_rescore(CandBuf cb, const float* q, int d, SegTable segs, int nq, fl
 void launch_final_select(CandBuf cb, int k, int nq, const int64_t* id_table, int64_t id_base, float* D,
                          int64_t* I, cudaStream_t s);
 void launch_fill_empty(float* D, int64_t* I, int64_t n, cudaStream_t s);
+// careful mode: undo the appends since the last refresh / cut the rescored shortlist to its exact top-k
+void launch_rollback(CandBuf cb, int nq, cudaStream_t s);
+void launch_exact_compact(CandBuf cb, int k, const float* margin, float* tau, float* thr, int nq, cudaStream_t s);
 
 // ---- scans ---------------------------------------------------------------------------------
 // exact fp32 streaming scan of rows [r0, r1) of one segment, 1..4 queries

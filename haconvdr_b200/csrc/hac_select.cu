@@ -281,6 +281,61 @@ __global__ void __launch_bounds__(512) final_select_kernel(CandBuf cb, int k, co
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Careful mode (shortlist overflow recovery).
+// rollback: forget the appends made since the last refresh (entries [0, sorted) are intact).
+__global__ void rollback_kernel(CandBuf cb, int nq) {
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q == 0) *cb.overflow = 0u;
+    if (q < nq) cb.count[q] = cb.sorted[q];
+}
+void launch_rollback(CandBuf cb, int nq, cudaStream_t s) {
+    rollback_kernel<<<(nq + 255) / 256, 256, 0, s>>>(cb, nq);
+}
+
+// exact compaction: the shortlist (already rescored) is cut to its k best entries by
+// (exact score desc, row asc); those entries now carry their exact score.  A row dropped here is
+// ranked behind k rows with smaller ids or larger scores and can never re-enter the top-k, so the
+// carry-over between chunks is bounded by k whatever the data looks like (mass duplicates).
+__global__ void __launch_bounds__(512) exact_compact_kernel(CandBuf cb, int k, const float* __restrict__ margin,
+                                                            float* __restrict__ tau, float* __restrict__ thr) {
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    uint64_t* keys = reinterpret_cast<uint64_t*>(smem_raw);
+    const int q = blockIdx.x;
+    const int cnt = (int)min(cb.count[q], cb.cap);
+    const int P = next_pow2(cnt);
+    float* sc = cb.score + (size_t)q * cb.cap;
+    uint32_t* rw = cb.row + (size_t)q * cb.cap;
+    const float* ex = cb.exact + (size_t)q * cb.cap;
+    for (int i = threadIdx.x; i < P; i += blockDim.x) keys[i] = i < cnt ? cand_key(ex[i], rw[i]) : 0ull;
+    bitonic_sort_desc(keys, P);
+    const int keep = min(cnt, k);
+    for (int i = threadIdx.x; i < keep; i += blockDim.x) {
+        sc[i] = key_float((uint32_t)(keys[i] >> 32));
+        rw[i] = 0xFFFFFFFFu - (uint32_t)keys[i];
+    }
+    if (threadIdx.x == 0) {
+        cb.count[q] = (uint32_t)keep;
+        cb.sorted[q] = (uint32_t)keep;
+        if (cnt >= k) {
+            const float t = fmaxf(tau[q], key_float((uint32_t)(keys[k - 1] >> 32)));
+            float th = t - 2.f * margin[q];
+            th -= fabsf(th) * 1e-6f;
+            tau[q] = t;
+            thr[q] = th;
+        }
+    }
+}
+void launch_exact_compact(CandBuf cb, int k, const float* margin, float* tau, float* thr, int nq, cudaStream_t s) {
+    const size_t smem = (size_t)cb.cap * sizeof(uint64_t);
+    static size_t configured = 0;
+    if (smem > 40 * 1024 && smem > configured) {
+        cudaFuncSetAttribute(exact_compact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        configured = smem;
+    }
+    exact_compact_kernel<<<nq, 512, smem, s>>>(cb, k, margin, tau, thr);
+}
+
 void launch_final_select(CandBuf cb, int k, int nq, const int64_t* id_table, int64_t id_base, float* D,
                          int64_t* I, cudaStream_t s) {
     const size_t smem = (size_t)cb.cap * sizeof(uint64_t);

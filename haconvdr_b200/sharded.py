@@ -43,6 +43,7 @@ class ShardedFlatIPIndex:
         self._lo = 0               # global offset of the next add's first row
         self._bases = []           # (local_row_start, global_row_start, n) per add
         self._pinned_q = None      # page-locked staging for host queries
+        self._pinned_out = None    # page-locked staging for host results
 
     # -- building the shard ---------------------------------------------------------------------
     def _after_add(self, lo_global: int, n_local: int):
@@ -83,15 +84,22 @@ class ShardedFlatIPIndex:
     # -- search ---------------------------------------------------------------------------------
     def search(self, q, k: int):
         """``q``: the same queries on every rank (numpy -> numpy results, CUDA tensor -> CUDA tensors).
-        Returns the merged global (D [Q,k], I [Q,k]) on every rank."""
+        Returns the merged global (D [Q,k], I [Q,k]) on every rank.
+
+        Host queries are copied straight from the caller's array when it is page-locked, otherwise
+        through a reused pinned staging buffer; host results come back through pinned buffers too."""
         torch, dist = self._torch, self._dist
         as_numpy = not (hasattr(q, "is_cuda") and q.is_cuda)
         if as_numpy and self._on_gpu():
+            if self.world_size == 1:
+                return self.local.search(q, k)                     # plain host-buffer C-ABI call
             qh = torch.from_numpy(np.ascontiguousarray(q, dtype=np.float32))
-            if self._pinned_q is None or self._pinned_q.shape != qh.shape:
-                self._pinned_q = torch.empty(qh.shape, dtype=torch.float32).pin_memory()   # reused across calls
-            self._pinned_q.copy_(qh)
-            q = self._pinned_q.to(self._device(), non_blocking=True)
+            if not qh.is_pinned():
+                if self._pinned_q is None or self._pinned_q.shape != qh.shape:
+                    self._pinned_q = torch.empty(qh.shape, dtype=torch.float32).pin_memory()
+                self._pinned_q.copy_(qh)
+                qh = self._pinned_q
+            q = qh.to(self._device(), non_blocking=True)
         D, I = self.local.search(q, k)
         if self.world_size > 1:
             if not torch.is_tensor(D):
@@ -103,7 +111,15 @@ class ShardedFlatIPIndex:
             dist.all_gather_into_tensor(Ig, I.contiguous(), group=self.group)
             D, I = self._merge(Dg.view(self.world_size, nq, k), Ig.view(self.world_size, nq, k), k)
         if as_numpy and torch.is_tensor(D):
-            return D.cpu().numpy(), I.cpu().numpy()
+            if D.is_cuda:
+                if self._pinned_out is None or self._pinned_out[0].shape != D.shape:
+                    self._pinned_out = (torch.empty(D.shape, dtype=D.dtype).pin_memory(),
+                                        torch.empty(I.shape, dtype=I.dtype).pin_memory())
+                self._pinned_out[0].copy_(D, non_blocking=True)
+                self._pinned_out[1].copy_(I, non_blocking=True)
+                torch.cuda.current_stream(D.device).synchronize()
+                return self._pinned_out[0].numpy().copy(), self._pinned_out[1].numpy().copy()
+            return D.numpy(), I.numpy()
         return D, I
 
     def _on_gpu(self) -> bool:

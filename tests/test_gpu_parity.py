@@ -232,3 +232,28 @@ def test_synthetic_rows_do_not_depend_on_shard_split():
     idx.add_synthetic(1000, seed=42, row0=0)
     D, I = idx.search(q, 10)
     _check(q, x, 10, D, I)
+
+
+def test_mass_duplicates_recovered_in_careful_mode():
+    """30 000 identical rows tie for the top: the shortlist overflows in fast mode, the careful mode
+    (roll back, split, exact compaction) must still return the exact (score desc, id asc) answer."""
+    hb = _engine()
+    rng = np.random.default_rng(21)
+    v = rng.standard_normal(768).astype(np.float32)
+    x = np.concatenate([rng.standard_normal((5000, 768), dtype=np.float32),
+                        np.tile(v, (30000, 1)),
+                        rng.standard_normal((5000, 768), dtype=np.float32)], 0)
+    q = rng.standard_normal((130, 768), dtype=np.float32)
+    q[:40] = (v * rng.uniform(0.5, 2.0, size=(40, 1)) + 0.05 * rng.standard_normal((40, 768))).astype(np.float32)
+    idx = hb.FlatIPIndex(768)
+    idx.add(x)
+    D, I = idx.search(q, 100)
+    st = idx.stats()
+    assert st["retries"] >= 1, st                       # the fast mode did overflow
+    D64, I64 = brute_force_fp64(q, x, 100)
+    assert np.array_equal(I[:40], np.tile(np.arange(5000, 5100), (40, 1)))     # first 100 duplicates, id order
+    assert_parity(D64, I64, D, I, rtol=RTOL, ref_scores_of=_scores_of(q, x))
+    # k = 1000 with the larger shortlist as well
+    D, I = idx.search(q[:8], 1000)
+    D64, I64 = brute_force_fp64(q[:8], x, 1000)
+    assert_parity(D64, I64, D, I, rtol=RTOL, ref_scores_of=_scores_of(q[:8], x))
