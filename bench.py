@@ -231,6 +231,19 @@ def run_ours(args):
     e2e_qps = args.queries / e2e_s
     assert np.array_equal(Ih, I.cpu().numpy()), "host and device API disagree"
 
+    # ---- phase breakdown of the multi-GPU step (diagnostics, outside the timed regions) ----------------
+    phases = None
+    if world > 1:
+        index.profile = True
+        acc = {}
+        for _ in range(5):
+            index.search(q_dev, args.k)
+            for kk, vv in index.last_phase_ms.items():
+                acc[kk] = acc.get(kk, 0.0) + vv / 5
+        index.profile = False
+        phases = {kk: max_over_ranks(vv) for kk, vv in acc.items()}
+        barrier()
+
     # ---- sanity: results are plausible for the N(0,1) corpus (rank-100 score ~ 4.5 sigma) ----------
     st = index.local.stats()
     assert st["path"] == HAC_PATH_MMA and st["retries"] == 0, st
@@ -275,6 +288,7 @@ def run_ours(args):
         "stats": {"candidates_emitted_per_step": emitted // args.steps, "candidates_rescored_per_step": rescored // args.steps,
                   "margin_max": st["margin_max"], "screen_err_max": st["screen_err_max"], "n_chunks": st["n_chunks"],
                   "search_ms_per_step_device": total_ms / args.steps, "setup_s": setup_s,
+                  "multi_gpu_phase_ms_max_over_ranks": phases,
                   "hbm_fp32_gb": st["bytes_fp32"] / 1e9, "hbm_shadow_gb": st["bytes_shadow"] / 1e9},
     }
     print(json.dumps(line), flush=True)

@@ -202,11 +202,8 @@ __global__ void __launch_bounds__(kRefreshThreads) refresh_kernel(CandBuf cb, in
 
 void launch_refresh(CandBuf cb, int k, const float* margin, float* tau, float* thr, int nq, cudaStream_t s) {
     const size_t smem = (size_t)cb.cap * sizeof(uint32_t);
-    static size_t configured = 0;
-    if (smem > 40 * 1024 && smem > configured) {
-        cudaFuncSetAttribute(refresh_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        configured = smem;
-    }
+    // the attribute is per device (several devices per process are possible), so it is set per launch
+    if (smem > 40 * 1024) cudaFuncSetAttribute(refresh_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     refresh_kernel<<<nq, kRefreshThreads, smem, s>>>(cb, k, margin, tau, thr);
 }
 
@@ -328,22 +325,16 @@ __global__ void __launch_bounds__(512) exact_compact_kernel(CandBuf cb, int k, c
 }
 void launch_exact_compact(CandBuf cb, int k, const float* margin, float* tau, float* thr, int nq, cudaStream_t s) {
     const size_t smem = (size_t)cb.cap * sizeof(uint64_t);
-    static size_t configured = 0;
-    if (smem > 40 * 1024 && smem > configured) {
-        cudaFuncSetAttribute(exact_compact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        configured = smem;
-    }
+    // the attribute is per device (several devices per process are possible), so it is set per launch
+    if (smem > 40 * 1024) cudaFuncSetAttribute(exact_compact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     exact_compact_kernel<<<nq, 512, smem, s>>>(cb, k, margin, tau, thr);
 }
 
 void launch_final_select(CandBuf cb, int k, int nq, const int64_t* id_table, int64_t id_base, float* D,
                          int64_t* I, cudaStream_t s) {
     const size_t smem = (size_t)cb.cap * sizeof(uint64_t);
-    static size_t configured = 0;
-    if (smem > 48 * 1024 && smem > configured) {
-        cudaFuncSetAttribute(final_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        configured = smem;
-    }
+    // the attribute is per device (several devices per process are possible), so it is set per launch
+    if (smem > 48 * 1024) cudaFuncSetAttribute(final_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     final_select_kernel<<<nq, 512, smem, s>>>(cb, k, id_table, id_base, D, I);
 }
 

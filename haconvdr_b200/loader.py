@@ -141,10 +141,11 @@ def load_embid(path: str) -> np.ndarray:
         return np.ascontiguousarray(pickle.load(h), dtype=np.int64)
 
 
-def stream_block_into(index, emb_path: str, chunk_bytes: int = 64 << 20, buffers=None) -> int:
+def stream_block_into(index, emb_path: str, chunk_bytes: int = 64 << 20, buffers=None, row_range=None) -> int:
     """Append the rows of one embedding block file to ``index`` (a FlatIPIndex) through pinned
-    staging.  Returns the number of rows.  Falls back to ``pickle.load`` + ``add`` for pickles the
-    header walker does not understand."""
+    staging.  ``row_range=(lo, hi)`` appends only rows [lo, hi) of the block (a rank's slice of a
+    block that straddles two shards).  Returns the number of rows appended.  Falls back to
+    ``pickle.load`` + ``add`` for pickles the header walker does not understand."""
     try:
         hdr = parse_ndarray_pickle_header(emb_path)
         if hdr.dtype != np.dtype("<f4") or len(hdr.shape) != 2 or hdr.shape[1] != index.d:
@@ -152,6 +153,8 @@ def stream_block_into(index, emb_path: str, chunk_bytes: int = 64 << 20, buffers
     except ValueError:
         with open(emb_path, "rb") as h:
             arr = pickle.load(h)
+        if row_range is not None:
+            arr = arr[row_range[0]:row_range[1]]
         index.add(arr)
         return int(arr.shape[0])
     row_bytes = hdr.shape[1] * 4
@@ -160,8 +163,11 @@ def stream_block_into(index, emb_path: str, chunk_bytes: int = 64 << 20, buffers
     bufs = buffers or [PinnedBuffer(rows_per_chunk * row_bytes) for _ in range(2)]
     rows_per_chunk = min(rows_per_chunk, bufs[0].nbytes // row_bytes)
     L = _lib.lib()
-    n_rows = hdr.shape[0]
-    chunks = [(r, min(rows_per_chunk, n_rows - r)) for r in range(0, n_rows, rows_per_chunk)]
+    lo, hi = (0, hdr.shape[0]) if row_range is None else (max(0, row_range[0]), min(hdr.shape[0], row_range[1]))
+    n_rows = max(0, hi - lo)
+    if n_rows == 0:
+        return 0
+    chunks = [(r, min(rows_per_chunk, hi - r)) for r in range(lo, hi, rows_per_chunk)]
     filled = [threading.Semaphore(0) for _ in bufs]
     freed = [threading.Semaphore(1) for _ in bufs]
     err = []

@@ -97,9 +97,7 @@ def load_resident(index, passage_embeddings_dir, passage_block_num, row_range=No
         else:
             lo, hi = max(row_range[0], seen), min(row_range[1], seen + nb)
             if hi > lo:
-                with open(emb_path, "rb") as h:
-                    arr = pickle.load(h)
-                impl.add(arr[lo - seen:hi - seen])
+                loader.stream_block_into(impl, emb_path, row_range=(lo - seen, hi - seen))
                 ids.append(emb2id[lo - seen:hi - seen])
         seen += nb
         n_blocks += 1
@@ -138,11 +136,15 @@ def rank_pids(retrieved_scores_mat, retrieved_pid_mat, offset2pid, top_k):
 
 def write_trec_run(path, query_ids, ranked, top_k, with_score=True, tag="ance"):
     """Run file exactly as `:273-282` (``with_score=False`` gives the PRJ variant,
-    `/root/reference/src/test_PRJ_topiocqa.py:298-299`).  A query id appearing twice keeps the
-    ranking of its last occurrence at the position of its first, as the reference's dict does."""
+    `/root/reference/src/test_PRJ_topiocqa.py:298-299`).  A query id appearing twice behaves as in the
+    reference (`:240-255`): one list per qid, a later occurrence overwrites its leading slots only."""
     by_qid = {}
     for qid, passages in zip(query_ids, ranked):
-        by_qid[qid] = passages
+        if qid not in by_qid:
+            by_qid[qid] = list(passages)
+        else:
+            n_new = sum(1 for p in passages if p != (0, 0))
+            by_qid[qid][:n_new] = passages[:n_new]
     with open(path, "w") as g:
         for qid, passages in by_qid.items():
             lines = []

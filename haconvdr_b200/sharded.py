@@ -44,6 +44,8 @@ class ShardedFlatIPIndex:
         self._bases = []           # (local_row_start, global_row_start, n) per add
         self._pinned_q = None      # page-locked staging for host queries
         self._pinned_out = None    # page-locked staging for host results
+        self.profile = False       # True: record per-phase CUDA-event times of each search (diagnostics)
+        self.last_phase_ms = None
 
     # -- building the shard ---------------------------------------------------------------------
     def _after_add(self, lo_global: int, n_local: int):
@@ -100,7 +102,13 @@ class ShardedFlatIPIndex:
                 self._pinned_q.copy_(qh)
                 qh = self._pinned_q
             q = qh.to(self._device(), non_blocking=True)
+        prof = self.profile and self._on_gpu() and self.world_size > 1
+        if prof:
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+            ev[0].record()
         D, I = self.local.search(q, k)
+        if prof:
+            ev[1].record()
         if self.world_size > 1:
             if not torch.is_tensor(D):
                 D, I = torch.from_numpy(np.ascontiguousarray(D)), torch.from_numpy(np.ascontiguousarray(I))
@@ -109,7 +117,14 @@ class ShardedFlatIPIndex:
             Ig = torch.empty((self.world_size * nq, k), dtype=I.dtype, device=I.device)
             dist.all_gather_into_tensor(Dg, D.contiguous(), group=self.group)   # rank-major: [G][Q][k]
             dist.all_gather_into_tensor(Ig, I.contiguous(), group=self.group)
+            if prof:
+                ev[2].record()
             D, I = self._merge(Dg.view(self.world_size, nq, k), Ig.view(self.world_size, nq, k), k)
+            if prof:
+                ev[3].record()
+                torch.cuda.synchronize()
+                self.last_phase_ms = {"local_search": ev[0].elapsed_time(ev[1]), "all_gather": ev[1].elapsed_time(ev[2]),
+                                      "merge": ev[2].elapsed_time(ev[3])}
         if as_numpy and torch.is_tensor(D):
             if D.is_cuda:
                 if self._pinned_out is None or self._pinned_out[0].shape != D.shape:

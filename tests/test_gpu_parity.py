@@ -257,3 +257,28 @@ def test_mass_duplicates_recovered_in_careful_mode():
     D, I = idx.search(q[:8], 1000)
     D64, I64 = brute_force_fp64(q[:8], x, 1000)
     assert_parity(D64, I64, D, I, rtol=RTOL, ref_scores_of=_scores_of(q[:8], x))
+
+
+def test_resident_path_to_trec_run_matches_reference_bytes():
+    """Blocks -> HBM-resident shard -> one search -> offset2pid + dedup -> TREC run: byte-identical to the
+    run file the reference's output_test_res wrote for the same inputs (golden)."""
+    import os
+    hb = _engine()
+    from haconvdr_b200 import retrieval
+    g = load_golden("trec_run_dedup_d64")
+    with tempfile.TemporaryDirectory() as tmp:
+        write_blocks(tmp, g["blocks"], 0)
+        idx = hb.FlatIPIndex(64)
+        n_blocks, n_rows = retrieval.load_resident(idx, tmp, 26)
+        assert (n_blocks, n_rows) == (2, 320) and idx.ntotal == 320
+        D, I = retrieval.search_resident(idx, g["q"], g["k"])
+        assert np.array_equal(I, g["I"][:, : g["k"]])
+        ranked = retrieval.rank_pids(D, I, g["offset2pid"].tolist(), g["k"])
+        run = retrieval.write_trec_run(os.path.join(tmp, "run.trec"), g["qids"].tolist(), ranked, g["k"])
+        got, want = open(run).read().split("\n"), str(g["run_text"]).split("\n")
+        assert len(got) == len(want)
+        for a, b in zip(got, want):
+            fa, fb = a.split(" "), b.split(" ")
+            assert fa[:5] == fb[:5] and fa[6:] == fb[6:]                 # qid Q0 pid rank 200-rank ... tag
+            if len(fa) > 5:
+                assert abs(float(fa[5]) - float(fb[5])) <= RTOL * abs(float(fb[5])) + 1e-5
