@@ -47,6 +47,7 @@ def parse_args():
     ap.add_argument("--k", type=int, default=TOP_K)
     ap.add_argument("--cpu-sample-rows", type=int, default=400_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--exchange", default="auto", choices=["auto", "p2p", "nccl"])
     return ap.parse_args()
 
 
@@ -171,7 +172,7 @@ def run_ours(args):
             os.close(saved_fd)
     t_setup = time.perf_counter()
 
-    index = ShardedFlatIPIndex(DIM, FlatIPIndex(DIM, local_rank))
+    index = ShardedFlatIPIndex(DIM, FlatIPIndex(DIM, local_rank), exchange=args.exchange)
     index.add_synthetic(args.rows, seed=42)
     shard_rows = index.local.ntotal
     q_dev = synth_rows_device(args.queries, DIM, seed=4242, device=local_rank)
@@ -280,6 +281,7 @@ def run_ours(args):
         "vs_baseline": None, "dtype": "f16 screen (fp32 accumulate) + f32 exact rescore", "data": "synthetic",
         "config": {"workload": WORKLOAD, "rows": args.rows, "rows_per_gpu": shard_rows, "queries": args.queries,
                    "k": args.k, "dim": DIM, "parallelism": "corpus-shard x%d" % world,
+                   "exchange": ("p2p symmetric-memory merge" if index._symm is not None else "nccl all-gather + merge") if world > 1 else None,
                    "l2": "inputs larger than L2 (%.1f GB of operands streamed per step per GPU)" % (
                        shard_rows * DIM * 2 / 1e9)},
         "e2e": {"value": e2e_qps, "unit": "queries/s", "h2d_bytes_per_step": int(q_host.nbytes),

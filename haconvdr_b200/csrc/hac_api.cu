@@ -717,6 +717,22 @@ int hac_merge_topk_device(int device, int n_lists, int64_t nq, int k, const floa
     return HAC_OK;
 }
 
+int hac_merge_topk_peers_device(int device, int n_lists, int64_t nq, int k, const float* const* D_list_ptrs,
+                                const int64_t* const* I_list_ptrs, int k_out, float* D_out_dev, int64_t* I_out_dev,
+                                void* stream) {
+    if (n_lists <= 0 || n_lists > kMaxPeerLists || nq < 0 || k <= 0 || k_out <= 0 || !D_list_ptrs || !I_list_ptrs ||
+        !D_out_dev || !I_out_dev)
+        return fail(HAC_E_INVALID, "merge_peers: bad argument");
+    if ((int64_t)n_lists * k > 16384) return fail(HAC_E_INVALID, "merge_peers: n_lists * k exceeds 16384");
+    for (int i = 0; i < n_lists; ++i)
+        if (!D_list_ptrs[i] || !I_list_ptrs[i]) return fail(HAC_E_INVALID, "merge_peers: null list pointer");
+    if (nq == 0) return HAC_OK;
+    DeviceGuard guard(device);
+    CU(launch_merge_topk_peers(n_lists, nq, k, D_list_ptrs, I_list_ptrs, k_out, D_out_dev, I_out_dev,
+                               static_cast<cudaStream_t>(stream)));
+    return HAC_OK;
+}
+
 int hac_gather_ids_device(int device, const int64_t* table_dev, int64_t table_n, const int64_t* ids_dev, int64_t n,
                           int64_t* out_dev, void* stream) {
     if (!table_dev || !ids_dev || !out_dev || n < 0) return fail(HAC_E_INVALID, "gather: bad argument");

@@ -7,6 +7,7 @@
 namespace hac {
 
 constexpr int kMaxSegments = 32;
+constexpr int kMaxPeerLists = 16;
 
 // Per-operand statistics kept on the device (written by the convert kernels, read by the
 // margin / scan kernels), so a search never has to synchronise with the host.
@@ -90,6 +91,9 @@ cudaError_t scan_mma_configure();
 // ---- merge / gather ---------------------------------------------------------------------------
 cudaError_t launch_merge_topk(int n_lists, int64_t nq, int k, const float* D_lists, const int64_t* I_lists,
                               int k_out, float* D_out, int64_t* I_out, cudaStream_t s);
+cudaError_t launch_merge_topk_peers(int n_lists, int64_t nq, int k, const float* const* D_ptrs,
+                                    const int64_t* const* I_ptrs, int k_out, float* D_out, int64_t* I_out,
+                                    cudaStream_t s);
 void launch_gather_ids(const int64_t* table, int64_t table_n, const int64_t* ids, int64_t n, int64_t* out,
                        cudaStream_t s);
 

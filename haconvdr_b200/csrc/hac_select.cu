@@ -396,6 +396,71 @@ __global__ void __launch_bounds__(512) merge_topk_kernel(int n_lists, int64_t nq
     }
 }
 
+// Same merge, but every list lives in a different buffer - typically the symmetric-memory result
+// buffers of the peer GPUs, read here directly over NVLink (ld.global on mapped peer pointers), so the
+// cross-shard exchange and the merge are ONE kernel and no staging copy of the candidates exists.
+struct PeerLists {
+    const float* D[kMaxPeerLists];
+    const int64_t* I[kMaxPeerLists];
+};
+
+__global__ void __launch_bounds__(512) merge_topk_peers_kernel(PeerLists lists, int n_lists, int64_t nq, int k,
+                                                               int k_out, float* __restrict__ D_out,
+                                                               int64_t* __restrict__ I_out) {
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    MergeItem* items = reinterpret_cast<MergeItem*>(smem_raw);
+    const int64_t q = blockIdx.x;
+    const int total = n_lists * k;
+    const int P = next_pow2(total);
+    for (int i = threadIdx.x; i < P; i += blockDim.x) {
+        MergeItem it;
+        it.key = 0u;
+        it.pad = 0u;
+        it.id = ~0ull;
+        if (i < total) {
+            const int l = i / k, j = i - l * k;
+            // volatile-free plain loads: the producer ranks finished (cross-GPU barrier) before this launch
+            it.key = float_key(lists.D[l][q * k + j]);
+            it.id = (uint64_t)lists.I[l][q * k + j];
+        }
+        items[i] = it;
+    }
+    bitonic_sort_desc(items, P);
+    for (int j = threadIdx.x; j < k_out; j += blockDim.x) {
+        float score = -FLT_MAX;
+        int64_t id = -1;
+        if (j < total) {
+            score = key_float(items[j].key);
+            id = (int64_t)items[j].id;
+            if (id < 0) score = -FLT_MAX;
+        }
+        D_out[q * k_out + j] = score;
+        I_out[q * k_out + j] = id;
+    }
+}
+
+cudaError_t launch_merge_topk_peers(int n_lists, int64_t nq, int k, const float* const* D_ptrs,
+                                    const int64_t* const* I_ptrs, int k_out, float* D_out, int64_t* I_out,
+                                    cudaStream_t s) {
+    if (n_lists > kMaxPeerLists) return cudaErrorInvalidValue;
+    PeerLists lists;
+    for (int i = 0; i < kMaxPeerLists; ++i) {
+        lists.D[i] = i < n_lists ? D_ptrs[i] : nullptr;
+        lists.I[i] = i < n_lists ? I_ptrs[i] : nullptr;
+    }
+    int P = 2;
+    while (P < n_lists * k) P <<= 1;
+    const size_t smem = (size_t)P * sizeof(MergeItem);
+    if (smem > 200 * 1024) return cudaErrorInvalidValue;
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(merge_topk_peers_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)smem);
+        if (e != cudaSuccess) return e;
+    }
+    merge_topk_peers_kernel<<<(unsigned)nq, 512, smem, s>>>(lists, n_lists, nq, k, k_out, D_out, I_out);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_merge_topk(int n_lists, int64_t nq, int k, const float* D_lists, const int64_t* I_lists,
                               int k_out, float* D_out, int64_t* I_out, cudaStream_t s) {
     int P = 2;

@@ -95,7 +95,9 @@ class FlatIPIndex:
         check(self._lib.hac_set_id_table(self._h, ids.ctypes.data, ids.shape[0]), "hac_set_id_table")
 
     # -- search -------------------------------------------------------------------------------
-    def search(self, q, k: int, path: int = HAC_PATH_AUTO):
+    def search(self, q, k: int, path: int = HAC_PATH_AUTO, out=None):
+        """``out=(D, I)``: optional preallocated CUDA result tensors (float32 / int64 ``[nq, k]``,
+        contiguous) for the tensor path, e.g. views of a symmetric-memory buffer peers read from."""
         k = int(k)
         if k <= 0 or k > HAC_MAX_K:
             raise ValueError("search: k=%d outside [1, %d]" % (k, HAC_MAX_K))
@@ -105,8 +107,14 @@ class FlatIPIndex:
             if q.device.index != self.device:
                 raise ValueError("search: tensor lives on cuda:%s, index on cuda:%d" % (q.device.index, self.device))
             q = q.contiguous().float()
-            D = torch.empty((q.shape[0], k), dtype=torch.float32, device=q.device)
-            I = torch.empty((q.shape[0], k), dtype=torch.int64, device=q.device)
+            if out is not None:
+                D, I = out
+                assert D.is_cuda and I.is_cuda and D.is_contiguous() and I.is_contiguous()
+                assert D.dtype == torch.float32 and I.dtype == torch.int64
+                assert tuple(D.shape) == (q.shape[0], k) and tuple(I.shape) == (q.shape[0], k)
+            else:
+                D = torch.empty((q.shape[0], k), dtype=torch.float32, device=q.device)
+                I = torch.empty((q.shape[0], k), dtype=torch.int64, device=q.device)
             stream = torch.cuda.current_stream(q.device).cuda_stream
             check(self._lib.hac_search_device_ex(self._h, q.shape[0], q.data_ptr(), k, D.data_ptr(), I.data_ptr(),
                                                  stream, int(path)), "hac_search_device")
@@ -144,6 +152,23 @@ def merge_topk_device(D_lists, I_lists, k_out: int):
     check(_lib.lib().hac_merge_topk_device(D_lists.device.index, n_lists, nq, k, D_lists.data_ptr(),
                                            I_lists.data_ptr(), int(k_out), D.data_ptr(), I.data_ptr(), stream),
           "hac_merge_topk_device")
+    return D, I
+
+
+def merge_topk_peers_device(D_ptrs, I_ptrs, nq: int, k: int, k_out: int, device):
+    """Merge lists that live in different buffers (raw device pointers, e.g. the peers' symmetric-memory
+    result buffers, read in-kernel over NVLink) -> ``(D [nq, k_out], I [nq, k_out])`` on ``device``."""
+    import torch
+    n = len(D_ptrs)
+    assert n == len(I_ptrs) and n >= 1
+    dev = torch.device(device)
+    D = torch.empty((nq, k_out), dtype=torch.float32, device=dev)
+    I = torch.empty((nq, k_out), dtype=torch.int64, device=dev)
+    arr_t = ctypes.c_void_p * n
+    stream = torch.cuda.current_stream(dev).cuda_stream
+    check(_lib.lib().hac_merge_topk_peers_device(dev.index, n, nq, k, arr_t(*D_ptrs), arr_t(*I_ptrs), int(k_out),
+                                                 D.data_ptr(), I.data_ptr(), stream),
+          "hac_merge_topk_peers_device")
     return D, I
 
 

@@ -5,8 +5,16 @@ The reference shards its index with faiss ``IndexShards`` (``co.shard = True``,
 host-side merge of the per-shard top-k lists.  Here rank ``r`` of ``G`` owns global rows
 ``[r*N/G, (r+1)*N/G)`` (ids = global offsets through ``set_id_base``), queries are replicated,
 and one search is: local exact top-k on every rank -> ONE all-gather of the ``Q x k``
-(score, id) candidates over NCCL/NVLink -> k-way merge kernel on the device.  The corpus rows
-never cross a link.
+(score, id) candidates -> k-way merge kernel on the device.  The corpus rows never cross a link.
+
+Two exchange implementations:
+  * ``"p2p"`` (default on GPUs when symmetric memory is available): every rank writes its local
+    result straight into a symmetric-memory buffer, one cross-GPU barrier, then ONE merge kernel reads
+    all G peers' lists in place over NVLink (``hac_merge_topk_peers_device``) - no NCCL launch, no
+    staging copy of the candidates.  Buffers alternate between two slots per search, so a single
+    barrier per search orders both the reads and the next overwrite.
+  * ``"nccl"``: ``all_gather_into_tensor`` of scores and ids, then the merge kernel (also the path
+    the gloo CPU tests drive with an injected merge).
 
 The local index and the merge are injected so the partitioning / gather / ordering logic can be
 exercised under ``gloo`` on CPU with the oracle standing in (tests only); the defaults are the
@@ -23,7 +31,7 @@ def shard_bounds(n_rows: int, world_size: int):
 
 
 class ShardedFlatIPIndex:
-    def __init__(self, d: int, local_index=None, device=None, group=None, merge=None):
+    def __init__(self, d: int, local_index=None, device=None, group=None, merge=None, exchange="auto"):
         import torch
         import torch.distributed as dist
         self._torch, self._dist = torch, dist
@@ -44,6 +52,10 @@ class ShardedFlatIPIndex:
         self._bases = []           # (local_row_start, global_row_start, n) per add
         self._pinned_q = None      # page-locked staging for host queries
         self._pinned_out = None    # page-locked staging for host results
+        self.exchange = exchange   # "auto" | "p2p" | "nccl"
+        self._symm = None          # (handle, buffer, nq, k) of the symmetric result buffer
+        self._symm_failed = False
+        self._step = 0
         self.profile = False       # True: record per-phase CUDA-event times of each search (diagnostics)
         self.last_phase_ms = None
 
@@ -106,10 +118,36 @@ class ShardedFlatIPIndex:
         if prof:
             ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
             ev[0].record()
-        D, I = self.local.search(q, k)
-        if prof:
-            ev[1].record()
-        if self.world_size > 1:
+        use_p2p = (self.world_size > 1 and self._on_gpu() and self.exchange in ("auto", "p2p")
+                   and self._ensure_symm(int(q.shape[0]), int(k)))
+        if use_p2p:
+            from .index import merge_topk_peers_device
+            hdl, buf, nq, _ = self._symm
+            slot = self._step & 1
+            self._step += 1
+            d_bytes, i_bytes = nq * k * 4, nq * k * 8
+            slot_bytes = (d_bytes + i_bytes + 255) // 256 * 256
+            off = slot * slot_bytes
+            D_loc = buf[off:off + d_bytes].view(torch.float32).view(nq, k)
+            I_loc = buf[off + d_bytes:off + d_bytes + i_bytes].view(torch.int64).view(nq, k)
+            self.local.search(q, k, out=(D_loc, I_loc))          # results land in the symmetric buffer
+            if prof:
+                ev[1].record()
+            hdl.barrier(channel=0)                               # every rank's lists are complete
+            if prof:
+                ev[2].record()
+            D, I = merge_topk_peers_device([p + off for p in hdl.buffer_ptrs],
+                                           [p + off + d_bytes for p in hdl.buffer_ptrs], nq, k, k, self._device())
+            if prof:
+                ev[3].record()
+                torch.cuda.synchronize()
+                self.last_phase_ms = {"local_search": ev[0].elapsed_time(ev[1]), "barrier": ev[1].elapsed_time(ev[2]),
+                                      "p2p_merge": ev[2].elapsed_time(ev[3])}
+        else:
+            D, I = self.local.search(q, k)
+            if prof:
+                ev[1].record()
+        if self.world_size > 1 and not use_p2p:
             if not torch.is_tensor(D):
                 D, I = torch.from_numpy(np.ascontiguousarray(D)), torch.from_numpy(np.ascontiguousarray(I))
             nq = D.shape[0]
@@ -136,6 +174,30 @@ class ShardedFlatIPIndex:
                 return self._pinned_out[0].numpy().copy(), self._pinned_out[1].numpy().copy()
             return D.numpy(), I.numpy()
         return D, I
+
+    def _ensure_symm(self, nq: int, k: int) -> bool:
+        """Symmetric-memory result buffer (2 slots) for (nq, k); False if unavailable (-> NCCL path)."""
+        if self._symm_failed:
+            return False
+        if self._symm is not None and self._symm[2] == nq and self._symm[3] == k:
+            return True
+        torch, dist = self._torch, self._dist
+        try:
+            import torch.distributed._symmetric_memory as symm_mem
+            slot_bytes = (nq * k * 12 + 255) // 256 * 256
+            with torch.cuda.device(self._device()):
+                buf = symm_mem.empty((2 * slot_bytes,), dtype=torch.uint8, device=self._device())
+                hdl = symm_mem.rendezvous(buf, self.group if self.group is not None else dist.group.WORLD)
+            self._symm = (hdl, buf, nq, k)
+            self._step = 0
+            return True
+        except Exception as e:          # no symmetric memory on this system: use the NCCL exchange
+            if self.exchange == "p2p":
+                raise
+            self._symm_failed = True
+            import warnings
+            warnings.warn("symmetric memory unavailable (%s); using the NCCL all-gather exchange" % (e,))
+            return False
 
     def _on_gpu(self) -> bool:
         return hasattr(self.local, "device") and hasattr(self.local, "_h")

@@ -123,6 +123,14 @@ int hac_merge_topk_device(int device, int n_lists, int64_t nq, int k, const floa
                           const int64_t* I_lists_dev, int k_out, float* D_out_dev,
                           int64_t* I_out_dev, void* stream);
 
+/* Same merge with every list in its own buffer: `D_list_ptrs` / `I_list_ptrs` are HOST arrays of n_lists
+ * (<= 16) DEVICE pointers, each to a [nq][k] list.  With symmetric-memory result buffers these are the
+ * peer GPUs' buffers, read in-kernel over NVLink, so the cross-shard exchange and the merge are one
+ * kernel (the caller orders it after a cross-GPU barrier).  Replaces NCCL all-gather + merge. */
+int hac_merge_topk_peers_device(int device, int n_lists, int64_t nq, int k, const float* const* D_list_ptrs,
+                                const int64_t* const* I_list_ptrs, int k_out, float* D_out_dev,
+                                int64_t* I_out_dev, void* stream);
+
 /* offset -> pid gather on the device (src/test_HAConvDR_topiocqa.py:250): out[i] =
  * table[ids[i]] for ids >= 0, -1 otherwise.  table/ids/out are device pointers. */
 int hac_gather_ids_device(int device, const int64_t* table_dev, int64_t table_n, const int64_t* ids_dev,

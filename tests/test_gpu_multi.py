@@ -36,6 +36,17 @@ x64 = x.astype(np.float64)
 assert_parity(D64, I64, D, I, rtol=1e-5, ref_scores_of=lambda qi, ids: x64[ids] @ q[qi].astype(np.float64))
 Dd, Id = idx.search(torch.from_numpy(q).cuda(), 100)
 assert np.array_equal(Id.cpu().numpy(), I) and np.array_equal(Dd.cpu().numpy(), D)
+# both exchange implementations (symmetric-memory P2P merge, NCCL all-gather + merge) agree bitwise
+assert idx._symm is not None, "P2P exchange was not used"
+idx.exchange = "nccl"
+Dn, In = idx.search(q, 100)
+assert np.array_equal(In, I) and np.array_equal(Dn, D)
+idx.exchange = "p2p"
+for _ in range(3):                      # alternating slots
+    Dp, Ip = idx.search(q, 100)
+    assert np.array_equal(Ip, I) and np.array_equal(Dp, D)
+idx.exchange = "auto"
+
 # synthetic shards reproduce the same global corpus for any world size
 idx.reset()
 idx.add_synthetic(100000, seed=42)
