@@ -282,3 +282,59 @@ def test_resident_path_to_trec_run_matches_reference_bytes():
             assert fa[:5] == fb[:5] and fa[6:] == fb[6:]                 # qid Q0 pid rank 200-rank ... tag
             if len(fa) > 5:
                 assert abs(float(fa[5]) - float(fb[5])) <= RTOL * abs(float(fb[5])) + 1e-5
+
+
+def test_query_batches_beyond_the_internal_batch_size():
+    """More queries than one internal batch (16384): results of every sub-batch land at the right offset."""
+    hb = _engine()
+    rng = np.random.default_rng(31)
+    x = rng.standard_normal((3000, 768), dtype=np.float32)
+    q = rng.standard_normal((16384 + 700, 768), dtype=np.float32)
+    idx = hb.FlatIPIndex(768)
+    idx.add(x)
+    D, I = idx.search(q, 5)
+    sel = np.r_[0:50, 16300:16450, 17000:17084]
+    _check(q[sel], x, 5, D[sel], I[sel], also_fp32_oracle=False)
+
+
+def test_operand_scaling_extreme_magnitudes():
+    """Power-of-two operand scaling keeps the f16 screen usable for tiny and huge embeddings."""
+    hb = _engine()
+    rng = np.random.default_rng(33)
+    base_x = rng.standard_normal((20000, 768), dtype=np.float32)
+    base_q = rng.standard_normal((70, 768), dtype=np.float32)
+    for sx, sq in ((1e-6, 1.0), (3e4, 1e-3), (1.0, 5e3)):
+        x, q = (base_x * np.float32(sx)), (base_q * np.float32(sq))
+        idx = hb.FlatIPIndex(768)
+        idx.add(x)
+        D, I = idx.search(q, 50)
+        st = idx.stats()
+        assert st["retries"] == 0 and st["screen_err_max"] <= st["margin_max"], (sx, sq, st)
+        _check(q, x, 50, D, I, also_fp32_oracle=False)
+
+
+def test_all_zero_corpus_is_one_big_tie():
+    hb = _engine()
+    x = np.zeros((9000, 768), np.float32)
+    q = np.random.default_rng(2).standard_normal((10, 768), dtype=np.float32)
+    idx = hb.FlatIPIndex(768)
+    idx.add(x)
+    D, I = idx.search(q, 100)
+    assert np.array_equal(I, np.tile(np.arange(100), (10, 1))) and np.all(D == 0)
+
+
+def test_device_api_on_a_side_stream():
+    import torch
+    hb = _engine()
+    rng = np.random.default_rng(41)
+    x = rng.standard_normal((40000, 768), dtype=np.float32)
+    q = rng.standard_normal((200, 768), dtype=np.float32)
+    idx = hb.FlatIPIndex(768)
+    side = torch.cuda.Stream()
+    with torch.cuda.stream(side):
+        xd = torch.from_numpy(x).cuda(non_blocking=True)
+        idx.add(xd)
+        qd = torch.from_numpy(q).cuda(non_blocking=True) * 1.0        # produced on the side stream
+        D, I = idx.search(qd, 100)
+        Dh, Ih = D.cpu().numpy(), I.cpu().numpy()
+    _check(q, x, 100, Dh, Ih, also_fp32_oracle=False)
