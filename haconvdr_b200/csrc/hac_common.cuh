@@ -56,7 +56,7 @@ __device__ __forceinline__ float lane_fma4(float acc, const float4 a, const floa
 
 // order-preserving float <-> uint key (larger float -> larger key)
 __device__ __forceinline__ uint32_t float_key(float f) {
-    uint32_t u = __float_as_uint(f);
+    uint32_t u = __float_as_uint(f + 0.0f);   // -0.0 and +0.0 are the same score: one key
     return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
 }
 __device__ __forceinline__ float key_float(uint32_t k) {
@@ -73,17 +73,6 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
 }
 __device__ __forceinline__ void fence_barrier_init() {
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    asm volatile(
-        "{\n\t.reg .pred P1;\n\t"
-        "WAIT_LOOP:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, 0x989680;\n\t"
-        "@P1 bra DONE;\n\t"
-        "bra WAIT_LOOP;\n\t"
-        "DONE:\n\t}" ::"r"(smem_u32(bar)),
-        "r"(parity)
-        : "memory");
 }
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -111,39 +100,6 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, u
                  "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
 }
-// as above with an L2 eviction-priority hint
-__device__ __forceinline__ void bulk_g2s_hint(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar,
-                                              uint64_t policy) {
-    asm volatile(
-        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::
-            "r"(smem_u32(smem_dst)),
-        "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
-        : "memory");
-}
-// destination and barrier given as shared::cluster addresses (2-CTA kernels signal the leader's barrier)
-__device__ __forceinline__ void bulk_g2s_cluster(uint32_t smem_dst_cluster, const void* gmem_src, uint32_t bytes,
-                                                 uint32_t bar_cluster) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                     smem_dst_cluster),
-                 "l"(gmem_src), "r"(bytes), "r"(bar_cluster)
-                 : "memory");
-}
-__device__ __forceinline__ uint64_t l2_policy_evict_last() {
-    uint64_t p;
-    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
-    return p;
-}
-__device__ __forceinline__ uint64_t l2_policy_evict_first() {
-    uint64_t p;
-    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
-    return p;
-}
-__device__ __forceinline__ uint32_t mapa_u32(uint32_t smem_addr, uint32_t cta) {
-    uint32_t r;
-    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(cta));
-    return r;
-}
-
 // ------------------------------------------------------------------------------------------
 // PTX: tcgen05 (5th-gen tensor cores) and tensor memory
 // ------------------------------------------------------------------------------------------

@@ -350,50 +350,73 @@ void launch_fill_empty(float* D, int64_t* I, int64_t n, cudaStream_t s) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// k-way merge of n_lists sorted lists per query (shards or corpus blocks) on the device.
+// k-way merge of n_lists SORTED lists per query (shards or corpus blocks) on the device, by rank
+// computation instead of a sort: the final position of an item is its position in its own list plus,
+// for every other list, the number of items there that rank before it (binary search) - one pass,
+// no sorting network, no barriers between steps.  Order: (score desc, id asc, list asc); fillers
+// (id -1, score -FLT_MAX) sort last.
 struct MergeItem {
     uint32_t key;
-    uint32_t pad;
+    uint32_t list;
     uint64_t id;   // int64 id viewed unsigned: fillers (-1) sort last among equal scores
-    __device__ bool operator<(const MergeItem& o) const {   // "ranks after"
-        return key < o.key || (key == o.key && id > o.id);
-    }
 };
+__device__ __forceinline__ bool ranks_before(const MergeItem& a, const MergeItem& b) {
+    if (a.key != b.key) return a.key > b.key;
+    if (a.id != b.id) return a.id < b.id;
+    return a.list < b.list;
+}
 
-__global__ void __launch_bounds__(512) merge_topk_kernel(int n_lists, int64_t nq, int k,
-                                                         const float* __restrict__ D_lists,
-                                                         const int64_t* __restrict__ I_lists, int k_out,
-                                                         float* __restrict__ D_out, int64_t* __restrict__ I_out) {
+__device__ __forceinline__ void merge_by_rank(const MergeItem* items, int n_lists, int k, int k_out, float* D_out,
+                                              int64_t* I_out) {
+    const int total = n_lists * k;
+    for (int i = threadIdx.x; i < total; i += blockDim.x) {
+        const MergeItem me = items[i];
+        const int l = i / k;
+        int rank = i - l * k;
+        for (int o = 0; o < n_lists; ++o) {
+            if (o == l) continue;
+            const MergeItem* other = items + o * k;
+            int lo = 0, hi = k;                       // first position of `other` that does not rank before me
+            while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                if (ranks_before(other[mid], me)) lo = mid + 1; else hi = mid;
+            }
+            rank += lo;
+        }
+        if (rank < k_out) {
+            const int64_t id = (int64_t)me.id;
+            D_out[rank] = id < 0 ? -FLT_MAX : key_float(me.key);
+            I_out[rank] = id;
+        }
+    }
+    for (int j = total + threadIdx.x; j < k_out; j += blockDim.x) {
+        D_out[j] = -FLT_MAX;
+        I_out[j] = -1;
+    }
+}
+
+constexpr int kMergeThreads = 256;
+
+__global__ void __launch_bounds__(kMergeThreads) merge_topk_kernel(int n_lists, int64_t nq, int k,
+                                                                   const float* __restrict__ D_lists,
+                                                                   const int64_t* __restrict__ I_lists, int k_out,
+                                                                   float* __restrict__ D_out,
+                                                                   int64_t* __restrict__ I_out) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     MergeItem* items = reinterpret_cast<MergeItem*>(smem_raw);
     const int64_t q = blockIdx.x;
     const int total = n_lists * k;
-    const int P = next_pow2(total);
-    for (int i = threadIdx.x; i < P; i += blockDim.x) {
+    for (int i = threadIdx.x; i < total; i += blockDim.x) {
+        const int l = i / k, j = i - l * k;
+        const size_t src = ((size_t)l * nq + q) * k + j;
         MergeItem it;
-        it.key = 0u;
-        it.pad = 0u;
-        it.id = ~0ull;
-        if (i < total) {
-            const int l = i / k, j = i - l * k;
-            const size_t src = ((size_t)l * nq + q) * k + j;
-            it.key = float_key(D_lists[src]);
-            it.id = (uint64_t)I_lists[src];
-        }
+        it.key = float_key(D_lists[src]);
+        it.list = (uint32_t)l;
+        it.id = (uint64_t)I_lists[src];
         items[i] = it;
     }
-    bitonic_sort_desc(items, P);
-    for (int j = threadIdx.x; j < k_out; j += blockDim.x) {
-        float score = -FLT_MAX;
-        int64_t id = -1;
-        if (j < total) {
-            score = key_float(items[j].key);
-            id = (int64_t)items[j].id;
-            if (id < 0) score = -FLT_MAX;
-        }
-        D_out[q * k_out + j] = score;
-        I_out[q * k_out + j] = id;
-    }
+    __syncthreads();
+    merge_by_rank(items, n_lists, k, k_out, D_out + q * k_out, I_out + q * k_out);
 }
 
 // Same merge, but every list lives in a different buffer - typically the symmetric-memory result
@@ -404,39 +427,25 @@ struct PeerLists {
     const int64_t* I[kMaxPeerLists];
 };
 
-__global__ void __launch_bounds__(512) merge_topk_peers_kernel(PeerLists lists, int n_lists, int64_t nq, int k,
-                                                               int k_out, float* __restrict__ D_out,
-                                                               int64_t* __restrict__ I_out) {
+__global__ void __launch_bounds__(kMergeThreads) merge_topk_peers_kernel(PeerLists lists, int n_lists, int64_t nq,
+                                                                         int k, int k_out,
+                                                                         float* __restrict__ D_out,
+                                                                         int64_t* __restrict__ I_out) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     MergeItem* items = reinterpret_cast<MergeItem*>(smem_raw);
     const int64_t q = blockIdx.x;
     const int total = n_lists * k;
-    const int P = next_pow2(total);
-    for (int i = threadIdx.x; i < P; i += blockDim.x) {
+    for (int i = threadIdx.x; i < total; i += blockDim.x) {
+        const int l = i / k, j = i - l * k;
         MergeItem it;
-        it.key = 0u;
-        it.pad = 0u;
-        it.id = ~0ull;
-        if (i < total) {
-            const int l = i / k, j = i - l * k;
-            // volatile-free plain loads: the producer ranks finished (cross-GPU barrier) before this launch
-            it.key = float_key(lists.D[l][q * k + j]);
-            it.id = (uint64_t)lists.I[l][q * k + j];
-        }
+        // plain loads of peer memory: the producer ranks finished (cross-GPU barrier) before this launch
+        it.key = float_key(lists.D[l][q * k + j]);
+        it.list = (uint32_t)l;
+        it.id = (uint64_t)lists.I[l][q * k + j];
         items[i] = it;
     }
-    bitonic_sort_desc(items, P);
-    for (int j = threadIdx.x; j < k_out; j += blockDim.x) {
-        float score = -FLT_MAX;
-        int64_t id = -1;
-        if (j < total) {
-            score = key_float(items[j].key);
-            id = (int64_t)items[j].id;
-            if (id < 0) score = -FLT_MAX;
-        }
-        D_out[q * k_out + j] = score;
-        I_out[q * k_out + j] = id;
-    }
+    __syncthreads();
+    merge_by_rank(items, n_lists, k, k_out, D_out + q * k_out, I_out + q * k_out);
 }
 
 cudaError_t launch_merge_topk_peers(int n_lists, int64_t nq, int k, const float* const* D_ptrs,
@@ -448,30 +457,26 @@ cudaError_t launch_merge_topk_peers(int n_lists, int64_t nq, int k, const float*
         lists.D[i] = i < n_lists ? D_ptrs[i] : nullptr;
         lists.I[i] = i < n_lists ? I_ptrs[i] : nullptr;
     }
-    int P = 2;
-    while (P < n_lists * k) P <<= 1;
-    const size_t smem = (size_t)P * sizeof(MergeItem);
+    const size_t smem = (size_t)n_lists * k * sizeof(MergeItem);
     if (smem > 200 * 1024) return cudaErrorInvalidValue;
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(merge_topk_peers_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              (int)smem);
         if (e != cudaSuccess) return e;
     }
-    merge_topk_peers_kernel<<<(unsigned)nq, 512, smem, s>>>(lists, n_lists, nq, k, k_out, D_out, I_out);
+    merge_topk_peers_kernel<<<(unsigned)nq, kMergeThreads, smem, s>>>(lists, n_lists, nq, k, k_out, D_out, I_out);
     return cudaGetLastError();
 }
 
 cudaError_t launch_merge_topk(int n_lists, int64_t nq, int k, const float* D_lists, const int64_t* I_lists,
                               int k_out, float* D_out, int64_t* I_out, cudaStream_t s) {
-    int P = 2;
-    while (P < n_lists * k) P <<= 1;
-    const size_t smem = (size_t)P * sizeof(MergeItem);
+    const size_t smem = (size_t)n_lists * k * sizeof(MergeItem);
     if (smem > 200 * 1024) return cudaErrorInvalidValue;
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(merge_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
     }
-    merge_topk_kernel<<<(unsigned)nq, 512, smem, s>>>(n_lists, nq, k, D_lists, I_lists, k_out, D_out, I_out);
+    merge_topk_kernel<<<(unsigned)nq, kMergeThreads, smem, s>>>(n_lists, nq, k, D_lists, I_lists, k_out, D_out, I_out);
     return cudaGetLastError();
 }
 

@@ -115,9 +115,9 @@ int hac_search_device_ex(hac_index* idx, int64_t nq, const float* q_dev, int k, 
                          int64_t* I_dev, void* stream, int path);
 
 /* ---- cross-shard / cross-block merge ----------------------------------------------------------
- * Merges `n_lists` sorted top-k lists per query (laid out [n_lists][nq][k], device memory)
- * into one top-k_out list per query by (score desc, id asc); earlier lists win exact ties on
- * equal ids only through the id order.  Replaces faiss IndexShards' host merge and the
+ * Merges `n_lists` top-k lists per query (laid out [n_lists][nq][k], device memory), each already
+ * sorted by (score desc, id asc) as hac_search returns them, into one top-k_out list per query by
+ * (score desc, id asc, list asc).  Replaces faiss IndexShards' host merge and the
  * reference's pure-Python pairwise merge (src/test_HAConvDR_topiocqa.py:126-149). */
 int hac_merge_topk_device(int device, int n_lists, int64_t nq, int k, const float* D_lists_dev,
                           const int64_t* I_lists_dev, int k_out, float* D_out_dev,

@@ -338,3 +338,32 @@ def test_device_api_on_a_side_stream():
         D, I = idx.search(qd, 100)
         Dh, Ih = D.cpu().numpy(), I.cpu().numpy()
     _check(q, x, 100, Dh, Ih, also_fp32_oracle=False)
+
+
+@pytest.mark.parametrize("n_lists,k,k_out", [(2, 100, 100), (8, 100, 100), (3, 7, 20), (8, 1000, 1000), (5, 1, 1)])
+def test_device_merge_against_numpy(n_lists, k, k_out):
+    """hac_merge_topk_device on sorted lists with exact ties and filler slots."""
+    import torch
+    from haconvdr_b200.index import merge_topk_device
+    rng = np.random.default_rng(n_lists * 1000 + k)
+    nq = 37
+    D = np.round(rng.standard_normal((n_lists, nq, k)) * 4).astype(np.float32)        # coarse values -> many ties
+    I = rng.permutation(n_lists * nq * k).reshape(n_lists, nq, k).astype(np.int64)   # unique ids
+    fill = rng.integers(0, k + 1, size=(n_lists, nq))                                 # valid entries per list
+    for l in range(n_lists):
+        for qi in range(nq):
+            D[l, qi, fill[l, qi]:] = NEG_FLT_MAX
+            I[l, qi, fill[l, qi]:] = -1
+            order = np.lexsort((np.where(I[l, qi] < 0, np.iinfo(np.int64).max, I[l, qi]), -D[l, qi].astype(np.float64)))
+            D[l, qi], I[l, qi] = D[l, qi][order], I[l, qi][order]
+    Dm, Im = merge_topk_device(torch.from_numpy(D).cuda(), torch.from_numpy(I).cuda(), k_out)
+    catD = D.transpose(1, 0, 2).reshape(nq, -1)
+    catI = I.transpose(1, 0, 2).reshape(nq, -1)
+    order = np.lexsort((np.where(catI < 0, np.iinfo(np.int64).max, catI), -catD.astype(np.float64)), axis=1)
+    wantD, wantI = np.take_along_axis(catD, order, 1), np.take_along_axis(catI, order, 1)
+    if k_out > catD.shape[1]:
+        pad = k_out - catD.shape[1]
+        wantD = np.concatenate([wantD, np.full((nq, pad), NEG_FLT_MAX, np.float32)], 1)
+        wantI = np.concatenate([wantI, np.full((nq, pad), -1, np.int64)], 1)
+    assert np.array_equal(Im.cpu().numpy(), wantI[:, :k_out])
+    assert np.array_equal(Dm.cpu().numpy(), wantD[:, :k_out])
