@@ -259,8 +259,13 @@ def run_ours(args):
     flops_per_launch_set = 2.0 * args.queries * shard_rows * DIM        # algorithmic, per search per rank
     achieved = flops_per_launch_set / (scan_ms_step * 1e-3) / 1e12
     peak = float(peaks.get("bf16_tflops_sustained", 1400.0))
+    # DRAM traffic of the scan kernel from the committed `ncu --set full` capture
+    # (profiles/r01_ncu_scan_mma_v3_summary.txt): 29.70 GB read + 0.05 GB written by the launch that covers
+    # 19 300 592 rows, i.e. 1539 B per corpus row against 1536 B algorithmic (f16 row): the corpus is read once.
+    traffic = 1539.0 * shard_rows
     roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                "traffic": None, "peak_source": "%s bf16_tflops_sustained (f16 and bf16 share the tensor-pipe rate)" % peak_kind,
+                "traffic": traffic, "traffic_note": "DRAM bytes per search per GPU, scaled from the ncu capture of the "
+                "largest launch (29.70 GB for 19.3M rows); algorithmic operand bytes %.2f GB" % (shard_rows * 1536 / 1e9), "peak_source": "%s bf16_tflops_sustained (f16 and bf16 share the tensor-pipe rate)" % peak_kind,
                 "kernel": "scan_mma_kernel", "kernel_ms_per_step": scan_ms_step,
                 "kernel_share_of_step": scan_ms_step / ms_per_step}
 
@@ -278,7 +283,7 @@ def run_ours(args):
     line = {
         "metric": METRIC, "value": qps, "unit": "queries/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
-        "vs_baseline": None, "dtype": "f16 screen (fp32 accumulate) + f32 exact rescore", "data": "synthetic",
+        "vs_baseline": None, "dtype": "f16 screen (f32 accumulate) + f32 exact rescore", "data": "synthetic",
         "config": {"workload": WORKLOAD, "rows": args.rows, "rows_per_gpu": shard_rows, "queries": args.queries,
                    "k": args.k, "dim": DIM, "parallelism": "corpus-shard x%d" % world,
                    "exchange": ("p2p symmetric-memory merge" if index._symm is not None else "nccl all-gather + merge") if world > 1 else None,
