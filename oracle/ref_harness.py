@@ -38,11 +38,16 @@ def load_reference_module(name: str = "test_HAConvDR_topiocqa"):
     stub("IPython", embed=lambda *a, **k: None)
     stub("faiss")
     stub("pytrec_eval")
-    stub("models", ANCE=dummy)
-    stub("utils", check_dir_exist_or_build=None, pstore=None, pload=None, set_seed=None, get_optimizer=None)
+    stub("models", ANCE=dummy, load_model=None)
+    stub("utils", check_dir_exist_or_build=None, pstore=None, pload=None, set_seed=None, get_optimizer=None,
+         split_and_padding_neighbor=None)
+    stub("preprocess_topiocqa", load_collection=None)
+    stub("preprocess_qrecc", load_collection=None)
+    stub("toml")
     stub("data", padding_seq_to_same_length=None, Retrieval_topiocqa=dummy, Retrieval_topiocqa_old=dummy,
          Retrieval_qrecc=dummy, Retrieval_qrecc_old=dummy, Retrieval_qrecc_new=dummy,
-         Retrieval_topiocqa_new=dummy)
+         Retrieval_topiocqa_new=dummy, ConvDataset=dummy, ConvDataset_topiocqa=dummy,
+         ConvDataset_topiocqa_rel=dummy, ConvDataset_qrecc=dummy, ConvDataset_qrecc_rel=dummy)
     saved = {k: sys.modules.get(k) for k in stubs}
     sys.modules.update(stubs)
     try:

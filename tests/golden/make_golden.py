@@ -57,7 +57,38 @@ def contiguous_ids(blocks, start=0):
     return out
 
 
+def make_prj():
+    """H. the PRJ drivers' copy of the loop and their score-less run file
+    (`/root/reference/src/test_PRJ_topiocqa.py:83-171`, `:218-299`; qrecc twin identical)."""
+    mod = ref_harness.load_reference_module("test_PRJ_topiocqa")
+    mod_q = ref_harness.load_reference_module("test_PRJ_qrecc")
+    rng = np.random.default_rng(777)
+    blocks = [rng.standard_normal((n, 64)).astype(np.float32) for n in (140, 160, 90)]
+    q = rng.standard_normal((8, 64)).astype(np.float32)
+    k = 12
+    D, I = run_reference(mod, blocks, contiguous_ids(blocks), q, k)
+    D2, I2 = run_reference(mod_q, blocks, contiguous_ids(blocks), q, k)
+    assert np.array_equal(D, D2) and np.array_equal(I, I2)
+    offset2pid = [int(v) for v in rng.integers(0, 80, size=390)]
+    qids = ["%d-%d-%d" % (i // 4 + 1, i % 4 + 2, i % 4) for i in range(len(q))]       # conv-turn-historyturn
+    with tempfile.TemporaryDirectory() as d:
+        test_file = os.path.join(d, "test.json")
+        with open(test_file, "w") as f:
+            for s in qids:
+                f.write(json.dumps({"id": s, "query": "q", "conv_id": 1, "turn_id": 1, "query_pair": "p"}) + "\n")
+        mod.print_trec_res = lambda *a, **kw: {}
+        args = types.SimpleNamespace(top_n=k, test_file_path=test_file, qrel_output_path=d,
+                                     trec_gold_qrel_file_path="", rel_threshold=1)
+        mod.output_test_res(qids, D, I, offset2pid, args)
+        with open(os.path.join(d, "dev_dense_rel_res.trec")) as f:
+            run_text = f.read()
+    save("prj_run_d64", x0=blocks[0], x1=blocks[1], x2=blocks[2], q=q, k=np.int64(k), D=D, I=I,
+         offset2pid=np.asarray(offset2pid, np.int64), qids=np.asarray(qids), run_text=np.asarray(run_text))
+
+
 def main():
+    if "--only-prj" in sys.argv:
+        return make_prj()
     mod = ref_harness.load_reference_module("test_HAConvDR_topiocqa")
     mod_q = ref_harness.load_reference_module("test_HAConvDR_qrecc")
     rng = np.random.default_rng(20241018)
@@ -131,6 +162,7 @@ def main():
             run_text = f.read()
     save("trec_run_dedup_d64", x0=blocks[0], x1=blocks[1], q=q, k=np.int64(k), D=D, I=I,
          offset2pid=np.asarray(offset2pid, np.int64), qids=np.asarray(qids), run_text=np.asarray(run_text))
+    make_prj()
 
 
 if __name__ == "__main__":

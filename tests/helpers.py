@@ -33,5 +33,5 @@ def write_blocks(dirname, blocks, id_start=0):
 GOLDEN_MERGE_CASES = [
     "kat_int_d768_1block", "merge_3blocks_d64", "merge_ties_across_blocks_d64",
     "short_single_block_d64", "short_two_blocks_d64", "block_num_limit_d64", "single_query_k1_d128",
-    "trec_run_dedup_d64",
+    "trec_run_dedup_d64", "prj_run_d64",
 ]

@@ -82,6 +82,15 @@ def test_rank_pids_and_trec_writer_match_reference_run():
     assert "".join(trec_lines(g["qids"].tolist(), ranked, g["k"])) == str(g["run_text"])
 
 
+def test_prj_run_file_without_score_column_matches_reference():
+    """The PRJ drivers (`src/test_PRJ_topiocqa.py:218-299`) write the run file without the score column."""
+    g = load_golden("prj_run_d64")
+    ranked = retrieval.rank_pids(g["D"], g["I"], g["offset2pid"].tolist(), g["k"])
+    with tempfile.TemporaryDirectory() as d:
+        p = retrieval.write_trec_run(os.path.join(d, "run.trec"), g["qids"].tolist(), ranked, g["k"], with_score=False)
+        assert open(p).read() == str(g["run_text"])
+
+
 def test_faiss_compat_surface_builds_without_gpu():
     from haconvdr_b200 import faiss_compat as faiss
     res = faiss.StandardGpuResources()

@@ -40,6 +40,14 @@ def test_trec_lines_match_reference_run_file():
     assert "".join(trec_lines(g["qids"].tolist(), ranked, g["k"])) == str(g["run_text"])
 
 
+def test_prj_golden_uses_the_same_loop():
+    g = load_golden("prj_run_d64")
+    with tempfile.TemporaryDirectory() as d:
+        write_blocks(d, g["blocks"], 0)
+        D, I = search_one_by_one(10, d, FlatIP(64), g["q"], g["k"])
+    assert np.array_equal(I, g["I"])
+
+
 def test_flat_ip_against_fp64_arbiter_and_c_port():
     rng = np.random.default_rng(7)
     x = rng.standard_normal((5000, 768), dtype=np.float32)
