@@ -8,7 +8,7 @@ Public surface:
   retrieval              search_one_by_one (reference loop), search_resident, offset2pid, TREC writer
   loader                 block-pickle loader (pinned staging -> HBM)
 """
-from ._lib import HAC_MAX_K, HAC_PATH_AUTO, HAC_PATH_GEMV, HAC_PATH_MMA  # noqa: F401
+from ._lib import HAC_MAX_K, HAC_PATH_AUTO, HAC_PATH_GEMV, HAC_PATH_I8, HAC_PATH_MMA  # noqa: F401
 from .index import FlatIPIndex  # noqa: F401
 
-__all__ = ["FlatIPIndex", "HAC_PATH_AUTO", "HAC_PATH_GEMV", "HAC_PATH_MMA", "HAC_MAX_K"]
+__all__ = ["FlatIPIndex", "HAC_PATH_AUTO", "HAC_PATH_GEMV", "HAC_PATH_MMA", "HAC_PATH_I8", "HAC_MAX_K"]

@@ -14,7 +14,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libhacidx.so")
 CSRC = os.path.join(_HERE, "csrc")
 
-HAC_PATH_AUTO, HAC_PATH_GEMV, HAC_PATH_MMA = 0, 1, 2
+HAC_PATH_AUTO, HAC_PATH_GEMV, HAC_PATH_MMA, HAC_PATH_I8 = 0, 1, 2, 3
 HAC_MAX_K = 1024
 
 c_i64 = ctypes.c_int64

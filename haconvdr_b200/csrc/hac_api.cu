@@ -44,6 +44,8 @@ int64_t round_up(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
 struct Segment {
     float* rows = nullptr;        // [cap_rows][d] fp32
     uint8_t* shadow = nullptr;    // f16 tiled image of the same rows
+    uint8_t* shadow8 = nullptr;   // int8 tiled image (d % 128 == 0 only)
+    TileQ8* tiles8 = nullptr;     // per-128-row-tile constants of the int8 image
     OperandStats* stats = nullptr;
     int64_t cap_rows = 0;
     int64_t n_rows = 0;
@@ -57,6 +59,8 @@ struct Workspace {
     int d = 0;
     float* q = nullptr;           // device copy of host queries
     uint8_t* q_shadow = nullptr;
+    uint8_t* q_shadow8 = nullptr;
+    QueryQ8* q_consts = nullptr;
     OperandStats* q_stats = nullptr;
     float *q_norm = nullptr, *q_err = nullptr, *margin = nullptr, *tau = nullptr, *thr = nullptr;
     float* scalars = nullptr;     // [0] absmax scratch, [1] margin_max, [2] screen_err_max
@@ -87,6 +91,12 @@ struct hac_index {
     bool mma_configured = false;
     int mma_cta_group = 1;                  // 2 = CTA-pair variant (measured equal within noise; HAC_MMA_CTA_GROUP / hac_set_option)
     double chunk_growth = 4.0;              // chunk i+1 = growth * rows seen so far
+    // f16 image: low mantissa bits forced to zero (corpus / queries).  The scan is power-limited and the tensor
+    // core draws less with sparser mantissas: 3 dropped corpus bits (an 8-bit significand) run the scan 5 %
+    // faster (76.3 -> 72.0 ms measured); the margin grows 0.76 -> 2.3 and 1.6x more rows are rescored (0.2 ms).
+    int drop_bits_x = 3, drop_bits_q = 0;
+    bool build_i8 = false;                  // keep an int8 image of the corpus too (rows*d bytes; HAC_PATH_I8)
+    int default_path = HAC_PATH_MMA;        // what HAC_PATH_AUTO resolves to
 };
 
 namespace {
@@ -109,11 +119,15 @@ __global__ void merge_stats_kernel(OperandStats* dst, const OperandStats* src) {
     dst->norm_max = fmaxf(dst->norm_max, src->norm_max);
     dst->hat_norm_max = fmaxf(dst->hat_norm_max, src->hat_norm_max);
     dst->err_norm_max = fmaxf(dst->err_norm_max, src->err_norm_max);
+    dst->i8_beta_max = fmaxf(dst->i8_beta_max, src->i8_beta_max);
+    dst->i8_gamma_max = fmaxf(dst->i8_gamma_max, src->i8_gamma_max);
 }
 
 void free_segment(Segment& s) {
     if (s.rows) cudaFree(s.rows);
     if (s.shadow) cudaFree(s.shadow);
+    if (s.shadow8) cudaFree(s.shadow8);
+    if (s.tiles8) cudaFree(s.tiles8);
     if (s.stats) cudaFree(s.stats);
     s = Segment{};
 }
@@ -124,6 +138,10 @@ int alloc_segment(hac_index* idx, int64_t cap_rows, Segment* out) {
     cudaError_t e = cudaMalloc(&s.rows, (size_t)s.cap_rows * idx->d * sizeof(float));
     if (e == cudaSuccess) e = cudaMalloc(&s.shadow, (size_t)shadow_bytes(s.cap_rows, idx->d));
     if (e == cudaSuccess) e = cudaMalloc(&s.stats, sizeof(OperandStats));
+    if (e == cudaSuccess && idx->d % kBlockK8 == 0 && idx->build_i8) {
+        e = cudaMalloc(&s.shadow8, (size_t)shadow8_bytes(s.cap_rows, idx->d));
+        if (e == cudaSuccess) e = cudaMalloc(&s.tiles8, (size_t)shadow_tiles(s.cap_rows) * sizeof(TileQ8));
+    }
     if (e != cudaSuccess) {
         free_segment(s);
         return fail_cuda(e, "segment allocation");
@@ -203,7 +221,13 @@ int add_rows(hac_index* idx, int64_t n, const float* src, RowSource kind, cudaSt
         launch_pick_scale(seg->stats, idx->add_scratch, /*keep_scale=*/seg->n_rows > 0 ? 1 : 0, s);
         const int64_t end = seg->n_rows + m;
         const int64_t n_pad = std::min(round_up(end, kRowAlign), seg->cap_rows) - seg->n_rows;
-        launch_convert_rows(dst, m, n_pad, d, seg->shadow, seg->n_rows, seg->stats, nullptr, nullptr, s);
+        launch_convert_rows(dst, m, n_pad, d, seg->shadow, seg->n_rows, seg->stats, nullptr, nullptr, idx->drop_bits_x, s);
+        if (seg->shadow8 != nullptr) {
+            // whole tiles are rebuilt from the fp32 rows (an append into a partly filled tile changes its scale)
+            launch_convert_tiles_i8(seg->rows, end, d, seg->n_rows / kTileRows,
+                                    std::min(round_up(end, kRowAlign), seg->cap_rows) / kTileRows, seg->shadow8,
+                                    seg->tiles8, seg->stats, s);
+        }
         merge_stats_kernel<<<1, 1, 0, s>>>(idx->corpus_stats, seg->stats);
         CU(cudaGetLastError());
         seg->n_rows = end;
@@ -222,7 +246,7 @@ uint32_t cap_for_k(int k, int level) {
 }
 
 void free_workspace(Workspace& w) {
-    void* ptrs[] = {w.q, w.q_shadow, w.q_stats, w.q_norm, w.q_err, w.margin, w.tau, w.thr, w.scalars, w.counters,
+    void* ptrs[] = {w.q, w.q_shadow, w.q_shadow8, w.q_consts, w.q_stats, w.q_norm, w.q_err, w.margin, w.tau, w.thr, w.scalars, w.counters,
                     w.cb.score, w.cb.row, w.cb.exact, w.cb.count, w.cb.sorted, w.cb.overflow, w.D, w.I};
     for (void* p : ptrs)
         if (p) cudaFree(p);
@@ -241,16 +265,19 @@ int ensure_workspace(hac_index* idx, int nq_pad, uint32_t cap, int64_t out_elems
     }
     if (nq_pad > w.nq_pad || idx->d != w.d) {
         // per-query arrays
-        void* ptrs[] = {w.q, w.q_shadow, w.q_norm, w.q_err, w.margin, w.tau, w.thr, w.cb.count, w.cb.sorted,
-                        w.cb.score, w.cb.row, w.cb.exact};
+        void* ptrs[] = {w.q, w.q_shadow, w.q_shadow8, w.q_consts, w.q_norm, w.q_err, w.margin, w.tau, w.thr, w.cb.count,
+                        w.cb.sorted, w.cb.score, w.cb.row, w.cb.exact};
         for (void* p : ptrs)
             if (p) cudaFree(p);
-        w.q = nullptr; w.q_shadow = nullptr; w.q_norm = w.q_err = w.margin = w.tau = w.thr = nullptr;
+        w.q = nullptr; w.q_shadow = nullptr; w.q_shadow8 = nullptr; w.q_consts = nullptr;
+        w.q_norm = w.q_err = w.margin = w.tau = w.thr = nullptr;
         w.cb.score = w.cb.exact = nullptr; w.cb.row = w.cb.count = w.cb.sorted = nullptr;
         const int np = std::max(nq_pad, w.nq_pad);
         w.nq_pad = 0; w.cap = 0;
         CU(cudaMalloc(&w.q, (size_t)np * idx->d * sizeof(float)));
         CU(cudaMalloc(&w.q_shadow, (size_t)shadow_bytes(np, idx->d)));
+        CU(cudaMalloc(&w.q_shadow8, (size_t)shadow_bytes(np, idx->d)));     // (sized like the f16 image: enough)
+        CU(cudaMalloc(&w.q_consts, np * sizeof(QueryQ8)));
         CU(cudaMalloc(&w.q_norm, np * sizeof(float)));
         CU(cudaMalloc(&w.q_err, np * sizeof(float)));
         CU(cudaMalloc(&w.margin, np * sizeof(float)));
@@ -293,20 +320,117 @@ struct HostReadback {
     float screen_err_max;
 };
 
+// int8 screen path.  Per chunk: int8 tensor-core scan with integer thresholds -> exact fp32 rescore of the
+// rows it emitted -> refresh on exact scores (tau = k-th best exact score so far, everything below dropped).
+// A row is emitted when its upper bound  a8 + m8(q, tile)  reaches tau, so only ONE margin separates the
+// screen from the exact threshold, and after the last chunk the shortlist IS the exact top-k.
+// Returns 1 when the shortlist overflowed (caller falls back to the f16 path), 0 on success, < 0 on error.
+int search_batch_i8(hac_index* idx, int nq, int nq_pad, const float* q_dev, int k, float* D_dev, int64_t* I_dev,
+                    cudaStream_t s, const SegTable& segs) {
+    const int d = idx->d;
+    hac_stats& st = idx->stats;
+    const uint32_t cap = cap_for_k(k, 0);
+    int rc = ensure_workspace(idx, nq_pad, cap, 0);
+    if (rc != HAC_OK) return rc;
+    Workspace& w = idx->ws;
+    CandBuf cb = w.cb;
+    cb.cap = cap;
+    HostReadback* hr = static_cast<HostReadback*>(w.host_pinned);
+    int launches = 0, n_chunks = 0, n_ev = 2;
+    cudaEventRecord(idx->ev[0], s);
+    launch_init_search(cb, w.tau, w.thr, nq, nq_pad, s);
+    launch_convert_queries_i8(q_dev, nq, nq_pad, d, w.q_shadow8, w.q_consts, s);
+    launch_margins(nullptr, nullptr, nullptr, d, w.margin, w.scalars + 1, nq, s);   // refresh margin = 0 (exact scores)
+    launch_margins_i8(w.q_consts, idx->corpus_stats, d, w.q_norm /*scratch*/, w.scalars + 1, nq, s);   // statistics
+    cudaMemsetAsync(w.scalars + 2, 0, sizeof(float), s);
+    cudaMemsetAsync(w.counters + 1, 0, sizeof(unsigned long long), s);
+    launches += 4;
+    // the first chunk is emitted unfiltered and rescored exactly, so it is kept small; later chunks grow with the
+    // rows seen so far: a chunk is expected to emit about growth * k * exp(m8 * z / sigma) rows per query
+    const double growth = k <= 128 ? 2.0 : 1.0;
+    const int64_t first = std::min<int64_t>(cap / 2, std::max<int64_t>(512, round_up(2 * (int64_t)k, kRowAlign)));
+    int64_t rows_done = 0;
+    for (size_t si = 0; si < idx->segs.size(); ++si) {
+        const Segment& seg = idx->segs[si];
+        int64_t r = 0;
+        while (r < seg.n_rows) {
+            int64_t size = rows_done == 0 ? first : (int64_t)(growth * (double)rows_done);
+            size = std::max<int64_t>(kRowAlign, size / kRowAlign * kRowAlign);
+            const int64_t r1 = std::min(seg.n_rows, r + size);
+            const bool timed = n_ev + 2 <= kMaxEvents;
+            if (timed) cudaEventRecord(idx->ev[n_ev], s);
+            MmaScanArgs a;
+            a.q_shadow = w.q_shadow8;
+            a.x_shadow = seg.shadow8;
+            a.q_stats = nullptr;
+            a.x_stats = nullptr;
+            a.x_tiles = seg.tiles8;
+            a.q_consts = w.q_consts;
+            a.thr = w.thr;
+            a.d = d;
+            a.n_qtiles = nq_pad / kTileRows;
+            a.ct0 = r / kRowAlign;
+            a.ct1 = (r1 + kRowAlign - 1) / kRowAlign;
+            a.seg_rows = std::min(seg.n_rows, r1);
+            a.row_id_base = seg.base;
+            a.cb = cb;
+            CU(launch_scan_mma_i8(a, idx->sm_count, s));
+            if (timed) {
+                cudaEventRecord(idx->ev[n_ev + 1], s);
+                n_ev += 2;
+            }
+            launch_rescore_new(cb, q_dev, d, segs, nq, w.scalars + 2, w.counters + 1, s);
+            launch_refresh(cb, k, w.margin, w.tau, w.thr, nq, s);
+            launches += 3;
+            ++n_chunks;
+            rows_done += r1 - r;
+            r = r1;
+        }
+    }
+    launch_final_select(cb, k, nq, idx->id_table, idx->id_base, D_dev, I_dev, /*use_score=*/true, s);
+    ++launches;
+    cudaEventRecord(idx->ev[1], s);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(&hr->overflow, cb.overflow, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    CU(cudaMemcpyAsync(&hr->emitted, w.counters, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+    CU(cudaMemcpyAsync(&hr->margin_max, w.scalars + 1, 2 * sizeof(float), cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    st.n_chunks = n_chunks;
+    st.kernel_launches = launches;
+    st.candidates_emitted = (int64_t)hr->emitted;
+    st.candidates_rescored = (int64_t)hr->rescored;
+    st.margin_max = hr->margin_max;
+    st.screen_err_max = hr->screen_err_max;
+    float ms = 0.f, scan_ms = 0.f;
+    cudaEventElapsedTime(&ms, idx->ev[0], idx->ev[1]);
+    for (int i = 2; i + 1 < n_ev; i += 2) {
+        float t = 0.f;
+        cudaEventElapsedTime(&t, idx->ev[i], idx->ev[i + 1]);
+        scan_ms += t;
+    }
+    st.total_ms = ms;
+    st.scan_ms = scan_ms;
+    return hr->overflow ? 1 : 0;
+}
+
 // One query batch (nq <= kMaxQueryBatch) over the whole shard; all buffers on the device.
 int search_batch(hac_index* idx, int nq, const float* q_dev, int k, float* D_dev, int64_t* I_dev, cudaStream_t s,
                  int path) {
     const int d = idx->d;
     const int nq_pad = (int)round_up(nq, kTileRows);
-    // AUTO: the f16 screen streams half the bytes of the fp32 rows, so it wins at every batch size
-    // (measured: Q=1 5.4 ms vs 11.6 ms over 25.7M rows); both end in the same exact rescore.
-    if (path == HAC_PATH_AUTO) path = HAC_PATH_MMA;
+    // AUTO: the tensor-core screens stream 1/4 (int8) or 1/2 (f16) of the bytes of the fp32 rows, so they win
+    // at every batch size (measured: Q=1 5.4 ms f16 vs 11.3 ms fp32 over 25.7M rows); all paths end in the
+    // same exact fp32 scores.
+    if (path == HAC_PATH_AUTO) path = idx->default_path;
+    bool have_i8 = !idx->segs.empty();
+    for (const auto& sg : idx->segs) have_i8 = have_i8 && sg.shadow8 != nullptr;
+    if (path == HAC_PATH_I8 && !have_i8) path = HAC_PATH_MMA;      // d % 128 != 0 or int8 image disabled
     if (path == HAC_PATH_GEMV && nq > 4) return fail(HAC_E_INVALID, "GEMV path takes at most 4 queries per batch");
     if (!idx->events_ready) {
         for (auto& e : idx->ev) CU(cudaEventCreate(&e));
         idx->events_ready = true;
     }
-    if (path == HAC_PATH_MMA && !idx->mma_configured) {
+    if ((path == HAC_PATH_MMA || path == HAC_PATH_I8) && !idx->mma_configured) {
         CU(scan_mma_configure());
         idx->mma_configured = true;
     }
@@ -320,6 +444,14 @@ int search_batch(hac_index* idx, int nq, const float* q_dev, int k, float* D_dev
         segs.base[i] = idx->segs[i].base;
         segs.rows[i] = idx->segs[i].rows;
     }
+    if (path == HAC_PATH_I8) {
+        const int rc8 = search_batch_i8(idx, nq, nq_pad, q_dev, k, D_dev, I_dev, s, segs);
+        if (rc8 <= 0) return rc8;
+        path = HAC_PATH_MMA;            // shortlist overflow: redo with the f16 screen (and its careful mode)
+        st.path = path;
+        st.retries = 1;
+    }
+    const int retries_before = st.retries;
     // level 0: fast mode - the whole search is enqueued without a host round trip; the overflow flag is
     //          read once at the end.
     // level 1: careful mode (only after level 0 overflowed: mass near-duplicates, adversarial data) -
@@ -343,7 +475,7 @@ int search_batch(hac_index* idx, int nq, const float* q_dev, int k, float* D_dev
             cudaMemsetAsync(w.q_stats, 0, sizeof(OperandStats), s);
             launch_absmax(q_dev, (int64_t)nq * d, w.scalars + 0, s);
             launch_pick_scale(w.q_stats, w.scalars + 0, 0, s);
-            launch_convert_rows(q_dev, nq, nq_pad, d, w.q_shadow, 0, w.q_stats, w.q_norm, w.q_err, s);
+            launch_convert_rows(q_dev, nq, nq_pad, d, w.q_shadow, 0, w.q_stats, w.q_norm, w.q_err, idx->drop_bits_q, s);
             launch_margins(w.q_norm, w.q_err, idx->corpus_stats, d, w.margin, w.scalars + 1, nq, s);
             launches += 4;
         } else {
@@ -437,7 +569,7 @@ int search_batch(hac_index* idx, int nq, const float* q_dev, int k, float* D_dev
             }
         }
         launch_rescore(cb, q_dev, d, segs, nq, w.scalars + 2, w.counters + 1, s);
-        launch_final_select(cb, k, nq, idx->id_table, idx->id_base, D_dev, I_dev, s);
+        launch_final_select(cb, k, nq, idx->id_table, idx->id_base, D_dev, I_dev, /*use_score=*/false, s);
         launches += 2;
         cudaEventRecord(idx->ev[1], s);
         CU(cudaGetLastError());
@@ -461,8 +593,8 @@ int search_batch(hac_index* idx, int nq, const float* q_dev, int k, float* D_dev
         }
         st.total_ms = ms;
         st.scan_ms = scan_ms;
+        st.retries = retries_before + level;
         if (!hr->overflow) return HAC_OK;
-        st.retries = level + 1;
     }
     return fail(HAC_E_OVERFLOW, "candidate shortlist overflowed even in careful mode");
 }
@@ -477,7 +609,7 @@ int search_common(hac_index* idx, int64_t nq, const float* q, bool q_on_host, in
         snprintf(buf, sizeof buf, "search: k=%d outside [1, %d]", k, HAC_MAX_K);
         return fail(HAC_E_INVALID, buf);
     }
-    if (path != HAC_PATH_AUTO && path != HAC_PATH_GEMV && path != HAC_PATH_MMA)
+    if (path != HAC_PATH_AUTO && path != HAC_PATH_GEMV && path != HAC_PATH_MMA && path != HAC_PATH_I8)
         return fail(HAC_E_INVALID, "search: unknown path");
     if (nq == 0) return HAC_OK;
     DeviceGuard guard(idx->device);
@@ -761,6 +893,27 @@ int hac_set_option(hac_index* idx, const char* name, int64_t value) {
         idx->mma_cta_group = (int)value;
         return HAC_OK;
     }
+    if (strcmp(name, "default_path") == 0) {
+        if (value != HAC_PATH_GEMV && value != HAC_PATH_MMA && value != HAC_PATH_I8)
+            return fail(HAC_E_INVALID, "default_path must be a HAC_PATH_* scan path");
+        idx->default_path = (int)value;
+        return HAC_OK;
+    }
+    if (strcmp(name, "f16_drop_bits_corpus") == 0 || strcmp(name, "f16_drop_bits_queries") == 0) {
+        if (value < 0 || value > 8) return fail(HAC_E_INVALID, "drop bits must be in [0, 8]");
+        if (name[14] == 'c') {
+            if (idx->ntotal != 0) return fail(HAC_E_STATE, "f16_drop_bits_corpus must be set on an empty index");
+            idx->drop_bits_x = (int)value;
+        } else {
+            idx->drop_bits_q = (int)value;
+        }
+        return HAC_OK;
+    }
+    if (strcmp(name, "build_i8") == 0) {
+        if (idx->ntotal != 0 || !idx->segs.empty()) return fail(HAC_E_STATE, "build_i8 must be set on an empty index");
+        idx->build_i8 = value != 0;
+        return HAC_OK;
+    }
     if (strcmp(name, "chunk_growth_x100") == 0) {
         if (value < 110 || value > 1600) return fail(HAC_E_INVALID, "chunk_growth_x100 must be in [110, 1600]");
         idx->chunk_growth = (double)value / 100.0;
@@ -779,7 +932,7 @@ int hac_get_stats(const hac_index* idx, hac_stats* out) {
     int64_t b32 = 0, bsh = 0;
     for (const auto& s : idx->segs) {
         b32 += s.cap_rows * (int64_t)idx->d * 4;
-        bsh += shadow_bytes(s.cap_rows, idx->d);
+        bsh += shadow_bytes(s.cap_rows, idx->d) + (s.shadow8 ? shadow8_bytes(s.cap_rows, idx->d) : 0);
     }
     out->bytes_fp32 = b32;
     out->bytes_shadow = bsh;

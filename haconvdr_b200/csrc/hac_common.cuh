@@ -35,6 +35,20 @@ __device__ __forceinline__ int64_t shadow_chunk_offset(int64_t r, int k8, int d)
            ((c ^ (rr & 7)) << 4);
 }
 
+// The int8 shadow uses the same piece image with one byte per element: a K block is 128 elements
+// (one 128-byte swizzle row), chunk c = 16 consecutive int8 values.
+constexpr int kBlockK8 = 128;
+__host__ __device__ inline int64_t shadow8_bytes(int64_t rows, int d) {
+    return shadow_tiles(rows) * (int64_t)(d / kBlockK8) * kPieceBytes;
+}
+__device__ __forceinline__ int64_t shadow8_chunk_offset(int64_t r, int k16, int d) {
+    const int64_t tile = r / kTileRows;
+    const int rr = (int)(r % kTileRows);
+    const int kb = k16 >> 3, c = k16 & 7;
+    return (tile * (d / kBlockK8) + kb) * (int64_t)kPieceBytes + (rr >> 3) * 1024 + (rr & 7) * 128 +
+           ((c ^ (rr & 7)) << 4);
+}
+
 // ------------------------------------------------------------------------------------------
 // The exact score.  One warp per (query, row): lane l accumulates float4 groups l, l+32, ...
 // sequentially with FMA (x,y,z,w order), then an xor-butterfly sums the 32 partials.  Every
@@ -153,6 +167,20 @@ __host__ __device__ constexpr uint32_t umma_idesc_f16(int M, int N) {
            | (0u << 7) | (0u << 10)        // a_format = b_format = F16
            | (0u << 15) | (0u << 16)       // K-major A and B
            | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+// kind::i8: D=s32, A=B=signed 8-bit, both K-major; K = 32 per instruction
+__host__ __device__ constexpr uint32_t umma_idesc_i8(int M, int N) {
+    return (2u << 4)                       // c_format = S32
+           | (1u << 7) | (1u << 10)        // a_format = b_format = signed int8
+           | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                        uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
 }
 template <int kCtaGroup>
 __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,

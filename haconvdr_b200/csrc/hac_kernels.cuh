@@ -18,7 +18,18 @@ struct OperandStats {
     float norm_max;      // max_j ||x_j||_2            (fp32 rows)
     float hat_norm_max;  // max_j ||f16(x_j*scale)/scale||_2
     float err_norm_max;  // max_j ||x_j - f16(x_j*scale)/scale||_2
-    float pad0, pad1;
+    float i8_beta_max;   // int8 image: max over tiles of beta  (max ||x_j||)
+    float i8_gamma_max;  // int8 image: max over tiles of gamma (max ||x_j - alpha*xi_j||)
+};
+
+// int8 shadow: constants of one 128-row tile (written by the int8 convert kernel).
+//   x_j ~= alpha * xi_j (xi int8);  beta = max_j ||x_j||;  gamma = max_j ||x_j - alpha*xi_j||  over the tile's rows
+struct TileQ8 {
+    float alpha, beta, gamma, pad;
+};
+// per-query constants of the int8 query image: q ~= t * qi;  eps = ||q - t*qi||;  nhat = ||t*qi||;  norm = ||q||
+struct QueryQ8 {
+    float t, eps, nhat, norm;
 };
 
 // Candidate shortlist: per query a list of (screen score, index-local row) pairs.
@@ -44,9 +55,18 @@ void launch_absmax(const float* x, int64_t n_elems, float* absmax_out, cudaStrea
 // scale <- 2^(12 - ceil(log2(absmax))) unless *stats already holds a scale and keep_scale != 0
 void launch_pick_scale(OperandStats* stats, const float* absmax_in, int keep_scale, cudaStream_t s);
 // rows [0,n) of x -> shadow rows [row0, row0+n); rows [n, n_pad) are written as zeros.
+// drop_bits: low mantissa bits of the f16 image forced to zero (0 = full 11-bit significand)
 void launch_convert_rows(const float* x, int64_t n, int64_t n_pad, int d, uint8_t* shadow, int64_t row0,
-                         OperandStats* stats, float* row_norm, float* row_err, cudaStream_t s);
+                         OperandStats* stats, float* row_norm, float* row_err, int drop_bits, cudaStream_t s);
 void launch_synth(float* out, int64_t n, int d, uint64_t seed, int64_t row0, int dist, cudaStream_t s);
+// int8 images: whole 128-row tiles [tile0, tile1) of a segment are (re)built from its fp32 rows (n_rows valid)
+void launch_convert_tiles_i8(const float* rows, int64_t n_rows, int d, int64_t tile0, int64_t tile1, uint8_t* shadow8,
+                             TileQ8* tiles, OperandStats* stats, cudaStream_t s);
+// diagnostic: margin[q] = eps_q*beta_max + nhat_q*gamma_max + slack, the loosest per-tile int8 margin of query q
+void launch_margins_i8(const QueryQ8* q_consts, const OperandStats* corpus, int d, float* margin, float* margin_max,
+                       int nq, cudaStream_t s);
+void launch_convert_queries_i8(const float* q, int nq, int nq_pad, int d, uint8_t* q_shadow8, QueryQ8* consts,
+                               cudaStream_t s);
 
 // ---- search state --------------------------------------------------------------------------
 void launch_init_search(CandBuf cb, float* tau, float* thr, int nq, int nq_pad, cudaStream_t s);
@@ -58,9 +78,14 @@ void launch_refresh(CandBuf cb, int k, const float* margin, float* tau, float* t
 // exact fp32 scores of every shortlisted pair
 void launch_rescore(CandBuf cb, const float* q, int d, SegTable segs, int nq, float* screen_err_max,
                     unsigned long long* rescored, cudaStream_t s);
+// same for the entries appended since the last refresh only ([sorted, count)); their screen score is
+// replaced by the exact one, so the refresh that follows works on exact scores (int8 path)
+void launch_rescore_new(CandBuf cb, const float* q, int d, SegTable segs, int nq, float* screen_err_max,
+                        unsigned long long* rescored, cudaStream_t s);
 // final top-k by (exact score desc, id asc) with id translation
+// use_score: the `score` array already holds exact scores (int8 path) - rank by it instead of `exact`
 void launch_final_select(CandBuf cb, int k, int nq, const int64_t* id_table, int64_t id_base, float* D,
-                         int64_t* I, cudaStream_t s);
+                         int64_t* I, bool use_score, cudaStream_t s);
 void launch_fill_empty(float* D, int64_t* I, int64_t n, cudaStream_t s);
 // careful mode: undo the appends since the last refresh / cut the rescored shortlist to its exact top-k
 void launch_rollback(CandBuf cb, int nq, cudaStream_t s);
@@ -76,6 +101,8 @@ struct MmaScanArgs {
     const uint8_t* x_shadow;
     const OperandStats* q_stats;
     const OperandStats* x_stats;
+    const TileQ8* x_tiles;      // int8 path: per-128-row-tile constants of the segment (else nullptr)
+    const QueryQ8* q_consts;    // int8 path: per-query constants
     const float* thr;       // [n_qtiles*128] unscaled emission thresholds
     int d;
     int n_qtiles;
@@ -86,6 +113,8 @@ struct MmaScanArgs {
 };
 // cta_group = 1: one CTA per tile; 2: CTA pairs (cluster of 2) sharing each MMA; needs an even n_qtiles
 cudaError_t launch_scan_mma(const MmaScanArgs& a, int sm_count, int cta_group, cudaStream_t s);
+// int8 screen (kind::i8, s32 accumulators, integer thresholds); x_tiles / q_consts must be set
+cudaError_t launch_scan_mma_i8(const MmaScanArgs& a, int sm_count, cudaStream_t s);
 cudaError_t scan_mma_configure();
 
 // ---- merge / gather ---------------------------------------------------------------------------

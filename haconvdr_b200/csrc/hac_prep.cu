@@ -58,7 +58,7 @@ __global__ void __launch_bounds__(256) convert_rows_kernel(const float* __restri
                                                            int d, uint8_t* __restrict__ shadow, int64_t row0,
                                                            OperandStats* __restrict__ stats,
                                                            float* __restrict__ row_norm,
-                                                           float* __restrict__ row_err) {
+                                                           float* __restrict__ row_err, int drop_bits) {
     const int lane = threadIdx.x & 31;
     const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
     const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -79,6 +79,13 @@ __global__ void __launch_bounds__(256) convert_rows_kernel(const float* __restri
                     float t = v[i] * scale;
                     t = fminf(fmaxf(t, -65504.f), 65504.f);
                     h[i] = __float2half_rn(t);
+                    if (drop_bits > 0) {
+                        // keep fewer significant bits (round to nearest): a sparser mantissa toggles less in the
+                        // tensor-core multipliers; the margin is computed from the actual error, so it stays rigorous
+                        unsigned short u = __half_as_ushort(h[i]);
+                        u = (unsigned short)((u + (1u << (drop_bits - 1))) & ~((1u << drop_bits) - 1u));
+                        h[i] = __ushort_as_half(u);
+                    }
                     const float back = __half2float(h[i]) * inv_scale;
                     const float e = v[i] - back;
                     s_x = fmaf(v[i], v[i], s_x);
@@ -115,11 +122,155 @@ __global__ void __launch_bounds__(256) convert_rows_kernel(const float* __restri
 }
 
 void launch_convert_rows(const float* x, int64_t n, int64_t n_pad, int d, uint8_t* shadow, int64_t row0,
-                         OperandStats* stats, float* row_norm, float* row_err, cudaStream_t s) {
+                         OperandStats* stats, float* row_norm, float* row_err, int drop_bits, cudaStream_t s) {
     if (n_pad <= 0) return;
     int64_t blocks = (n_pad + 7) / 8;  // 8 warps per block, one row per warp per pass
     if (blocks > 148 * 8) blocks = 148 * 8;
-    convert_rows_kernel<<<(int)blocks, 256, 0, s>>>(x, n, n_pad, d, shadow, row0, stats, row_norm, row_err);
+    convert_rows_kernel<<<(int)blocks, 256, 0, s>>>(x, n, n_pad, d, shadow, row0, stats, row_norm, row_err, drop_bits);
+}
+
+// ---------------------------------------------------------------------------------------------
+// int8 images.  Corpus: one CTA per 128-row tile; the tile shares one scale alpha = absmax/127, so the
+// scan epilogue compares raw s32 accumulators against one integer threshold per (query, tile).
+// Per tile the kernel also records beta = max ||x_j|| and gamma = max ||x_j - alpha*xi_j|| (upper bounds),
+// the two norms the rigorous screen margin needs.
+__device__ __forceinline__ uint32_t pack4_i8(int a, int b, int c, int d) {
+    return (uint32_t)(a & 0xff) | ((uint32_t)(b & 0xff) << 8) | ((uint32_t)(c & 0xff) << 16) | ((uint32_t)(d & 0xff) << 24);
+}
+__device__ __forceinline__ int quant_i8(float x, float inv, float alpha, float& sx, float& se) {
+    int q = __float2int_rn(x * inv);
+    q = max(-127, min(127, q));
+    const float e = fmaf(-alpha, (float)q, x);
+    sx = fmaf(x, x, sx);
+    se = fmaf(e, e, se);
+    return q;
+}
+// quantise the 16 elements of chunk c16 of one row and store them into the swizzled piece image
+__device__ __forceinline__ void convert_chunk_i8(const float* __restrict__ row, int c16, float inv, float alpha,
+                                                 uint8_t* dst, float& sx, float& se) {
+    const float4* src = reinterpret_cast<const float4*>(row + c16 * 16);
+    uint4 out;
+    uint32_t w[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float4 v = __ldg(src + i);
+        w[i] = pack4_i8(quant_i8(v.x, inv, alpha, sx, se), quant_i8(v.y, inv, alpha, sx, se),
+                        quant_i8(v.z, inv, alpha, sx, se), quant_i8(v.w, inv, alpha, sx, se));
+    }
+    out = make_uint4(w[0], w[1], w[2], w[3]);
+    *reinterpret_cast<uint4*>(dst) = out;
+}
+
+__global__ void __launch_bounds__(256) convert_tiles_i8_kernel(const float* __restrict__ rows, int64_t n_rows, int d,
+                                                               int64_t tile0, uint8_t* __restrict__ shadow8,
+                                                               TileQ8* __restrict__ tiles,
+                                                               OperandStats* __restrict__ stats) {
+    __shared__ int s_absmax, s_beta, s_gamma;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t tile = tile0 + blockIdx.x;
+    const int64_t row_base = tile * kTileRows;
+    const int chunks = d >> 4;
+    if (threadIdx.x == 0) { s_absmax = 0; s_beta = 0; s_gamma = 0; }
+    __syncthreads();
+    float m = 0.f;
+    for (int rr = warp; rr < kTileRows; rr += 8) {
+        const int64_t r = row_base + rr;
+        if (r >= n_rows) break;
+        const float4* src = reinterpret_cast<const float4*>(rows + (size_t)r * d);
+        for (int i = lane; i < (d >> 2); i += 32) {
+            const float4 v = __ldg(src + i);
+            m = fmaxf(m, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if (lane == 0) atomicMax(&s_absmax, __float_as_int(m));
+    __syncthreads();
+    const float absmax = __int_as_float(s_absmax);
+    const bool usable = absmax > 0.f && isfinite(absmax);
+    const float alpha = usable ? absmax / 127.f : 1.f;
+    const float inv = usable ? 127.f / absmax : 0.f;
+    for (int rr = warp; rr < kTileRows; rr += 8) {
+        const int64_t r = row_base + rr;
+        float sx = 0.f, se = 0.f;
+        for (int c = lane; c < chunks; c += 32) {
+            uint8_t* dst = shadow8 + shadow8_chunk_offset(r, c, d);
+            if (r < n_rows) convert_chunk_i8(rows + (size_t)r * d, c, inv, alpha, dst, sx, se);
+            else *reinterpret_cast<uint4*>(dst) = make_uint4(0u, 0u, 0u, 0u);
+        }
+        if (r < n_rows) {
+            sx = warp_sum(sx);
+            se = warp_sum(se);
+            if (lane == 0) {
+                atomicMax(&s_beta, __float_as_int(sqrtf(sx)));
+                atomicMax(&s_gamma, __float_as_int(sqrtf(se)));
+            }
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        TileQ8 t;
+        t.alpha = alpha;
+        t.beta = __int_as_float(s_beta) * 1.0001f;                                   // upper bounds
+        t.gamma = __int_as_float(s_gamma) * 1.0001f + 1e-6f * __int_as_float(s_beta);
+        t.pad = 0.f;
+        tiles[tile] = t;
+        if (stats != nullptr) {
+            atomicMax(reinterpret_cast<int*>(&stats->i8_beta_max), __float_as_int(t.beta));
+            atomicMax(reinterpret_cast<int*>(&stats->i8_gamma_max), __float_as_int(t.gamma));
+        }
+    }
+}
+
+void launch_convert_tiles_i8(const float* rows, int64_t n_rows, int d, int64_t tile0, int64_t tile1, uint8_t* shadow8,
+                             TileQ8* tiles, OperandStats* stats, cudaStream_t s) {
+    if (tile1 <= tile0) return;
+    convert_tiles_i8_kernel<<<(unsigned)(tile1 - tile0), 256, 0, s>>>(rows, n_rows, d, tile0, shadow8, tiles, stats);
+}
+
+// queries: one warp per query, one scale per query
+__global__ void __launch_bounds__(256) convert_queries_i8_kernel(const float* __restrict__ q, int nq, int nq_pad,
+                                                                 int d, uint8_t* __restrict__ q_shadow8,
+                                                                 QueryQ8* __restrict__ consts) {
+    const int lane = threadIdx.x & 31;
+    const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (r >= nq_pad) return;
+    const int chunks = d >> 4;
+    if (r >= nq) {
+        for (int c = lane; c < chunks; c += 32)
+            *reinterpret_cast<uint4*>(q_shadow8 + shadow8_chunk_offset(r, c, d)) = make_uint4(0u, 0u, 0u, 0u);
+        if (lane == 0) consts[r] = QueryQ8{0.f, 0.f, 0.f, 0.f};
+        return;
+    }
+    const float* row = q + (size_t)r * d;
+    float m = 0.f;
+    for (int i = lane; i < (d >> 2); i += 32) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(row) + i);
+        m = fmaxf(m, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    const bool usable = m > 0.f && isfinite(m);
+    const float t = usable ? m / 127.f : 1.f, inv = usable ? 127.f / m : 0.f;
+    float sx = 0.f, se = 0.f;
+    for (int c = lane; c < chunks; c += 32)
+        convert_chunk_i8(row, c, inv, t, q_shadow8 + shadow8_chunk_offset(r, c, d), sx, se);
+    sx = warp_sum(sx);
+    se = warp_sum(se);
+    if (lane == 0) {
+        QueryQ8 c;
+        c.t = t;
+        c.norm = sqrtf(sx) * 1.0001f;
+        c.eps = sqrtf(se) * 1.0001f + 1e-6f * c.norm;
+        c.nhat = c.norm + c.eps;                      // ||t*qi|| <= ||q|| + ||q - t*qi||
+        consts[r] = c;
+    }
+}
+
+void launch_convert_queries_i8(const float* q, int nq, int nq_pad, int d, uint8_t* q_shadow8, QueryQ8* consts,
+                               cudaStream_t s) {
+    if (nq_pad <= 0) return;
+    convert_queries_i8_kernel<<<(nq_pad * 32 + 255) / 256, 256, 0, s>>>(q, nq, nq_pad, d, q_shadow8, consts);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -20,6 +20,8 @@
 // Tile order: consecutive CTAs take the query tiles of the same 256-row corpus tile, so a corpus
 // tile is pulled from HBM once and re-read from L2 by the other query tiles.
 // Roofline: tensor pipe; algorithmic FLOPs = 2 * queries * rows * d per launch.
+#include <limits.h>
+
 #include "hac_common.cuh"
 #include "hac_kernels.cuh"
 
@@ -67,15 +69,33 @@ __device__ __forceinline__ void wait_or_trap(uint64_t* bar, uint32_t parity) {
     __trap();
 }
 
-template <int kCG>
+// integer emission threshold of the int8 screen for one (query, 128-row tile):
+//   exact score s <= t*alpha*A + eps*beta + nhat*gamma (+ slack)  [Cauchy-Schwarz on the two quantisation errors],
+//   so a row can only matter if  A >= (thr - eps*beta - nhat*gamma - slack) / (t*alpha).
+__device__ __forceinline__ int i8_threshold(float thr, const QueryQ8& qc, const TileQ8& tile, int d) {
+    if (thr == INFINITY) return INT_MAX;                 // padded query: never emits
+    if (thr == -INFINITY) return INT_MIN;                // no threshold yet: everything is emitted
+    const float slack = (float)d * 2.4e-7f * qc.norm * tile.beta + 1e-6f * fabsf(thr);   // fp32 rounding of s (d * 2^-22)
+    const float num = thr - (qc.eps * tile.beta + qc.nhat * tile.gamma) - slack;
+    const float den = qc.t * tile.alpha;
+    if (!(den > 0.f)) return num <= 0.f ? INT_MIN : INT_MAX;
+    float tf = num / den;
+    tf -= fabsf(tf) * 1e-5f + 1.f;                       // conservative under fp32 rounding: may only lower it
+    if (tf <= -2.0e9f) return INT_MIN;
+    if (tf >= 2.0e9f) return INT_MAX;
+    return (int)floorf(tf);
+}
+
+template <int kCG, bool kI8>
 __global__ void __launch_bounds__(kThreads, 1) scan_mma_kernel(const MmaScanArgs a) {
+    static_assert(!kI8 || kCG == 1, "the int8 screen exists for the single-CTA variant only");
     using C = Cfg<kCG>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     Barriers* bars = reinterpret_cast<Barriers*>(smem + C::kStages * C::kStageBytes);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int kb_count = a.d / kBlockK;
+    const int kb_count = a.d / (kI8 ? kBlockK8 : kBlockK);
     const uint32_t cta_rank = kCG == 2 ? cluster_ctarank() : 0u;
     const bool leader = cta_rank == 0;
     // work unit: (corpus tile of 256 rows) x (query tile of 128*kCG queries); one unit per CTA group
@@ -130,7 +150,7 @@ __global__ void __launch_bounds__(kThreads, 1) scan_mma_kernel(const MmaScanArgs
         if (leader) {
             // ---------------- MMA issuer ----------------
             if (elect_one()) {
-                constexpr uint32_t idesc = umma_idesc_f16(kTileM * kCG, kTileN);
+                constexpr uint32_t idesc = kI8 ? umma_idesc_i8(kTileM, kTileN) : umma_idesc_f16(kTileM * kCG, kTileN);
                 uint32_t stage = 0, phase = 0, it = 0;
                 for (int64_t u = unit0; u < n_units; u += unit_step, ++it) {
                     const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
@@ -145,9 +165,11 @@ __global__ void __launch_bounds__(kThreads, 1) scan_mma_kernel(const MmaScanArgs
                         const uint64_t descA = umma_desc_k128(sA);
                         const uint64_t descB = umma_desc_k128(sA + C::kABytes);
 #pragma unroll
-                        for (int k = 0; k < kBlockK / 16; ++k) {
-                            // advance 16 elements (32 B) along K inside the swizzle atom: +2 in the >>4 address field
-                            umma_f16<kCG>(tmem_d, descA + 2 * k, descB + 2 * k, idesc, (kb | k) != 0);
+                        for (int k = 0; k < 4; ++k) {
+                            // advance 32 B along K inside the swizzle atom (16 f16 or 32 int8 elements): +2 in the
+                            // >>4 address field
+                            if constexpr (kI8) umma_i8(tmem_d, descA + 2 * k, descB + 2 * k, idesc, (kb | k) != 0);
+                            else umma_f16<kCG>(tmem_d, descA + 2 * k, descB + 2 * k, idesc, (kb | k) != 0);
                         }
                         // slot free / accumulator ready, signalled when the MMAs above retire
                         if constexpr (kCG == 1) {
@@ -177,38 +199,93 @@ __global__ void __launch_bounds__(kThreads, 1) scan_mma_kernel(const MmaScanArgs
     } else {
         // ---------------- epilogue: fused threshold filter ----------------
         const int quarter = warp & 3;                    // TMEM lanes [32*quarter, 32*quarter+32)
-        const float scale = a.q_stats->scale * a.x_stats->scale;
-        const float inv_scale = a.q_stats->inv_scale * a.x_stats->inv_scale;
+        float scale = 1.f, inv_scale = 1.f;
+        if constexpr (!kI8) {
+            scale = a.q_stats->scale * a.x_stats->scale;
+            inv_scale = a.q_stats->inv_scale * a.x_stats->inv_scale;
+        }
         unsigned long long emitted = 0;
         uint32_t it = 0;
         // Survivors are first stashed per thread (local memory) and appended to the shortlist only
         // AFTER the accumulator buffer has been handed back to the MMA warp, so the round trip of the
         // global atomic overlaps the next tile's MMAs instead of stalling the TMEM pipeline.
-        float stash_v[kStash];
-        uint32_t stash_r[kStash];
+        // The append itself is deferred by one more tile: the atomic that reserves the slots is issued when a
+        // tile ends, its result is first used when the NEXT tile ends, so no warp ever waits for it.
+        float stash_v[2][kStash];
+        uint32_t stash_r[2][kStash];
+        uint32_t pend_n = 0, pend_base = 0;
+        int pend_q = 0;
+        auto flush_pending = [&](int buf) {
+            if (pend_n != 0) {
+                if (pend_base + pend_n > a.cb.cap) *a.cb.overflow = 1u;
+                for (uint32_t i = 0; i < pend_n; ++i) {
+                    if (pend_base + i < a.cb.cap) {
+                        a.cb.score[(size_t)pend_q * a.cb.cap + pend_base + i] = stash_v[buf][i];
+                        a.cb.row[(size_t)pend_q * a.cb.cap + pend_base + i] = stash_r[buf][i];
+                    }
+                }
+                pend_n = 0;
+            }
+        };
+        // Per-unit constants (thresholds) are fetched one unit ahead, so their global-load latency is
+        // hidden behind the TMEM drain of the current tile.
+        struct UnitConsts {
+            float thr;
+            QueryQ8 qc;
+            TileQ8 t0, t1;
+        };
+        auto fetch = [&](int64_t u) {
+            UnitConsts c;
+            const int64_t ct = a.ct0 + u / n_qgroups;
+            const int q = ((int)(u % n_qgroups) * kCG + (int)cta_rank) * kTileM + quarter * 32 + lane;
+            c.thr = a.thr[q];
+            if constexpr (kI8) {
+                c.qc = a.q_consts[q];
+                c.t0 = a.x_tiles[2 * ct];
+                c.t1 = a.x_tiles[2 * ct + 1];
+            }
+            return c;
+        };
+        UnitConsts cur{};
+        if (unit0 < n_units) cur = fetch(unit0);
         for (int64_t u = unit0; u < n_units; u += unit_step, ++it) {
             const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
             const int64_t ct = a.ct0 + u / n_qgroups;
             const int qt = (int)(u % n_qgroups) * kCG + (int)cta_rank;
             const int q = qt * kTileM + quarter * 32 + lane;
-            const float thr_s = a.thr[q] * scale;        // threshold in accumulator units (power-of-two scale)
+            const float thr_s = cur.thr * scale;         // threshold in accumulator units (power-of-two scale)
             const int64_t row0 = ct * kTileN;
+            // int8: one integer threshold and one de-quantisation factor per 128-row half of the tile
+            int thr_i[2] = {0, 0};
+            float deq[2] = {0.f, 0.f};
+            if constexpr (kI8) {
+                thr_i[0] = i8_threshold(cur.thr, cur.qc, cur.t0, a.d);
+                thr_i[1] = i8_threshold(cur.thr, cur.qc, cur.t1, a.d);
+                deq[0] = cur.qc.t * cur.t0.alpha;
+                deq[1] = cur.qc.t * cur.t1.alpha;
+            }
+            UnitConsts nxt{};
+            if (u + unit_step < n_units) nxt = fetch(u + unit_step);
             uint32_t stash_n = 0;
-            wait_or_trap(&bars->tmem_full[acc], acc_phase);
-            tc_fence_after();
-            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * kTileN;
-#pragma unroll 1
-            for (int c = 0; c < kTileN / 32; ++c) {
-                uint32_t v[32];
-                tmem_ld_32x32(taddr + c * 32, v);
-                tmem_ld_wait();
+            // one 32-column group of this thread's query: compare, stash or append the survivors
+            auto process = [&](const uint32_t (&v)[32], int c) {
+                const int thr_c = thr_i[c >> 2];
+                const float out_scale = kI8 ? deq[c >> 2] : inv_scale;
+                auto passes = [&](uint32_t bits) {
+                    if constexpr (kI8) return (int)bits >= thr_c;
+                    else return __uint_as_float(bits) >= thr_s;
+                };
+                auto value = [&](uint32_t bits) {
+                    if constexpr (kI8) return (float)(int)bits * out_scale;
+                    else return __uint_as_float(bits) * out_scale;
+                };
                 bool any = false;
 #pragma unroll
-                for (int j = 0; j < 32; ++j) any |= (__uint_as_float(v[j]) >= thr_s);
+                for (int j = 0; j < 32; ++j) any |= passes(v[j]);
                 if (any) {
                     uint32_t mask = 0;
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) mask |= (__uint_as_float(v[j]) >= thr_s ? 1u : 0u) << j;
+                    for (int j = 0; j < 32; ++j) mask |= (passes(v[j]) ? 1u : 0u) << j;
                     const int64_t rem = a.seg_rows - (row0 + c * 32);      // rows past the segment end are padding
                     if (rem < 32) mask &= rem <= 0 ? 0u : ((1u << rem) - 1u);
                     const uint32_t n = __popc(mask);
@@ -217,8 +294,8 @@ __global__ void __launch_bounds__(kThreads, 1) scan_mma_kernel(const MmaScanArgs
 #pragma unroll
                         for (int j = 0; j < 32; ++j) {
                             if ((mask >> j) & 1u) {
-                                stash_v[stash_n] = __uint_as_float(v[j]) * inv_scale;
-                                stash_r[stash_n] = row_id + j;
+                                stash_v[it & 1][stash_n] = value(v[j]);
+                                stash_r[it & 1][stash_n] = row_id + j;
                                 ++stash_n;
                             }
                         }
@@ -230,7 +307,7 @@ __global__ void __launch_bounds__(kThreads, 1) scan_mma_kernel(const MmaScanArgs
                         for (int j = 0; j < 32; ++j) {
                             const uint32_t pos = base + __popc(mask & ((1u << j) - 1u));
                             if (((mask >> j) & 1u) && pos < a.cb.cap) {
-                                a.cb.score[(size_t)q * a.cb.cap + pos] = __uint_as_float(v[j]) * inv_scale;
+                                a.cb.score[(size_t)q * a.cb.cap + pos] = value(v[j]);
                                 a.cb.row[(size_t)q * a.cb.cap + pos] = row_id + j;
                             }
                         }
@@ -238,22 +315,36 @@ __global__ void __launch_bounds__(kThreads, 1) scan_mma_kernel(const MmaScanArgs
                     emitted += n;
                 }
                 __syncwarp();
+            };
+            wait_or_trap(&bars->tmem_full[acc], acc_phase);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * kTileN;
+            // two register buffers: the next 32 columns are in flight while the current ones are compared
+            uint32_t va[32], vb[32];
+            tmem_ld_32x32(taddr, va);
+            tmem_ld_wait();
+#pragma unroll 1
+            for (int c = 0; c < kTileN / 32; c += 2) {
+                tmem_ld_32x32(taddr + (c + 1) * 32, vb);
+                process(va, c);
+                tmem_ld_wait();
+                if (c + 2 < kTileN / 32) tmem_ld_32x32(taddr + (c + 2) * 32, va);
+                process(vb, c + 1);
+                tmem_ld_wait();
             }
             tc_fence_before();
             if constexpr (kCG == 1) mbar_arrive(&bars->tmem_empty[acc]);
             else mbar_arrive_cluster(&bars->tmem_empty[acc], 0);       // the leader's barrier counts both CTAs
+            flush_pending((it & 1) ^ 1);                  // the previous tile's survivors: their slots have arrived
             if (stash_n != 0) {
-                const uint32_t base = atomicAdd(a.cb.count + q, stash_n);
-                if (base + stash_n > a.cb.cap) *a.cb.overflow = 1u;
-                for (uint32_t i = 0; i < stash_n; ++i) {
-                    if (base + i < a.cb.cap) {
-                        a.cb.score[(size_t)q * a.cb.cap + base + i] = stash_v[i];
-                        a.cb.row[(size_t)q * a.cb.cap + base + i] = stash_r[i];
-                    }
-                }
+                pend_base = atomicAdd(a.cb.count + q, stash_n);   // result consumed one tile later
+                pend_n = stash_n;
+                pend_q = q;
             }
             __syncwarp();
+            cur = nxt;
         }
+        flush_pending((it & 1) ^ 1);
         if (emitted) atomicAdd(a.cb.emitted, emitted);
     }
 
@@ -265,10 +356,22 @@ __global__ void __launch_bounds__(kThreads, 1) scan_mma_kernel(const MmaScanArgs
 }  // namespace
 
 cudaError_t scan_mma_configure() {
-    cudaError_t e = cudaFuncSetAttribute(scan_mma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(scan_mma_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          Cfg<1>::kSmemBytes);
     if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(scan_mma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<2>::kSmemBytes);
+    e = cudaFuncSetAttribute(scan_mma_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<1>::kSmemBytes);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(scan_mma_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                Cfg<2>::kSmemBytes);
+}
+
+cudaError_t launch_scan_mma_i8(const MmaScanArgs& a, int sm_count, cudaStream_t s) {
+    const int64_t n_units = (a.ct1 - a.ct0) * a.n_qtiles;
+    if (n_units <= 0) return cudaSuccess;
+    if (a.x_tiles == nullptr || a.q_consts == nullptr || a.d % kBlockK8 != 0) return cudaErrorInvalidValue;
+    const int grid = (int)(n_units < sm_count ? n_units : sm_count);
+    scan_mma_kernel<1, true><<<grid, kThreads, Cfg<1>::kSmemBytes, s>>>(a);
+    return cudaGetLastError();
 }
 
 cudaError_t launch_scan_mma(const MmaScanArgs& a, int sm_count, int cta_group, cudaStream_t s) {
@@ -289,11 +392,11 @@ cudaError_t launch_scan_mma(const MmaScanArgs& a, int sm_count, int cta_group, c
         attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr;
         cfg.numAttrs = 1;
-        return cudaLaunchKernelEx(&cfg, scan_mma_kernel<2>, a);
+        return cudaLaunchKernelEx(&cfg, scan_mma_kernel<2, false>, a);
     }
     const int64_t n_units = n_ctiles * a.n_qtiles;
     const int grid = (int)(n_units < sm_count ? n_units : sm_count);
-    scan_mma_kernel<1><<<grid, kThreads, Cfg<1>::kSmemBytes, s>>>(a);
+    scan_mma_kernel<1, false><<<grid, kThreads, Cfg<1>::kSmemBytes, s>>>(a);
     return cudaGetLastError();
 }
 

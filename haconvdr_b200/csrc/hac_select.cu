@@ -80,6 +80,22 @@ __global__ void margins_kernel(const float* q_norm, const float* q_err, const Op
     atomicMax(reinterpret_cast<int*>(margin_max), __float_as_int(m));
 }
 
+__global__ void margins_i8_kernel(const QueryQ8* q_consts, const OperandStats* corpus, int d, float* margin,
+                                  float* margin_max, int nq) {
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= nq) return;
+    const QueryQ8 c = q_consts[q];
+    const float m = c.eps * corpus->i8_beta_max + c.nhat * corpus->i8_gamma_max +
+                    (float)d * 2.4e-7f * c.norm * corpus->i8_beta_max;
+    margin[q] = m;
+    atomicMax(reinterpret_cast<int*>(margin_max), __float_as_int(m));
+}
+void launch_margins_i8(const QueryQ8* q_consts, const OperandStats* corpus, int d, float* margin, float* margin_max,
+                       int nq, cudaStream_t s) {
+    cudaMemsetAsync(margin_max, 0, sizeof(float), s);
+    margins_i8_kernel<<<(nq + 127) / 128, 128, 0, s>>>(q_consts, corpus, d, margin, margin_max, nq);
+}
+
 void launch_margins(const float* q_norm, const float* q_err, const OperandStats* corpus, int d, float* margin,
                     float* margin_max, int nq, cudaStream_t s) {
     cudaMemsetAsync(margin_max, 0, sizeof(float), s);
@@ -218,16 +234,18 @@ __device__ __forceinline__ const float* seg_row_ptr(const SegTable& segs, uint32
     return segs.rows[s] + (size_t)(row - segs.base[s]) * d;
 }
 
+template <bool kNewOnly>
 __global__ void __launch_bounds__(256) rescore_kernel(CandBuf cb, const float* __restrict__ qmat, int d,
                                                       SegTable segs, float* __restrict__ screen_err_max,
                                                       unsigned long long* __restrict__ rescored) {
     const int q = blockIdx.x;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
     const int cnt = (int)min(cb.count[q], cb.cap);
+    const int first = kNewOnly ? (int)min(cb.sorted[q], (uint32_t)cnt) : 0;   // entries before it are exact already
     const int d4 = d >> 2;
     const float4* qrow = reinterpret_cast<const float4*>(qmat + (size_t)q * d);
     float worst = 0.f;
-    for (int slot = warp; slot < cnt; slot += n_warps) {
+    for (int slot = first + warp; slot < cnt; slot += n_warps) {
         const uint32_t row = cb.row[(size_t)q * cb.cap + slot];
         const float4* xrow = reinterpret_cast<const float4*>(seg_row_ptr(segs, row, d));
         float acc = 0.f;
@@ -236,11 +254,79 @@ __global__ void __launch_bounds__(256) rescore_kernel(CandBuf cb, const float* _
         if (lane == 0) {
             cb.exact[(size_t)q * cb.cap + slot] = acc;
             worst = fmaxf(worst, fabsf(acc - cb.score[(size_t)q * cb.cap + slot]));
+            if (kNewOnly) cb.score[(size_t)q * cb.cap + slot] = acc;   // the refresh then ranks exact scores
         }
     }
     if (lane == 0) {
         if (worst > 0.f) atomicMax(reinterpret_cast<int*>(screen_err_max), __float_as_int(worst));
-        if (warp == 0) atomicAdd(rescored, (unsigned long long)cnt);
+        if (warp == 0) atomicAdd(rescored, (unsigned long long)(cnt - first));
+    }
+}
+
+// d = 128 * VPL: the query slice lives in registers, two shortlisted rows are fetched per warp and iteration with
+// all 2*VPL 16-byte loads issued up front (the generic kernel above serialises one load per loop trip and is
+// latency-bound at ~2 TB/s; this one streams the random 3 KB rows at the HBM rate).  Same per-lane FMA order.
+template <bool kNewOnly, int VPL>
+__global__ void __launch_bounds__(128) rescore_vec_kernel(CandBuf cb, const float* __restrict__ qmat, SegTable segs,
+                                                          float* __restrict__ screen_err_max,
+                                                          unsigned long long* __restrict__ rescored) {
+    constexpr int d = VPL * 128;
+    const int q = blockIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
+    const int cnt = (int)min(cb.count[q], cb.cap);
+    const int first = kNewOnly ? (int)min(cb.sorted[q], (uint32_t)cnt) : 0;
+    float4 qv[VPL];
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) qv[i] = __ldg(reinterpret_cast<const float4*>(qmat + (size_t)q * d) + i * 32 + lane);
+    const uint32_t* rows = cb.row + (size_t)q * cb.cap;
+    float worst = 0.f;
+    for (int slot = first + 2 * warp; slot < cnt; slot += 2 * n_warps) {
+        const bool has_b = slot + 1 < cnt;
+        const uint32_t ra = rows[slot], rb = has_b ? rows[slot + 1] : ra;
+        const float4* pa = reinterpret_cast<const float4*>(seg_row_ptr(segs, ra, d));
+        const float4* pb = reinterpret_cast<const float4*>(seg_row_ptr(segs, rb, d));
+        float4 xa[VPL], xb[VPL];
+#pragma unroll
+        for (int i = 0; i < VPL; ++i) {
+            xa[i] = __ldg(pa + i * 32 + lane);
+            xb[i] = __ldg(pb + i * 32 + lane);
+        }
+        float a = 0.f, b = 0.f;
+#pragma unroll
+        for (int i = 0; i < VPL; ++i) {
+            a = lane_fma4(a, qv[i], xa[i]);
+            b = lane_fma4(b, qv[i], xb[i]);
+        }
+        a = warp_sum(a);
+        b = warp_sum(b);
+        if (lane == 0) {
+            const size_t o = (size_t)q * cb.cap + slot;
+            cb.exact[o] = a;
+            worst = fmaxf(worst, fabsf(a - cb.score[o]));
+            if (kNewOnly) cb.score[o] = a;
+            if (has_b) {
+                cb.exact[o + 1] = b;
+                worst = fmaxf(worst, fabsf(b - cb.score[o + 1]));
+                if (kNewOnly) cb.score[o + 1] = b;
+            }
+        }
+    }
+    if (lane == 0) {
+        if (worst > 0.f) atomicMax(reinterpret_cast<int*>(screen_err_max), __float_as_int(worst));
+        if (warp == 0) atomicAdd(rescored, (unsigned long long)(cnt - first));
+    }
+}
+
+template <bool kNewOnly>
+static void launch_rescore_any(CandBuf cb, const float* q, int d, SegTable segs, int nq, float* screen_err_max,
+                               unsigned long long* rescored, cudaStream_t s) {
+    switch (d) {
+        case 128: rescore_vec_kernel<kNewOnly, 1><<<nq, 128, 0, s>>>(cb, q, segs, screen_err_max, rescored); break;
+        case 256: rescore_vec_kernel<kNewOnly, 2><<<nq, 128, 0, s>>>(cb, q, segs, screen_err_max, rescored); break;
+        case 512: rescore_vec_kernel<kNewOnly, 4><<<nq, 128, 0, s>>>(cb, q, segs, screen_err_max, rescored); break;
+        case 768: rescore_vec_kernel<kNewOnly, 6><<<nq, 128, 0, s>>>(cb, q, segs, screen_err_max, rescored); break;
+        case 1024: rescore_vec_kernel<kNewOnly, 8><<<nq, 128, 0, s>>>(cb, q, segs, screen_err_max, rescored); break;
+        default: rescore_kernel<kNewOnly><<<nq, 256, 0, s>>>(cb, q, d, segs, screen_err_max, rescored); break;
     }
 }
 
@@ -248,19 +334,25 @@ void launch_rescore(CandBuf cb, const float* q, int d, SegTable segs, int nq, fl
                     unsigned long long* rescored, cudaStream_t s) {
     cudaMemsetAsync(screen_err_max, 0, sizeof(float), s);
     cudaMemsetAsync(rescored, 0, sizeof(unsigned long long), s);
-    rescore_kernel<<<nq, 256, 0, s>>>(cb, q, d, segs, screen_err_max, rescored);
+    launch_rescore_any<false>(cb, q, d, segs, nq, screen_err_max, rescored, s);
+}
+
+// accumulates into screen_err_max / rescored (the caller zeroes them once per search)
+void launch_rescore_new(CandBuf cb, const float* q, int d, SegTable segs, int nq, float* screen_err_max,
+                        unsigned long long* rescored, cudaStream_t s) {
+    launch_rescore_any<true>(cb, q, d, segs, nq, screen_err_max, rescored, s);
 }
 
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(512) final_select_kernel(CandBuf cb, int k, const int64_t* __restrict__ id_table,
                                                            int64_t id_base, float* __restrict__ D,
-                                                           int64_t* __restrict__ I) {
+                                                           int64_t* __restrict__ I, bool use_score) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     uint64_t* keys = reinterpret_cast<uint64_t*>(smem_raw);
     const int q = blockIdx.x;
     const int cnt = (int)min(cb.count[q], cb.cap);
     const int P = next_pow2(cnt);
-    const float* ex = cb.exact + (size_t)q * cb.cap;
+    const float* ex = (use_score ? cb.score : cb.exact) + (size_t)q * cb.cap;
     const uint32_t* rw = cb.row + (size_t)q * cb.cap;
     for (int i = threadIdx.x; i < P; i += blockDim.x) keys[i] = i < cnt ? cand_key(ex[i], rw[i]) : 0ull;
     bitonic_sort_desc(keys, P);
@@ -331,11 +423,11 @@ void launch_exact_compact(CandBuf cb, int k, const float* margin, float* tau, fl
 }
 
 void launch_final_select(CandBuf cb, int k, int nq, const int64_t* id_table, int64_t id_base, float* D,
-                         int64_t* I, cudaStream_t s) {
+                         int64_t* I, bool use_score, cudaStream_t s) {
     const size_t smem = (size_t)cb.cap * sizeof(uint64_t);
     // the attribute is per device (several devices per process are possible), so it is set per launch
     if (smem > 48 * 1024) cudaFuncSetAttribute(final_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    final_select_kernel<<<nq, 512, smem, s>>>(cb, k, id_table, id_base, D, I);
+    final_select_kernel<<<nq, 512, smem, s>>>(cb, k, id_table, id_base, D, I, use_score);
 }
 
 __global__ void fill_empty_kernel(float* D, int64_t* I, int64_t n) {

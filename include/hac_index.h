@@ -45,6 +45,7 @@ extern "C" {
 #define HAC_PATH_AUTO 0
 #define HAC_PATH_GEMV 1      /* exact fp32 HBM-streaming scan, small query batches */
 #define HAC_PATH_MMA 2       /* tcgen05 f16 screen + exact fp32 rescore of the shortlist */
+#define HAC_PATH_I8 3        /* tcgen05 int8 screen (s32 accumulate) + exact fp32 rescore of every emitted row */
 
 typedef struct hac_index hac_index;
 
@@ -145,7 +146,13 @@ int hac_pinned_free(void* host);
 /* ---- tuning knobs ---------------------------------------------------------------------------
  * Named integer options (unknown names -> HAC_E_INVALID):
  *   "mma_cta_group"  1 = one CTA per scan tile, 2 = CTA pairs sharing each MMA (cta_group::2)
- *   "chunk_growth_x100"  corpus-chunk growth factor of the threshold schedule, in percent (default 400) */
+ *   "chunk_growth_x100"  corpus-chunk growth factor of the threshold schedule, in percent (default 400)
+ *   "default_path"   the scan path HAC_PATH_AUTO resolves to (HAC_PATH_GEMV / _MMA / _I8)
+ *   "build_i8"       1 = also keep an int8 image of the corpus (rows*d bytes of HBM) so that HAC_PATH_I8
+ *                    can be used (default 0; without it HAC_PATH_I8 falls back to HAC_PATH_MMA); empty index only
+ *   "f16_drop_bits_corpus" / "f16_drop_bits_queries"  low mantissa bits of the f16 image forced to zero
+ *                    (0..8, default 3 / 0): sparser operands draw less tensor-core power, the screen margin
+ *                    is computed from the actual rounding error so exactness is unaffected; corpus: empty index only */
 int hac_set_option(hac_index* idx, const char* name, int64_t value);
 
 /* ---- introspection --------------------------------------------------------------------------- */

@@ -367,3 +367,55 @@ def test_device_merge_against_numpy(n_lists, k, k_out):
         wantI = np.concatenate([wantI, np.full((nq, pad), -1, np.int64)], 1)
     assert np.array_equal(Im.cpu().numpy(), wantI[:, :k_out])
     assert np.array_equal(Dm.cpu().numpy(), wantD[:, :k_out])
+
+
+@pytest.mark.parametrize("nq,n,k", [(1, 30011, 100), (5, 257, 10), (130, 50000, 100), (300, 120001, 100),
+                                    (129, 4096, 1), (64, 70000, 1000), (257, 9000, 7)])
+def test_int8_screen_path(nq, n, k):
+    """The int8 tensor-core screen ends in the same exact fp32 scores: bitwise equal to the f16 path."""
+    hb = _engine()
+    rng = np.random.default_rng(nq * 11 + k)
+    x = rng.standard_normal((n, 768), dtype=np.float32)
+    q = rng.standard_normal((nq, 768), dtype=np.float32)
+    idx = hb.FlatIPIndex(768)
+    idx.set_option("build_i8", 1)
+    idx.add(x[: n // 3])
+    idx.add(x[n // 3:])                                  # second append re-quantises the straddled tile
+    D8, I8 = idx.search(q, k, path=hb.HAC_PATH_I8)
+    st = idx.stats()
+    assert st["path"] == hb.HAC_PATH_I8 and st["retries"] == 0, st
+    assert st["screen_err_max"] <= st["margin_max"], st
+    Dm, Im = idx.search(q, k, path=hb.HAC_PATH_MMA)
+    assert np.array_equal(I8, Im) and np.array_equal(D8, Dm)
+    _check(q, x, k, D8, I8, also_fp32_oracle=False)
+
+
+def test_int8_screen_anisotropic_and_scaled_data():
+    hb = _engine()
+    rng = np.random.default_rng(55)
+    mu = rng.standard_normal(768).astype(np.float32)
+    x = (mu + 0.3 * rng.standard_normal((60000, 768))).astype(np.float32) * np.float32(37.0)
+    q = (mu + 0.3 * rng.standard_normal((140, 768))).astype(np.float32) * np.float32(1e-3)
+    idx = hb.FlatIPIndex(768)
+    idx.set_option("build_i8", 1)
+    idx.add(x)
+    D8, I8 = idx.search(q, 100, path=hb.HAC_PATH_I8)
+    st = idx.stats()
+    assert st["screen_err_max"] <= st["margin_max"], st
+    Dm, Im = idx.search(q, 100, path=hb.HAC_PATH_MMA)
+    assert np.array_equal(I8, Im) and np.array_equal(D8, Dm)
+    _check(q, x, 100, D8, I8, also_fp32_oracle=False)
+
+
+def test_int8_screen_mass_duplicates_fall_back():
+    hb = _engine()
+    rng = np.random.default_rng(21)
+    v = rng.standard_normal(768).astype(np.float32)
+    x = np.concatenate([rng.standard_normal((5000, 768), dtype=np.float32), np.tile(v, (30000, 1))], 0)
+    q = (v * rng.uniform(0.5, 2.0, size=(40, 1)) + 0.05 * rng.standard_normal((40, 768))).astype(np.float32)
+    idx = hb.FlatIPIndex(768)
+    idx.set_option("build_i8", 1)
+    idx.add(x)
+    D, I = idx.search(q, 100, path=hb.HAC_PATH_I8)
+    assert idx.stats()["retries"] >= 1
+    assert np.array_equal(I, np.tile(np.arange(5000, 5100), (40, 1)))
