@@ -4,8 +4,8 @@ This is the timed CPU baseline ("port") of bench.py: it follows faiss 1.7.x
 ``IndexFlatIP::search`` for nq >= 20 - fp32 ``sgemm`` over 4096-query x 1024-row
 blocks, then per-query min-heap updates with strict ``>`` - which is what
 `/root/reference/src/test_HAConvDR_topiocqa.py:102` executes on CPU when
-``use_gpu`` is false.  The sgemm is numpy's BLAS; the heap half is
-``flat_ip_c.c`` (OpenMP over queries).
+``use_gpu`` is false.  The sgemm is torch's MKL ``mm`` (numpy's BLAS when torch is absent);
+the heap half is ``flat_ip_c.c`` (OpenMP over queries).
 """
 from __future__ import annotations
 
@@ -60,12 +60,20 @@ def search_blas(q: np.ndarray, x: np.ndarray, k: int, query_block: int = 4096, c
     I = np.empty((nq, k), np.int64)
     L.oracle_heap_init(nq, k, _fp(D), _ip(I))
     buf = np.empty((min(query_block, nq), corpus_block), np.float32)
+    try:                                   # MKL sgemm("N","T") through torch: no transposed-view penalty
+        import torch
+        tq, tx, tbuf = torch.from_numpy(q), torch.from_numpy(x), torch.from_numpy(buf)
+    except ImportError:
+        torch = None
     for q0 in range(0, nq, query_block):
         q1 = min(nq, q0 + query_block)
         for j0 in range(0, n, corpus_block):
             j1 = min(n, j0 + corpus_block)
             ip = buf[: q1 - q0, : j1 - j0]
-            np.matmul(q[q0:q1], x[j0:j1].T, out=ip)
+            if torch is not None:
+                torch.mm(tq[q0:q1], tx[j0:j1].T, out=tbuf[: q1 - q0, : j1 - j0])
+            else:
+                np.matmul(q[q0:q1], x[j0:j1].T, out=ip)
             L.oracle_heap_addn(q1 - q0, k, _fp(D[q0:q1]), _ip(I[q0:q1]), _fp(ip), j1 - j0, buf.shape[1], j0)
     L.oracle_heap_reorder(nq, k, _fp(D), _ip(I))
     return D, I
