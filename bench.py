@@ -45,7 +45,7 @@ def parse_args():
     ap.add_argument("--rows", type=int, default=N_ROWS)
     ap.add_argument("--queries", type=int, default=N_QUERIES)
     ap.add_argument("--k", type=int, default=TOP_K)
-    ap.add_argument("--cpu-sample-rows", type=int, default=400_000)
+    ap.add_argument("--cpu-sample-rows", type=int, default=2_000_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--exchange", default="auto", choices=["auto", "p2p", "nccl"])
     return ap.parse_args()
