@@ -133,15 +133,19 @@ class ShardedInProcessIndex:
 
     def search(self, q, k):
         import torch
+        from concurrent.futures import ThreadPoolExecutor
         q = np.ascontiguousarray(q, dtype=np.float32)
         assert q.ndim == 2 and q.shape[1] == self.d, "search: expected [nq, %d] float32" % self.d
         dev0 = torch.device("cuda", self.devices[0])
         q_host = torch.from_numpy(q).pin_memory()
-        parts = []
-        for dev, sh in zip(self.devices, self.shards):
-            qd = q_host.to(torch.device("cuda", dev), non_blocking=True)
-            with torch.cuda.device(dev):
-                parts.append(sh.search(qd, k))
+
+        def one(dev, sh):                      # one host thread per shard, as faiss IndexShards does;
+            with torch.cuda.device(dev):       # the C-ABI call releases the GIL, so the devices run concurrently
+                qd = q_host.to(torch.device("cuda", dev), non_blocking=True)
+                return sh.search(qd, k)
+
+        with ThreadPoolExecutor(len(self.shards)) as pool:
+            parts = list(pool.map(one, self.devices, self.shards))
         D = torch.stack([p[0].to(dev0) for p in parts])
         I = torch.stack([p[1].to(dev0) for p in parts])
         with torch.cuda.device(dev0):
