@@ -12,6 +12,10 @@ GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+    # the CUDA library is a build artefact (git-ignored): compile it if this is a fresh checkout
+    from haconvdr_b200 import _lib
+    if not os.path.exists(_lib.LIB_PATH):
+        _lib.build()
 
 
 @pytest.fixture(scope="session")
