@@ -260,7 +260,7 @@ def run_ours(args):
     achieved = flops_per_launch_set / (scan_ms_step * 1e-3) / 1e12
     peak = float(peaks.get("bf16_tflops_sustained", 1400.0))
     # DRAM traffic of the scan kernel from the committed `ncu --set full` capture
-    # (profiles/r01_ncu_scan_mma_v3_summary.txt): 29.70 GB read + 0.05 GB written by the launch that covers
+    # (profiles/r01_final_ncu_scan_mma_summary.txt): 29.70 GB read + 0.05 GB written by the launch that covers
     # 19 300 592 rows, i.e. 1539 B per corpus row against 1536 B algorithmic (f16 row): the corpus is read once.
     traffic = 1539.0 * shard_rows
     roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
