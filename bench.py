@@ -77,6 +77,11 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    # torchrun pins OMP_NUM_THREADS=1; the CPU reference uses every host core (before MKL / libgomp load)
+    os.environ["OMP_NUM_THREADS"] = str(os.cpu_count())
+    os.environ["MKL_NUM_THREADS"] = str(os.cpu_count())
+    import torch
+    torch.set_num_threads(os.cpu_count())
     n_sample = min(args.cpu_sample_rows, args.rows)
     t_start = time.perf_counter()
     qps, dt, cores = cpu_port_rate(n_sample, args.queries, args.k, args.rows, steps=args.steps, warmup=args.warmup)
