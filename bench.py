@@ -250,6 +250,41 @@ def run_ours(args):
         phases = {kk: max_over_ranks(vv) for kk, vv in acc.items()}
         barrier()
 
+    # ---- parity spot check run with every timing: 4 queries re-scored in fp64 with torch over the regenerated
+    # corpus (independent of the engine and of oracle/): same top-k ids, scores within 1e-5 relative ---------------
+    n_chk = 4
+    lo = index._bases[0][1]
+    chk_s = torch.full((n_chk, args.k), -float("inf"), dtype=torch.float64, device=dev)
+    chk_i = torch.full((n_chk, args.k), -1, dtype=torch.int64, device=dev)
+    q64 = q_dev[:n_chk].double()
+    for r0 in range(0, shard_rows, 2_000_000):
+        nr = min(2_000_000, shard_rows - r0)
+        xs = synth_rows_device(nr, DIM, seed=42, row0=lo + r0, device=local_rank)
+        sc = q64 @ xs.double().T
+        top = torch.topk(sc, min(args.k, nr), dim=1)
+        cat_s = torch.cat([chk_s, top.values], 1)
+        cat_i = torch.cat([chk_i, top.indices + lo + r0], 1)
+        best = torch.topk(cat_s, args.k, dim=1)
+        chk_s, chk_i = best.values, torch.gather(cat_i, 1, best.indices)
+        del xs, sc
+    if world > 1:
+        gs = [torch.empty_like(chk_s) for _ in range(world)]
+        gi = [torch.empty_like(chk_i) for _ in range(world)]
+        dist.all_gather(gs, chk_s)
+        dist.all_gather(gi, chk_i)
+        cat_s, cat_i = torch.cat(gs, 1), torch.cat(gi, 1)
+        best = torch.topk(cat_s, args.k, dim=1)
+        chk_s, chk_i = best.values, torch.gather(cat_i, 1, best.indices)
+    got_s, got_i = D[:n_chk].double(), I[:n_chk]
+    same_sets = all(set(chk_i[r].tolist()) == set(got_i[r].tolist()) for r in range(n_chk))
+    order = torch.argsort(chk_i, dim=1)
+    ref_sorted = torch.gather(chk_s, 1, order)
+    got_sorted = torch.gather(got_s, 1, torch.argsort(got_i, dim=1))
+    max_rel = float(((ref_sorted - got_sorted).abs() / ref_sorted.abs().clamp_min(1e-30)).max()) if same_sets else float("nan")
+    parity = {"queries_checked": n_chk, "recall_at_k": 1.0 if same_sets else 0.0, "max_rel_score_err": max_rel,
+              "ok": bool(same_sets and max_rel <= 1e-5), "how": "fp64 torch re-scoring of the regenerated corpus"}
+    assert parity["ok"], parity
+
     # ---- sanity: results are plausible for the N(0,1) corpus (rank-100 score ~ 4.5 sigma) ----------
     st = index.local.stats()
     assert st["path"] == HAC_PATH_MMA and st["retries"] == 0, st
@@ -297,6 +332,7 @@ def run_ours(args):
         "e2e": {"value": e2e_qps, "unit": "queries/s", "h2d_bytes_per_step": int(q_host.nbytes),
                 "d2h_bytes_per_step": int(args.queries * args.k * 12), "ms_per_step": e2e_s * 1e3},
         "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu_baseline, "clocks": clocks,
+        "parity_check": parity,
         "stats": {"candidates_emitted_per_step": emitted // args.steps, "candidates_rescored_per_step": rescored // args.steps,
                   "margin_max": st["margin_max"], "screen_err_max": st["screen_err_max"], "n_chunks": st["n_chunks"],
                   "search_ms_per_step_device": total_ms / args.steps, "setup_s": setup_s,

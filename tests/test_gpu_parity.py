@@ -94,7 +94,7 @@ def test_small_batch_gemv_path(nq):
 
 
 @pytest.mark.parametrize("nq,n,k", [(5, 257, 10), (130, 50000, 100), (300, 120001, 100), (129, 4096, 1),
-                                    (64, 70000, 1000), (257, 9000, 7)])
+                                    (64, 70000, 1000), (257, 9000, 7), (33, 30000, 1024)])
 def test_large_batch_mma_path(nq, n, k):
     hb = _engine()
     rng = np.random.default_rng(nq * 7 + k)
