@@ -419,3 +419,21 @@ def test_int8_screen_mass_duplicates_fall_back():
     D, I = idx.search(q, 100, path=hb.HAC_PATH_I8)
     assert idx.stats()["retries"] >= 1
     assert np.array_equal(I, np.tile(np.arange(5000, 5100), (40, 1)))
+
+
+@pytest.mark.parametrize("d", [64, 128, 192, 256, 512, 1024])
+def test_other_dimensions_all_paths(d):
+    """d is fixed to 768 in the reference; the engine takes any multiple of 64 up to 1024."""
+    hb = _engine()
+    rng = np.random.default_rng(d)
+    x = rng.standard_normal((21000, d), dtype=np.float32)
+    q = rng.standard_normal((70, d), dtype=np.float32)
+    idx = hb.FlatIPIndex(d)
+    idx.set_option("build_i8", 1)
+    idx.add(x)
+    D, I = idx.search(q, 20, path=hb.HAC_PATH_MMA)
+    _check(q, x, 20, D, I, also_fp32_oracle=False)
+    Dg, Ig = idx.search(q[:3], 20, path=hb.HAC_PATH_GEMV)
+    assert np.array_equal(Ig, I[:3]) and np.array_equal(Dg, D[:3])
+    D8, I8 = idx.search(q, 20, path=hb.HAC_PATH_I8)          # falls back to the f16 screen when d % 128 != 0
+    assert np.array_equal(I8, I) and np.array_equal(D8, D)
