@@ -61,6 +61,9 @@ struct Workspace {
     uint8_t* q_shadow = nullptr;
     uint8_t* q_shadow8 = nullptr;
     QueryQ8* q_consts = nullptr;
+    uint2* pairs = nullptr;       // int8 path: (row, slot) pairs of one chunk in row order
+    uint32_t* pair_hist = nullptr;   // [2 * pair_buckets + 1]: histogram, cursors, total
+    int64_t pairs_cap = 0, pair_buckets = 0;
     OperandStats* q_stats = nullptr;
     float *q_norm = nullptr, *q_err = nullptr, *margin = nullptr, *tau = nullptr, *thr = nullptr;
     float* scalars = nullptr;     // [0] absmax scratch, [1] margin_max, [2] screen_err_max
@@ -95,6 +98,7 @@ struct hac_index {
     // core draws less with sparser mantissas: 3 dropped corpus bits (an 8-bit significand) run the scan 5 %
     // faster (76.3 -> 72.0 ms measured); the margin grows 0.76 -> 2.3 and 1.6x more rows are rescored (0.2 ms).
     int drop_bits_x = 3, drop_bits_q = 0;
+    bool i8_rescore_by_row = true;          // int8 path: rescore each chunk's emitted rows in row order
     bool build_i8 = false;                  // keep an int8 image of the corpus too (rows*d bytes; HAC_PATH_I8)
     int default_path = HAC_PATH_MMA;        // what HAC_PATH_AUTO resolves to
 };
@@ -250,6 +254,8 @@ void free_workspace(Workspace& w) {
                     w.cb.score, w.cb.row, w.cb.exact, w.cb.count, w.cb.sorted, w.cb.overflow, w.D, w.I};
     for (void* p : ptrs)
         if (p) cudaFree(p);
+    if (w.pairs) cudaFree(w.pairs);
+    if (w.pair_hist) cudaFree(w.pair_hist);
     if (w.host_pinned) cudaFreeHost(w.host_pinned);
     w = Workspace{};
 }
@@ -337,6 +343,24 @@ int search_batch_i8(hac_index* idx, int nq, int nq_pad, const float* q_dev, int 
     cb.cap = cap;
     HostReadback* hr = static_cast<HostReadback*>(w.host_pinned);
     int launches = 0, n_chunks = 0, n_ev = 2;
+    {   // scratch of the row-ordered rescore
+        const int64_t need_pairs = (int64_t)nq_pad * cap;
+        int64_t max_rows = 0;
+        for (const auto& sg : idx->segs) max_rows = std::max(max_rows, sg.n_rows);
+        const int64_t need_buckets = (max_rows >> 11) + 2;
+        if (need_pairs > w.pairs_cap) {
+            if (w.pairs) cudaFree(w.pairs);
+            w.pairs = nullptr; w.pairs_cap = 0;
+            CU(cudaMalloc(&w.pairs, need_pairs * sizeof(uint2)));
+            w.pairs_cap = need_pairs;
+        }
+        if (need_buckets > w.pair_buckets) {
+            if (w.pair_hist) cudaFree(w.pair_hist);
+            w.pair_hist = nullptr; w.pair_buckets = 0;
+            CU(cudaMalloc(&w.pair_hist, (2 * need_buckets + 1) * sizeof(uint32_t)));
+            w.pair_buckets = need_buckets;
+        }
+    }
     cudaEventRecord(idx->ev[0], s);
     launch_init_search(cb, w.tau, w.thr, nq, nq_pad, s);
     launch_convert_queries_i8(q_dev, nq, nq_pad, d, w.q_shadow8, w.q_consts, s);
@@ -379,9 +403,15 @@ int search_batch_i8(hac_index* idx, int nq, int nq_pad, const float* q_dev, int 
                 cudaEventRecord(idx->ev[n_ev + 1], s);
                 n_ev += 2;
             }
-            launch_rescore_new(cb, q_dev, d, segs, nq, w.scalars + 2, w.counters + 1, s);
+            bool by_row = idx->i8_rescore_by_row && r1 - r >= 65536;
+            if (by_row)
+                by_row = launch_rescore_new_by_row(cb, q_dev, d, segs, nq, seg.base + (uint32_t)r, seg.base + (uint32_t)r1,
+                                                   w.pair_hist, w.pair_hist + w.pair_buckets,
+                                                   w.pair_hist + 2 * w.pair_buckets, w.pairs, idx->sm_count,
+                                                   w.scalars + 2, w.counters + 1, s);
+            if (!by_row) launch_rescore_new(cb, q_dev, d, segs, nq, w.scalars + 2, w.counters + 1, s);
             launch_refresh(cb, k, w.margin, w.tau, w.thr, nq, s);
-            launches += 3;
+            launches += by_row ? 6 : 3;
             ++n_chunks;
             rows_done += r1 - r;
             r = r1;
@@ -909,6 +939,7 @@ int hac_set_option(hac_index* idx, const char* name, int64_t value) {
         }
         return HAC_OK;
     }
+    if (strcmp(name, "i8_rescore_by_row") == 0) { idx->i8_rescore_by_row = value != 0; return HAC_OK; }
     if (strcmp(name, "build_i8") == 0) {
         if (idx->ntotal != 0 || !idx->segs.empty()) return fail(HAC_E_STATE, "build_i8 must be set on an empty index");
         idx->build_i8 = value != 0;

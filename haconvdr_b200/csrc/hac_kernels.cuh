@@ -82,6 +82,11 @@ void launch_rescore(CandBuf cb, const float* q, int d, SegTable segs, int nq, fl
 // replaced by the exact one, so the refresh that follows works on exact scores (int8 path)
 void launch_rescore_new(CandBuf cb, const float* q, int d, SegTable segs, int nq, float* screen_err_max,
                         unsigned long long* rescored, cudaStream_t s);
+// same, but the (query, row) pairs are first bucketed by row and rescored in row order (page locality, one HBM
+// fetch per distinct row); scratch: hist/cursor [buckets of 2048 rows + 1], total [1], pairs [max pairs]
+bool launch_rescore_new_by_row(CandBuf cb, const float* q, int d, SegTable segs, int nq, uint32_t row_lo,
+                               uint32_t row_hi, uint32_t* hist, uint32_t* cursor, uint32_t* total, uint2* pairs,
+                               int sm_count, float* screen_err_max, unsigned long long* rescored, cudaStream_t s);
 // final top-k by (exact score desc, id asc) with id translation
 // use_score: the `score` array already holds exact scores (int8 path) - rank by it instead of `exact`
 void launch_final_select(CandBuf cb, int k, int nq, const int64_t* id_table, int64_t id_base, float* D,

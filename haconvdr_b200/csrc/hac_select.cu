@@ -586,3 +586,132 @@ void launch_gather_ids(const int64_t* table, int64_t table_n, const int64_t* ids
 }
 
 }  // namespace hac
+
+// ---------------------------------------------------------------------------------------------
+// int8 path, stage 2 in row order.  The rows a chunk emitted are spread over tens of GB; rescoring them query by
+// query touches a new 2 MB page with almost every row and runs at ~1.6 TB/s (ncu: all warps stalled on
+// long-scoreboard, DRAM 20 % busy).  Here the (query, row) pairs of the chunk are first bucketed by row
+// (counting sort over 2048-row buckets), then rescored in that order: neighbouring warps read neighbouring
+// rows (same pages), and a row emitted by several queries is fetched from HBM once and re-read from L2.
+namespace hac {
+
+constexpr int kPairBucketShift = 11;
+
+__global__ void pairs_hist_kernel(CandBuf cb, int nq, uint32_t row_lo, uint32_t* __restrict__ hist) {
+    const int q = blockIdx.x;
+    const uint32_t cnt = min(cb.count[q], cb.cap), first = min(cb.sorted[q], cnt);
+    const uint32_t* rows = cb.row + (size_t)q * cb.cap;
+    for (uint32_t i = first + threadIdx.x; i < cnt; i += blockDim.x)
+        atomicAdd(hist + ((rows[i] - row_lo) >> kPairBucketShift), 1u);
+}
+
+// exclusive scan of the bucket histogram (one block); cursor <- offsets, total <- number of pairs
+__global__ void __launch_bounds__(1024) pairs_scan_kernel(const uint32_t* __restrict__ hist, int n_buckets,
+                                                          uint32_t* __restrict__ cursor, uint32_t* __restrict__ total) {
+    __shared__ uint32_t warp_sums[32];
+    __shared__ uint32_t carry;
+    if (threadIdx.x == 0) carry = 0u;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int base = 0; base < n_buckets; base += 1024) {
+        const int i = base + threadIdx.x;
+        const uint32_t v = i < n_buckets ? hist[i] : 0u;
+        uint32_t incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        if (lane == 31) warp_sums[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            uint32_t w = warp_sums[lane], wi = w;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t t = __shfl_up_sync(0xffffffffu, wi, o);
+                if (lane >= o) wi += t;
+            }
+            warp_sums[lane] = wi - w;            // exclusive prefix of the warp sums
+        }
+        __syncthreads();
+        const uint32_t excl = carry + warp_sums[warp] + incl - v;
+        if (i < n_buckets) cursor[i] = excl;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry = excl + v;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *total = carry;
+}
+
+__global__ void pairs_scatter_kernel(CandBuf cb, int nq, uint32_t row_lo, uint32_t* __restrict__ cursor,
+                                     uint2* __restrict__ pairs) {
+    const int q = blockIdx.x;
+    const uint32_t cnt = min(cb.count[q], cb.cap), first = min(cb.sorted[q], cnt);
+    const uint32_t* rows = cb.row + (size_t)q * cb.cap;
+    for (uint32_t i = first + threadIdx.x; i < cnt; i += blockDim.x) {
+        const uint32_t row = rows[i];
+        const uint32_t pos = atomicAdd(cursor + ((row - row_lo) >> kPairBucketShift), 1u);
+        pairs[pos] = make_uint2(row, (uint32_t)q * cb.cap + i);      // (row, flat slot in the shortlist arrays)
+    }
+}
+
+template <int VPL>
+__global__ void __launch_bounds__(256) rescore_pairs_kernel(CandBuf cb, const uint2* __restrict__ pairs,
+                                                            const uint32_t* __restrict__ total,
+                                                            const float* __restrict__ qmat, SegTable segs,
+                                                            float* __restrict__ screen_err_max,
+                                                            unsigned long long* __restrict__ rescored) {
+    constexpr int d = VPL * 128;
+    const int lane = threadIdx.x & 31;
+    const uint32_t gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
+    const uint32_t n = *total;
+    float worst = 0.f;
+    for (uint32_t p = gw; p < n; p += n_warps) {                 // consecutive warps take consecutive (row-ordered) pairs
+        const uint2 pr = pairs[p];
+        const uint32_t q = pr.y / cb.cap;
+        const float4* xrow = reinterpret_cast<const float4*>(seg_row_ptr(segs, pr.x, d));
+        const float4* qrow = reinterpret_cast<const float4*>(qmat + (size_t)q * d);
+        float4 xv[VPL], qv[VPL];
+#pragma unroll
+        for (int i = 0; i < VPL; ++i) {
+            xv[i] = __ldg(xrow + i * 32 + lane);
+            qv[i] = __ldg(qrow + i * 32 + lane);
+        }
+        float a = 0.f;
+#pragma unroll
+        for (int i = 0; i < VPL; ++i) a = lane_fma4(a, qv[i], xv[i]);
+        a = warp_sum(a);
+        if (lane == 0) {
+            worst = fmaxf(worst, fabsf(a - cb.score[pr.y]));
+            cb.exact[pr.y] = a;
+            cb.score[pr.y] = a;
+        }
+    }
+    if (lane == 0) {
+        if (worst > 0.f) atomicMax(reinterpret_cast<int*>(screen_err_max), __float_as_int(worst));
+        if (gw == 0) atomicAdd(rescored, (unsigned long long)n);
+    }
+}
+
+// rescore the entries appended since the last refresh, in row order; rows of the chunk lie in [row_lo, row_hi)
+bool launch_rescore_new_by_row(CandBuf cb, const float* q, int d, SegTable segs, int nq, uint32_t row_lo, uint32_t row_hi,
+                               uint32_t* hist, uint32_t* cursor, uint32_t* total, uint2* pairs, int sm_count,
+                               float* screen_err_max, unsigned long long* rescored, cudaStream_t s) {
+    const int n_buckets = (int)(((row_hi - row_lo) >> kPairBucketShift) + 1);
+    cudaMemsetAsync(hist, 0, (size_t)n_buckets * sizeof(uint32_t), s);
+    pairs_hist_kernel<<<nq, 256, 0, s>>>(cb, nq, row_lo, hist);
+    pairs_scan_kernel<<<1, 1024, 0, s>>>(hist, n_buckets, cursor, total);
+    pairs_scatter_kernel<<<nq, 256, 0, s>>>(cb, nq, row_lo, cursor, pairs);
+    const int grid = sm_count * 6;
+    switch (d) {
+        case 128: rescore_pairs_kernel<1><<<grid, 256, 0, s>>>(cb, pairs, total, q, segs, screen_err_max, rescored); break;
+        case 256: rescore_pairs_kernel<2><<<grid, 256, 0, s>>>(cb, pairs, total, q, segs, screen_err_max, rescored); break;
+        case 512: rescore_pairs_kernel<4><<<grid, 256, 0, s>>>(cb, pairs, total, q, segs, screen_err_max, rescored); break;
+        case 768: rescore_pairs_kernel<6><<<grid, 256, 0, s>>>(cb, pairs, total, q, segs, screen_err_max, rescored); break;
+        case 1024: rescore_pairs_kernel<8><<<grid, 256, 0, s>>>(cb, pairs, total, q, segs, screen_err_max, rescored); break;
+        default: return false;
+    }
+    return true;
+}
+
+}  // namespace hac
