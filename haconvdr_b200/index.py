@@ -172,6 +172,20 @@ def merge_topk_peers_device(D_ptrs, I_ptrs, nq: int, k: int, k_out: int, device)
     return D, I
 
 
+def gather_ids_device(table, ids):
+    """offset -> pid on the device (`/root/reference/src/test_HAConvDR_topiocqa.py:250`): ``table`` int64 CUDA
+    tensor (offset2pid), ``ids`` int64 CUDA tensor of offsets (any shape); unfilled slots (-1) map to -1."""
+    import torch
+    assert table.is_cuda and ids.is_cuda and table.dtype == torch.int64 and ids.dtype == torch.int64
+    ids_c = ids.contiguous()
+    out = torch.empty_like(ids_c)
+    stream = torch.cuda.current_stream(ids.device).cuda_stream
+    check(_lib.lib().hac_gather_ids_device(ids.device.index, table.contiguous().data_ptr(), table.numel(),
+                                           ids_c.data_ptr(), ids_c.numel(), out.data_ptr(), stream),
+          "hac_gather_ids_device")
+    return out
+
+
 def synth_rows_device(n: int, d: int, seed: int, row0: int = 0, dist: int = 0, device: int = 0):
     """Rows of the device generator as a CUDA tensor (queries, and read-back for parity tests)."""
     import torch

@@ -437,3 +437,14 @@ def test_other_dimensions_all_paths(d):
     assert np.array_equal(Ig, I[:3]) and np.array_equal(Dg, D[:3])
     D8, I8 = idx.search(q, 20, path=hb.HAC_PATH_I8)          # falls back to the f16 screen when d % 128 != 0
     assert np.array_equal(I8, I) and np.array_equal(D8, D)
+
+
+def test_offset2pid_gather_on_device():
+    import torch
+    from haconvdr_b200.index import gather_ids_device
+    rng = np.random.default_rng(4)
+    table = rng.integers(0, 10**9, size=5000).astype(np.int64)
+    ids = rng.integers(-1, 5000, size=(37, 100)).astype(np.int64)
+    out = gather_ids_device(torch.from_numpy(table).cuda(), torch.from_numpy(ids).cuda()).cpu().numpy()
+    want = np.where(ids >= 0, table[np.maximum(ids, 0)], -1)
+    assert np.array_equal(out, want)
