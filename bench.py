@@ -225,12 +225,15 @@ def run_ours(args):
     qps = args.queries / (ms_per_step * 1e-3)
 
     # ---- end to end through the host-buffer API (`e2e`) -------------------------------------------
+    # results are read back into page-locked arrays the caller owns (faiss-style D=, I= arguments)
+    Dh = torch.empty((args.queries, args.k), dtype=torch.float32).pin_memory().numpy()
+    Ih = torch.empty((args.queries, args.k), dtype=torch.int64).pin_memory().numpy()
     for _ in range(2):
-        Dh, Ih = index.search(q_host, args.k)
+        index.search(q_host, args.k, D=Dh, I=Ih)
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        Dh, Ih = index.search(q_host, args.k)
+        index.search(q_host, args.k, D=Dh, I=Ih)
     torch.cuda.synchronize()
     e2e_s = max_over_ranks((time.perf_counter() - t0) / args.steps)
     barrier()

@@ -95,9 +95,11 @@ class FlatIPIndex:
         check(self._lib.hac_set_id_table(self._h, ids.ctypes.data, ids.shape[0]), "hac_set_id_table")
 
     # -- search -------------------------------------------------------------------------------
-    def search(self, q, k: int, path: int = HAC_PATH_AUTO, out=None):
+    def search(self, q, k: int, path: int = HAC_PATH_AUTO, out=None, D=None, I=None):
         """``out=(D, I)``: optional preallocated CUDA result tensors (float32 / int64 ``[nq, k]``,
-        contiguous) for the tensor path, e.g. views of a symmetric-memory buffer peers read from."""
+        contiguous) for the tensor path, e.g. views of a symmetric-memory buffer peers read from.
+        ``D=``, ``I=``: preallocated NumPy result arrays for the host path, as ``faiss.Index.search`` accepts
+        (page-locked arrays receive the results by direct DMA)."""
         k = int(k)
         if k <= 0 or k > HAC_MAX_K:
             raise ValueError("search: k=%d outside [1, %d]" % (k, HAC_MAX_K))
@@ -123,8 +125,12 @@ class FlatIPIndex:
             q = q.detach().cpu().numpy()
         q = np.ascontiguousarray(q, dtype=np.float32)
         assert q.ndim == 2 and q.shape[1] == self.d, "search: expected [nq, %d] float32" % self.d
-        D = np.empty((q.shape[0], k), dtype=np.float32)
-        I = np.empty((q.shape[0], k), dtype=np.int64)
+        if D is None:
+            D = np.empty((q.shape[0], k), dtype=np.float32)
+        if I is None:
+            I = np.empty((q.shape[0], k), dtype=np.int64)
+        assert D.shape == (q.shape[0], k) and D.dtype == np.float32 and D.flags.c_contiguous
+        assert I.shape == (q.shape[0], k) and I.dtype == np.int64 and I.flags.c_contiguous
         check(self._lib.hac_search_ex(self._h, q.shape[0], q.ctypes.data, k, D.ctypes.data, I.ctypes.data,
                                       int(path)), "hac_search")
         return D, I

@@ -96,17 +96,19 @@ class ShardedFlatIPIndex:
         self.ntotal, self._lo, self._bases = 0, 0, []
 
     # -- search ---------------------------------------------------------------------------------
-    def search(self, q, k: int):
+    def search(self, q, k: int, D=None, I=None):
         """``q``: the same queries on every rank (numpy -> numpy results, CUDA tensor -> CUDA tensors).
-        Returns the merged global (D [Q,k], I [Q,k]) on every rank.
+        Returns the merged global (D [Q,k], I [Q,k]) on every rank.  ``D=``, ``I=``: optional preallocated
+        NumPy result arrays for the host path (page-locked ones receive the results by direct DMA).
 
         Host queries are copied straight from the caller's array when it is page-locked, otherwise
         through a reused pinned staging buffer; host results come back through pinned buffers too."""
         torch, dist = self._torch, self._dist
+        out_D, out_I = D, I                                        # caller's result arrays (host path), may be None
         as_numpy = not (hasattr(q, "is_cuda") and q.is_cuda)
         if as_numpy and self._on_gpu():
             if self.world_size == 1:
-                return self.local.search(q, k)                     # plain host-buffer C-ABI call
+                return self.local.search(q, k, D=out_D, I=out_I)   # plain host-buffer C-ABI call
             qh = torch.from_numpy(np.ascontiguousarray(q, dtype=np.float32))
             if not qh.is_pinned():
                 if self._pinned_q is None or self._pinned_q.shape != qh.shape:
@@ -165,12 +167,23 @@ class ShardedFlatIPIndex:
                                       "merge": ev[2].elapsed_time(ev[3])}
         if as_numpy and torch.is_tensor(D):
             if D.is_cuda:
+                if out_D is not None and out_I is not None:
+                    tD, tI = torch.from_numpy(out_D), torch.from_numpy(out_I)
+                    if tD.is_pinned() and tI.is_pinned():          # caller's page-locked arrays: direct DMA
+                        tD.copy_(D, non_blocking=True)
+                        tI.copy_(I, non_blocking=True)
+                        torch.cuda.current_stream(D.device).synchronize()
+                        return out_D, out_I
                 if self._pinned_out is None or self._pinned_out[0].shape != D.shape:
                     self._pinned_out = (torch.empty(D.shape, dtype=D.dtype).pin_memory(),
                                         torch.empty(I.shape, dtype=I.dtype).pin_memory())
                 self._pinned_out[0].copy_(D, non_blocking=True)
                 self._pinned_out[1].copy_(I, non_blocking=True)
                 torch.cuda.current_stream(D.device).synchronize()
+                if out_D is not None and out_I is not None:
+                    out_D[...] = self._pinned_out[0].numpy()
+                    out_I[...] = self._pinned_out[1].numpy()
+                    return out_D, out_I
                 return self._pinned_out[0].numpy().copy(), self._pinned_out[1].numpy().copy()
             return D.numpy(), I.numpy()
         return D, I

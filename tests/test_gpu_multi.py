@@ -46,6 +46,13 @@ for _ in range(3):                      # alternating slots
     Dp, Ip = idx.search(q, 100)
     assert np.array_equal(Ip, I) and np.array_equal(Dp, D)
 idx.exchange = "auto"
+# faiss-style preallocated outputs, page-locked and ordinary
+Dp = torch.empty((150, 100), dtype=torch.float32).pin_memory().numpy(); Ip = torch.empty((150, 100), dtype=torch.int64).pin_memory().numpy()
+r = idx.search(q, 100, D=Dp, I=Ip)
+assert r[0] is Dp and np.array_equal(Ip, I) and np.array_equal(Dp, D)
+Do = np.empty((150, 100), np.float32); Io = np.empty((150, 100), np.int64)
+idx.search(q, 100, D=Do, I=Io)
+assert np.array_equal(Io, I) and np.array_equal(Do, D)
 
 # synthetic shards reproduce the same global corpus for any world size
 idx.reset()

@@ -439,6 +439,20 @@ def test_other_dimensions_all_paths(d):
     assert np.array_equal(I8, I) and np.array_equal(D8, D)
 
 
+def test_preallocated_host_outputs_like_faiss():
+    hb = _engine()
+    rng = np.random.default_rng(6)
+    x = rng.standard_normal((5000, 768), dtype=np.float32)
+    q = rng.standard_normal((9, 768), dtype=np.float32)
+    idx = hb.FlatIPIndex(768)
+    idx.add(x)
+    D0, I0 = idx.search(q, 10)
+    D = np.empty((9, 10), np.float32)
+    I = np.empty((9, 10), np.int64)
+    r = idx.search(q, 10, D=D, I=I)
+    assert r[0] is D and r[1] is I and np.array_equal(D, D0) and np.array_equal(I, I0)
+
+
 def test_offset2pid_gather_on_device():
     import torch
     from haconvdr_b200.index import gather_ids_device
