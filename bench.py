@@ -220,6 +220,13 @@ def run_ours(args):
     ev1.record()
     barrier()
     clocks = sampler.stop() if rank == 0 else None
+    # per-rank device time of the local search (diagnostic: shows how unevenly the GPUs of the box run)
+    per_rank_ms = [total_ms / args.steps]
+    if world > 1:
+        t = torch.tensor([total_ms / args.steps], dtype=torch.float64, device=dev)
+        g = [torch.empty_like(t) for _ in range(world)]
+        dist.all_gather(g, t)
+        per_rank_ms = [float(v.item()) for v in g]
     ms_per_step = max_over_ranks(ev0.elapsed_time(ev1) / args.steps)
     scan_ms_step = max_over_ranks(scan_ms / args.steps)
     qps = args.queries / (ms_per_step * 1e-3)
@@ -340,6 +347,7 @@ def run_ours(args):
                   "margin_max": st["margin_max"], "screen_err_max": st["screen_err_max"], "n_chunks": st["n_chunks"],
                   "search_ms_per_step_device": total_ms / args.steps, "setup_s": setup_s,
                   "multi_gpu_phase_ms_max_over_ranks": phases,
+                  "local_search_ms_per_rank": [round(v, 3) for v in per_rank_ms],
                   "hbm_fp32_gb": st["bytes_fp32"] / 1e9, "hbm_shadow_gb": st["bytes_shadow"] / 1e9},
     }
     print(json.dumps(line), flush=True)
