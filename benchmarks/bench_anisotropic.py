@@ -1,0 +1,49 @@
+#!/usr/bin/env python
+"""Stress distribution of SURVEY.md 8d: x = mu + 0.3*eps with a shared mean mu (ANCE-like anisotropy: scores
+crowd around |mu|^2 with a small spread), full TopiOCQA scale, one GPU.  Reports throughput, shortlist
+volume and the margin statistics; checks 4 queries against an fp64 re-scoring."""
+import argparse, json, os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--rows", type=int, default=25_700_592)
+    ap.add_argument("--queries", type=int, default=2514)
+    ap.add_argument("--k", type=int, default=100)
+    args = ap.parse_args()
+    import torch
+    from haconvdr_b200 import FlatIPIndex
+    from haconvdr_b200.index import synth_rows_device
+    idx = FlatIPIndex(768, 0, reserve=args.rows)
+    idx.add_synthetic(args.rows, seed=42, dist=1)
+    q = synth_rows_device(args.queries, 768, seed=42, row0=10**9, dist=1)   # same mean vector, fresh noise
+    ts = []
+    for _ in range(5):
+        D, I = idx.search(q, args.k)
+        ts.append(idx.stats())
+    st = sorted(ts, key=lambda s: s["total_ms"])[2]
+    # fp64 check of 4 queries
+    n_chk = 4
+    best_s = torch.full((n_chk, args.k), -float("inf"), dtype=torch.float64, device="cuda")
+    best_i = torch.full((n_chk, args.k), -1, dtype=torch.int64, device="cuda")
+    for r0 in range(0, args.rows, 2_000_000):
+        nr = min(2_000_000, args.rows - r0)
+        xs = synth_rows_device(nr, 768, seed=42, row0=r0, dist=1)
+        sc = q[:n_chk].double() @ xs.double().T
+        top = torch.topk(sc, min(args.k, nr), dim=1)
+        cs, ci = torch.cat([best_s, top.values], 1), torch.cat([best_i, top.indices + r0], 1)
+        b = torch.topk(cs, args.k, dim=1)
+        best_s, best_i = b.values, torch.gather(ci, 1, b.indices)
+        del xs, sc
+    same = all(set(best_i[r].tolist()) == set(I[r].tolist()) for r in range(n_chk))
+    print(json.dumps({"config": "anisotropic corpus x = mu + 0.3*eps, %d x 768, %d queries, k=%d" % (args.rows, args.queries, args.k),
+                      "ms_per_search": st["total_ms"], "scan_ms": st["scan_ms"], "queries_per_s": args.queries / st["total_ms"] * 1e3,
+                      "retries": st["retries"], "n_chunks": st["n_chunks"], "candidates_emitted": st["candidates_emitted"],
+                      "candidates_rescored": st["candidates_rescored"], "margin_max": st["margin_max"],
+                      "screen_err_max": st["screen_err_max"], "score_top1_median": float(D[:, 0].median()),
+                      "score_rank_k_median": float(D[:, -1].median()), "fp64_check_recall": 1.0 if same else 0.0}), flush=True)
+
+
+if __name__ == "__main__":
+    main()

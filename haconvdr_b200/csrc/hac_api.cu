@@ -66,6 +66,7 @@ struct Workspace {
     int64_t pairs_cap = 0, pair_buckets = 0;
     OperandStats* q_stats = nullptr;
     float *q_norm = nullptr, *q_err = nullptr, *margin = nullptr, *tau = nullptr, *thr = nullptr;
+    float* q_shift = nullptr;     // q . centre per query (f16 path)
     float* scalars = nullptr;     // [0] absmax scratch, [1] margin_max, [2] screen_err_max
     unsigned long long* counters = nullptr;  // [0] emitted, [1] rescored
     CandBuf cb{};
@@ -87,6 +88,11 @@ struct hac_index {
     int64_t id_table_n = 0;
     OperandStats* corpus_stats = nullptr;   // index-wide maxima (device)
     float* add_scratch = nullptr;           // absmax scratch for add
+    // screen centre (hac_prep.cu): [d] column means of the first rows added + [1] its norm; fixed until reset
+    float* center = nullptr;
+    double* center_accum = nullptr;
+    bool center_enabled = true, center_valid = false;
+    int sticky_level = 0;                   // searches start in careful mode once the fast mode overflowed (until reset)
     Workspace ws;
     hac_stats stats{};
     cudaEvent_t ev[kMaxEvents] = {};
@@ -101,6 +107,7 @@ struct hac_index {
     bool i8_rescore_by_row = true;          // int8 path: rescore each chunk's emitted rows in row order
     bool build_i8 = false;                  // keep an int8 image of the corpus too (rows*d bytes; HAC_PATH_I8)
     int default_path = HAC_PATH_MMA;        // what HAC_PATH_AUTO resolves to
+    int i8_auto_max_queries = 48;           // HAC_PATH_AUTO takes the int8 screen up to this batch size when the image exists
 };
 
 namespace {
@@ -221,11 +228,17 @@ int add_rows(hac_index* idx, int64_t n, const float* src, RowSource kind, cudaSt
         } else {
             launch_synth(dst, m, d, seed, row0_global + done, dist, s);
         }
+        if (idx->center_enabled && !idx->center_valid && idx->ntotal == 0) {
+            launch_column_mean(dst, std::min<int64_t>(m, 1 << 20), d, idx->center_accum, idx->center, s);
+            idx->center_valid = true;
+        }
+        const float* center = idx->center_valid ? idx->center : nullptr;
         launch_absmax(dst, m * d, idx->add_scratch, s);
         launch_pick_scale(seg->stats, idx->add_scratch, /*keep_scale=*/seg->n_rows > 0 ? 1 : 0, s);
         const int64_t end = seg->n_rows + m;
         const int64_t n_pad = std::min(round_up(end, kRowAlign), seg->cap_rows) - seg->n_rows;
-        launch_convert_rows(dst, m, n_pad, d, seg->shadow, seg->n_rows, seg->stats, nullptr, nullptr, idx->drop_bits_x, s);
+        launch_convert_rows(dst, m, n_pad, d, seg->shadow, seg->n_rows, seg->stats, nullptr, nullptr, idx->drop_bits_x,
+                            center, s);
         if (seg->shadow8 != nullptr) {
             // whole tiles are rebuilt from the fp32 rows (an append into a partly filled tile changes its scale)
             launch_convert_tiles_i8(seg->rows, end, d, seg->n_rows / kTileRows,
@@ -251,7 +264,7 @@ uint32_t cap_for_k(int k, int level) {
 
 void free_workspace(Workspace& w) {
     void* ptrs[] = {w.q, w.q_shadow, w.q_shadow8, w.q_consts, w.q_stats, w.q_norm, w.q_err, w.margin, w.tau, w.thr, w.scalars, w.counters,
-                    w.cb.score, w.cb.row, w.cb.exact, w.cb.count, w.cb.sorted, w.cb.overflow, w.D, w.I};
+                    w.cb.score, w.cb.row, w.cb.exact, w.cb.count, w.cb.sorted, w.cb.overflow, w.D, w.I, w.q_shift};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     if (w.pairs) cudaFree(w.pairs);
@@ -272,11 +285,11 @@ int ensure_workspace(hac_index* idx, int nq_pad, uint32_t cap, int64_t out_elems
     if (nq_pad > w.nq_pad || idx->d != w.d) {
         // per-query arrays
         void* ptrs[] = {w.q, w.q_shadow, w.q_shadow8, w.q_consts, w.q_norm, w.q_err, w.margin, w.tau, w.thr, w.cb.count,
-                        w.cb.sorted, w.cb.score, w.cb.row, w.cb.exact};
+                        w.cb.sorted, w.cb.score, w.cb.row, w.cb.exact, w.q_shift};
         for (void* p : ptrs)
             if (p) cudaFree(p);
         w.q = nullptr; w.q_shadow = nullptr; w.q_shadow8 = nullptr; w.q_consts = nullptr;
-        w.q_norm = w.q_err = w.margin = w.tau = w.thr = nullptr;
+        w.q_norm = w.q_err = w.margin = w.tau = w.thr = w.q_shift = nullptr;
         w.cb.score = w.cb.exact = nullptr; w.cb.row = w.cb.count = w.cb.sorted = nullptr;
         const int np = std::max(nq_pad, w.nq_pad);
         w.nq_pad = 0; w.cap = 0;
@@ -289,6 +302,7 @@ int ensure_workspace(hac_index* idx, int nq_pad, uint32_t cap, int64_t out_elems
         CU(cudaMalloc(&w.margin, np * sizeof(float)));
         CU(cudaMalloc(&w.tau, np * sizeof(float)));
         CU(cudaMalloc(&w.thr, np * sizeof(float)));
+        CU(cudaMalloc(&w.q_shift, np * sizeof(float)));
         CU(cudaMalloc(&w.cb.count, np * sizeof(uint32_t)));
         CU(cudaMalloc(&w.cb.sorted, np * sizeof(uint32_t)));
         w.nq_pad = np; w.d = idx->d;
@@ -335,7 +349,10 @@ int search_batch_i8(hac_index* idx, int nq, int nq_pad, const float* q_dev, int 
                     cudaStream_t s, const SegTable& segs) {
     const int d = idx->d;
     hac_stats& st = idx->stats;
-    const uint32_t cap = cap_for_k(k, 0);
+    // a handful of queries: rescoring is cheap and every chunk costs ~40 us of launch / refresh latency, so the
+    // shortlist is doubled and the chunks grow twice as fast (7 instead of 11 chunks over 25.7M rows)
+    const bool few = nq <= 4 && k <= 128;
+    const uint32_t cap = few ? 2 * cap_for_k(k, 0) : cap_for_k(k, 0);
     int rc = ensure_workspace(idx, nq_pad, cap, 0);
     if (rc != HAC_OK) return rc;
     Workspace& w = idx->ws;
@@ -364,15 +381,15 @@ int search_batch_i8(hac_index* idx, int nq, int nq_pad, const float* q_dev, int 
     cudaEventRecord(idx->ev[0], s);
     launch_init_search(cb, w.tau, w.thr, nq, nq_pad, s);
     launch_convert_queries_i8(q_dev, nq, nq_pad, d, w.q_shadow8, w.q_consts, s);
-    launch_margins(nullptr, nullptr, nullptr, d, w.margin, w.scalars + 1, nq, s);   // refresh margin = 0 (exact scores)
+    launch_margins(nullptr, nullptr, nullptr, nullptr, d, w.margin, w.scalars + 1, nq, s);   // refresh margin = 0 (exact scores)
     launch_margins_i8(w.q_consts, idx->corpus_stats, d, w.q_norm /*scratch*/, w.scalars + 1, nq, s);   // statistics
     cudaMemsetAsync(w.scalars + 2, 0, sizeof(float), s);
     cudaMemsetAsync(w.counters + 1, 0, sizeof(unsigned long long), s);
     launches += 4;
     // the first chunk is emitted unfiltered and rescored exactly, so it is kept small; later chunks grow with the
     // rows seen so far: a chunk is expected to emit about growth * k * exp(m8 * z / sigma) rows per query
-    const double growth = k <= 128 ? 2.0 : 1.0;
-    const int64_t first = std::min<int64_t>(cap / 2, std::max<int64_t>(512, round_up(2 * (int64_t)k, kRowAlign)));
+    const double growth = few ? 4.0 : (k <= 128 ? 2.0 : 1.0);
+    const int64_t first = few ? cap / 2 : std::min<int64_t>(cap / 2, std::max<int64_t>(512, round_up(2 * (int64_t)k, kRowAlign)));
     int64_t rows_done = 0;
     for (size_t si = 0; si < idx->segs.size(); ++si) {
         const Segment& seg = idx->segs[si];
@@ -388,6 +405,7 @@ int search_batch_i8(hac_index* idx, int nq, int nq_pad, const float* q_dev, int 
             a.x_shadow = seg.shadow8;
             a.q_stats = nullptr;
             a.x_stats = nullptr;
+            a.q_shift = nullptr;
             a.x_tiles = seg.tiles8;
             a.q_consts = w.q_consts;
             a.thr = w.thr;
@@ -403,7 +421,9 @@ int search_batch_i8(hac_index* idx, int nq, int nq_pad, const float* q_dev, int 
                 cudaEventRecord(idx->ev[n_ev + 1], s);
                 n_ev += 2;
             }
-            bool by_row = idx->i8_rescore_by_row && r1 - r >= 65536;
+            // row-ordered rescoring pays off when a chunk emits millions of pairs; small batches go straight to the
+            // per-query kernel (its CTAs split each shortlist), three launches less per chunk
+            bool by_row = idx->i8_rescore_by_row && r1 - r >= 65536 && nq >= 256;
             if (by_row)
                 by_row = launch_rescore_new_by_row(cb, q_dev, d, segs, nq, seg.base + (uint32_t)r, seg.base + (uint32_t)r1,
                                                    w.pair_hist, w.pair_hist + w.pair_buckets,
@@ -451,9 +471,14 @@ int search_batch(hac_index* idx, int nq, const float* q_dev, int k, float* D_dev
     // AUTO: the tensor-core screens stream 1/4 (int8) or 1/2 (f16) of the bytes of the fp32 rows, so they win
     // at every batch size (measured: Q=1 5.4 ms f16 vs 11.3 ms fp32 over 25.7M rows); all paths end in the
     // same exact fp32 scores.
-    if (path == HAC_PATH_AUTO) path = idx->default_path;
     bool have_i8 = !idx->segs.empty();
     for (const auto& sg : idx->segs) have_i8 = have_i8 && sg.shadow8 != nullptr;
+    if (path == HAC_PATH_AUTO) {
+        // small batches are HBM-bound: when the int8 image exists its scan streams half the bytes of the f16 one
+        // (measured Q=1: 2.8 ms vs 5.4 ms over 25.7M rows) and rescoring its ~10^4 emitted rows per query is cheap
+        path = (have_i8 && idx->default_path == HAC_PATH_MMA && nq <= idx->i8_auto_max_queries) ? HAC_PATH_I8
+                                                                                                  : idx->default_path;
+    }
     if (path == HAC_PATH_I8 && !have_i8) path = HAC_PATH_MMA;      // d % 128 != 0 or int8 image disabled
     if (path == HAC_PATH_GEMV && nq > 4) return fail(HAC_E_INVALID, "GEMV path takes at most 4 queries per batch");
     if (!idx->events_ready) {
@@ -488,7 +513,9 @@ int search_batch(hac_index* idx, int nq, const float* q_dev, int k, float* D_dev
     //          larger shortlist, the flag is read after every chunk; an overflowing chunk is rolled back and
     //          split in two; when a minimal chunk still overflows the carry-over is cut to its exact top-k
     //          (rescore + exact compaction), which bounds it by k whatever the data.  Always terminates.
-    for (int level = 0; level < 2; ++level) {
+    const float* center = idx->center_valid ? idx->center : nullptr;
+    const int start_level = idx->sticky_level;
+    for (int level = start_level; level < 2; ++level) {
         const bool careful = level == 1;
         const uint32_t cap = cap_for_k(k, level);
         int rc = ensure_workspace(idx, nq_pad, cap, 0);
@@ -505,11 +532,17 @@ int search_batch(hac_index* idx, int nq, const float* q_dev, int k, float* D_dev
             cudaMemsetAsync(w.q_stats, 0, sizeof(OperandStats), s);
             launch_absmax(q_dev, (int64_t)nq * d, w.scalars + 0, s);
             launch_pick_scale(w.q_stats, w.scalars + 0, 0, s);
-            launch_convert_rows(q_dev, nq, nq_pad, d, w.q_shadow, 0, w.q_stats, w.q_norm, w.q_err, idx->drop_bits_q, s);
-            launch_margins(w.q_norm, w.q_err, idx->corpus_stats, d, w.margin, w.scalars + 1, nq, s);
+            launch_convert_rows(q_dev, nq, nq_pad, d, w.q_shadow, 0, w.q_stats, w.q_norm, w.q_err, idx->drop_bits_q,
+                                nullptr, s);
+            launch_margins(w.q_norm, w.q_err, idx->corpus_stats, center ? center + d : nullptr, d, w.margin,
+                           w.scalars + 1, nq, s);
             launches += 4;
+            if (center != nullptr) {
+                launch_query_shift(q_dev, nq, nq_pad, d, center, w.q_shift, s);
+                ++launches;
+            }
         } else {
-            launch_margins(nullptr, nullptr, nullptr, d, w.margin, w.scalars + 1, nq, s);
+            launch_margins(nullptr, nullptr, nullptr, nullptr, d, w.margin, w.scalars + 1, nq, s);
             ++launches;
         }
         auto scan = [&](const Segment& seg, int64_t r, int64_t r1) -> int {
@@ -521,6 +554,7 @@ int search_batch(hac_index* idx, int nq, const float* q_dev, int k, float* D_dev
                 a.x_shadow = seg.shadow;
                 a.q_stats = w.q_stats;
                 a.x_stats = seg.stats;
+                a.q_shift = center != nullptr ? w.q_shift : nullptr;
                 a.thr = w.thr;
                 a.d = d;
                 a.n_qtiles = nq_pad / kTileRows;
@@ -623,8 +657,9 @@ int search_batch(hac_index* idx, int nq, const float* q_dev, int k, float* D_dev
         }
         st.total_ms = ms;
         st.scan_ms = scan_ms;
-        st.retries = retries_before + level;
+        st.retries = retries_before + level - start_level;
         if (!hr->overflow) return HAC_OK;
+        idx->sticky_level = 1;      // this corpus overflows the fast mode: later searches start in careful mode
     }
     return fail(HAC_E_OVERFLOW, "candidate shortlist overflowed even in careful mode");
 }
@@ -722,6 +757,8 @@ int hac_create(int d, int device, hac_index** out) {
     cudaError_t e = cudaStreamCreateWithFlags(&idx->stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaMalloc(&idx->corpus_stats, sizeof(OperandStats));
     if (e == cudaSuccess) e = cudaMalloc(&idx->add_scratch, 4 * sizeof(float));
+    if (e == cudaSuccess) e = cudaMalloc(&idx->center, (size_t)(d + 1) * sizeof(float));
+    if (e == cudaSuccess) e = cudaMalloc(&idx->center_accum, (size_t)d * sizeof(double));
     if (e == cudaSuccess) e = cudaMemset(idx->corpus_stats, 0, sizeof(OperandStats));
     if (e != cudaSuccess) {
         hac_destroy(idx);
@@ -740,6 +777,8 @@ int hac_destroy(hac_index* idx) {
     if (idx->id_table) cudaFree(idx->id_table);
     if (idx->corpus_stats) cudaFree(idx->corpus_stats);
     if (idx->add_scratch) cudaFree(idx->add_scratch);
+    if (idx->center) cudaFree(idx->center);
+    if (idx->center_accum) cudaFree(idx->center_accum);
     if (idx->events_ready)
         for (auto& e : idx->ev) cudaEventDestroy(e);
     if (idx->stream) cudaStreamDestroy(idx->stream);
@@ -822,6 +861,8 @@ int hac_reset(hac_index* idx) {
     }
     idx->id_base = 0;
     idx->ntotal = 0;
+    idx->center_valid = false;      // the next block gets its own centre
+    idx->sticky_level = 0;
     CU(cudaStreamSynchronize(idx->stream));
     return HAC_OK;
 }
@@ -904,6 +945,17 @@ int hac_gather_ids_device(int device, const int64_t* table_dev, int64_t table_n,
     return HAC_OK;
 }
 
+int hac_reciprocal_rank_device(int device, const int64_t* pids_dev, int64_t nq, int k, const int64_t* rel_ptr_dev,
+                               const int64_t* rel_pids_dev, float* rr_out_dev, int32_t* rank_out_dev, void* stream) {
+    if (!pids_dev || !rel_ptr_dev || !rr_out_dev || !rank_out_dev || nq < 0 || k <= 0 || k > 4096)
+        return fail(HAC_E_INVALID, "reciprocal_rank: bad argument");
+    DeviceGuard guard(device);
+    launch_reciprocal_rank(pids_dev, nq, k, rel_ptr_dev, rel_pids_dev, rr_out_dev, rank_out_dev,
+                           static_cast<cudaStream_t>(stream));
+    CU(cudaGetLastError());
+    return HAC_OK;
+}
+
 int hac_pinned_alloc(size_t bytes, void** out_host) {
     if (out_host == nullptr) return fail(HAC_E_INVALID, "pinned_alloc: null out pointer");
     *out_host = nullptr;
@@ -939,7 +991,18 @@ int hac_set_option(hac_index* idx, const char* name, int64_t value) {
         }
         return HAC_OK;
     }
+    if (strcmp(name, "center_screen") == 0) {
+        if (idx->ntotal != 0) return fail(HAC_E_STATE, "center_screen must be set on an empty index");
+        idx->center_enabled = value != 0;
+        idx->center_valid = false;
+        return HAC_OK;
+    }
     if (strcmp(name, "i8_rescore_by_row") == 0) { idx->i8_rescore_by_row = value != 0; return HAC_OK; }
+    if (strcmp(name, "i8_auto_max_queries") == 0) {
+        if (value < 0 || value > kMaxQueryBatch) return fail(HAC_E_INVALID, "i8_auto_max_queries out of range");
+        idx->i8_auto_max_queries = (int)value;
+        return HAC_OK;
+    }
     if (strcmp(name, "build_i8") == 0) {
         if (idx->ntotal != 0 || !idx->segs.empty()) return fail(HAC_E_STATE, "build_i8 must be set on an empty index");
         idx->build_i8 = value != 0;

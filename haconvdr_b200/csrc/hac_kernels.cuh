@@ -56,8 +56,14 @@ void launch_absmax(const float* x, int64_t n_elems, float* absmax_out, cudaStrea
 void launch_pick_scale(OperandStats* stats, const float* absmax_in, int keep_scale, cudaStream_t s);
 // rows [0,n) of x -> shadow rows [row0, row0+n); rows [n, n_pad) are written as zeros.
 // drop_bits: low mantissa bits of the f16 image forced to zero (0 = full 11-bit significand)
+// center: nullptr, or d floats subtracted from every row before rounding (the image then holds x - c)
 void launch_convert_rows(const float* x, int64_t n, int64_t n_pad, int d, uint8_t* shadow, int64_t row0,
-                         OperandStats* stats, float* row_norm, float* row_err, int drop_bits, cudaStream_t s);
+                         OperandStats* stats, float* row_norm, float* row_err, int drop_bits, const float* center,
+                         cudaStream_t s);
+// center[0..d) <- column means of rows [0, n) of x, center[d] <- ||center|| (upper bound); accum: d doubles of scratch
+void launch_column_mean(const float* x, int64_t n, int d, double* accum, float* center, cudaStream_t s);
+// shift[q] = q . center for q < nq, 0 for the padding up to nq_pad
+void launch_query_shift(const float* q, int nq, int nq_pad, int d, const float* center, float* shift, cudaStream_t s);
 void launch_synth(float* out, int64_t n, int d, uint64_t seed, int64_t row0, int dist, cudaStream_t s);
 // int8 images: whole 128-row tiles [tile0, tile1) of a segment are (re)built from its fp32 rows (n_rows valid)
 void launch_convert_tiles_i8(const float* rows, int64_t n_rows, int d, int64_t tile0, int64_t tile1, uint8_t* shadow8,
@@ -71,8 +77,9 @@ void launch_convert_queries_i8(const float* q, int nq, int nq_pad, int d, uint8_
 // ---- search state --------------------------------------------------------------------------
 void launch_init_search(CandBuf cb, float* tau, float* thr, int nq, int nq_pad, cudaStream_t s);
 // margin[q] = ||e_q|| * Xhat_max + ||q|| * Ex_max + slack   (0 when corpus==nullptr: exact scan)
-void launch_margins(const float* q_norm, const float* q_err, const OperandStats* corpus, int d, float* margin,
-                    float* margin_max, int nq, cudaStream_t s);
+// center_norm: nullptr, or a pointer to ||c|| when the corpus image (and its statistics) is centred
+void launch_margins(const float* q_norm, const float* q_err, const OperandStats* corpus, const float* center_norm,
+                    int d, float* margin, float* margin_max, int nq, cudaStream_t s);
 // per query: sort the shortlist, raise tau to the k-th best screen score, drop entries below tau - 2m
 void launch_refresh(CandBuf cb, int k, const float* margin, float* tau, float* thr, int nq, cudaStream_t s);
 // exact fp32 scores of every shortlisted pair
@@ -109,6 +116,7 @@ struct MmaScanArgs {
     const TileQ8* x_tiles;      // int8 path: per-128-row-tile constants of the segment (else nullptr)
     const QueryQ8* q_consts;    // int8 path: per-query constants
     const float* thr;       // [n_qtiles*128] unscaled emission thresholds
+    const float* q_shift;   // f16 path: [n_qtiles*128] q . c of a centred corpus image, or nullptr
     int d;
     int n_qtiles;
     int64_t ct0, ct1;       // 256-row tiles of the segment
@@ -130,5 +138,8 @@ cudaError_t launch_merge_topk_peers(int n_lists, int64_t nq, int k, const float*
                                     cudaStream_t s);
 void launch_gather_ids(const int64_t* table, int64_t table_n, const int64_t* ids, int64_t n, int64_t* out,
                        cudaStream_t s);
+// per query: rank (1-based, 0 = none) and reciprocal rank of the first relevant pid in the deduplicated ranking
+void launch_reciprocal_rank(const int64_t* pids, int64_t nq, int k, const int64_t* rel_ptr, const int64_t* rel_pids,
+                            float* rr_out, int32_t* rank_out, cudaStream_t s);
 
 }  // namespace hac

@@ -231,6 +231,7 @@ __global__ void __launch_bounds__(kThreads, 1) scan_mma_kernel(const MmaScanArgs
         // hidden behind the TMEM drain of the current tile.
         struct UnitConsts {
             float thr;
+            float shift;             // q . c of a centred corpus image (f16 path), else 0
             QueryQ8 qc;
             TileQ8 t0, t1;
         };
@@ -239,6 +240,10 @@ __global__ void __launch_bounds__(kThreads, 1) scan_mma_kernel(const MmaScanArgs
             const int64_t ct = a.ct0 + u / n_qgroups;
             const int q = ((int)(u % n_qgroups) * kCG + (int)cta_rank) * kTileM + quarter * 32 + lane;
             c.thr = a.thr[q];
+            c.shift = 0.f;
+            if constexpr (!kI8) {
+                if (a.q_shift != nullptr) c.shift = a.q_shift[q];
+            }
             if constexpr (kI8) {
                 c.qc = a.q_consts[q];
                 c.t0 = a.x_tiles[2 * ct];
@@ -253,7 +258,13 @@ __global__ void __launch_bounds__(kThreads, 1) scan_mma_kernel(const MmaScanArgs
             const int64_t ct = a.ct0 + u / n_qgroups;
             const int qt = (int)(u % n_qgroups) * kCG + (int)cta_rank;
             const int q = qt * kTileM + quarter * 32 + lane;
-            const float thr_s = cur.thr * scale;         // threshold in accumulator units (power-of-two scale)
+            // threshold in accumulator units (power-of-two scale); the accumulator lacks the per-query constant
+            // q.c of a centred image, so it is taken off the threshold (rounded down: may only lower it) and added
+            // back to the scores that are stored
+            const float shift = cur.shift;
+            float thr_c = cur.thr - shift;
+            if (shift != 0.f) thr_c -= (fabsf(cur.thr) + fabsf(shift)) * 2.4e-7f;
+            const float thr_s = thr_c * scale;
             const int64_t row0 = ct * kTileN;
             // int8: one integer threshold and one de-quantisation factor per 128-row half of the tile
             int thr_i[2] = {0, 0};
@@ -277,7 +288,7 @@ __global__ void __launch_bounds__(kThreads, 1) scan_mma_kernel(const MmaScanArgs
                 };
                 auto value = [&](uint32_t bits) {
                     if constexpr (kI8) return (float)(int)bits * out_scale;
-                    else return __uint_as_float(bits) * out_scale;
+                    else return fmaf(__uint_as_float(bits), out_scale, shift);
                 };
                 bool any = false;
 #pragma unroll

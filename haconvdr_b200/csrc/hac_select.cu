@@ -3,6 +3,7 @@
 // The full score matrix never exists: these kernels only ever see the few hundred candidates
 // per query that passed the fused filter of the scan kernels.
 #include <float.h>
+#include <limits.h>
 
 #include <algorithm>
 
@@ -61,19 +62,30 @@ void launch_init_search(CandBuf cb, float* tau, float* thr, int nq, int nq_pad, 
     init_search_kernel<<<(nq_pad + 255) / 256, 256, 0, s>>>(cb, tau, thr, nq, nq_pad);
 }
 
-// m_q bounds |screen score - exact fp32 score| for every row of the index:
-//   |sum qhat*xhat - sum q*x| <= ||q - qhat||*||xhat|| + ||q||*||x - xhat||        (Cauchy-Schwarz)
-//   + accumulation slack d * 2^-21 * ||q|| * ||x||  (covers truncating fp32 accumulation in the
-//     tensor core and the rounding of the exact fp32 dot product, each <= d * 2^-23 * ||q||*||x||).
-__global__ void margins_kernel(const float* q_norm, const float* q_err, const OperandStats* corpus, int d,
-                               float* margin, float* margin_max, int nq) {
+// m_q bounds |screen score - exact fp32 score| for every row of the index.  With the corpus image centred on c
+// (hac_prep.cu) the screen score is  sum qhat*xhat + fl(q.c)  and xhat approximates v = fl(x - c):
+//   |sum qhat*xhat - q.(x-c)| <= ||q - qhat||*||xhat|| + ||q||*||v - xhat||              (Cauchy-Schwarz)
+//                                + 2^-24 * ||q|| * ||x - c||                              (rounding of x - c)
+//   tensor-core fp32 accumulation (truncating, any order):      <= d * 2^-23 * ||qhat|| * ||xhat||
+//   rounding of the exact fp32 dot (per-lane chain of d/32 FMAs + 5 butterfly adds, hac_common.cuh; the generic
+//   kernel's chain is no longer):                               <= (d/32 + 5) * 2^-24 * ||q|| * ||x||
+//   fl(q.c), the subtraction thr - q.c and the addition a + q.c: <= 3 * 2^-24 * ||q|| * (||c|| + ||x||)
+// All norms of the statistics are those of the centred rows; ||x|| <= ||x - c|| + ||c||.  Every term is taken
+// with a factor >= 2 of safety.
+__global__ void margins_kernel(const float* q_norm, const float* q_err, const OperandStats* corpus,
+                               const float* center_norm, int d, float* margin, float* margin_max, int nq) {
     const int q = blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= nq) return;
     float m = 0.f;
     if (corpus != nullptr) {
         const float qn = q_norm[q], qe = q_err[q];
-        const float xn = fmaxf(corpus->norm_max, corpus->hat_norm_max);
-        m = qe * corpus->hat_norm_max + qn * corpus->err_norm_max + (float)d * 4.76837158e-7f * (qn + qe) * xn;
+        const float cn = center_norm != nullptr ? *center_norm : 0.f;
+        const float xc = fmaxf(corpus->norm_max, corpus->hat_norm_max);      // centred rows
+        const float xu = xc + cn;                                            // uncentred rows
+        m = qe * corpus->hat_norm_max + qn * corpus->err_norm_max
+            + (float)d * 2.38418579e-7f * (qn + qe) * xc                     // d * 2^-22: tensor-core accumulation
+            + (float)(d / 32 + 8) * 1.1920929e-7f * qn * xu                  // (d/32 + 8) * 2^-23: exact fp32 dot
+            + 9.5367432e-7f * qn * (xu + cn);                                // 2^-20: centring round-offs
         m *= 1.001f;
     }
     margin[q] = m;
@@ -96,10 +108,10 @@ void launch_margins_i8(const QueryQ8* q_consts, const OperandStats* corpus, int 
     margins_i8_kernel<<<(nq + 127) / 128, 128, 0, s>>>(q_consts, corpus, d, margin, margin_max, nq);
 }
 
-void launch_margins(const float* q_norm, const float* q_err, const OperandStats* corpus, int d, float* margin,
-                    float* margin_max, int nq, cudaStream_t s) {
+void launch_margins(const float* q_norm, const float* q_err, const OperandStats* corpus, const float* center_norm,
+                    int d, float* margin, float* margin_max, int nq, cudaStream_t s) {
     cudaMemsetAsync(margin_max, 0, sizeof(float), s);
-    margins_kernel<<<(nq + 127) / 128, 128, 0, s>>>(q_norm, q_err, corpus, d, margin, margin_max, nq);
+    margins_kernel<<<(nq + 127) / 128, 128, 0, s>>>(q_norm, q_err, corpus, center_norm, d, margin, margin_max, nq);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -280,7 +292,8 @@ __global__ void __launch_bounds__(128) rescore_vec_kernel(CandBuf cb, const floa
     for (int i = 0; i < VPL; ++i) qv[i] = __ldg(reinterpret_cast<const float4*>(qmat + (size_t)q * d) + i * 32 + lane);
     const uint32_t* rows = cb.row + (size_t)q * cb.cap;
     float worst = 0.f;
-    for (int slot = first + 2 * warp; slot < cnt; slot += 2 * n_warps) {
+    // gridDim.y CTAs share one query's shortlist (small batches: the pairs, not the queries, fill the GPU)
+    for (int slot = first + 2 * (warp + n_warps * (int)blockIdx.y); slot < cnt; slot += 2 * n_warps * (int)gridDim.y) {
         const bool has_b = slot + 1 < cnt;
         const uint32_t ra = rows[slot], rb = has_b ? rows[slot + 1] : ra;
         const float4* pa = reinterpret_cast<const float4*>(seg_row_ptr(segs, ra, d));
@@ -313,19 +326,21 @@ __global__ void __launch_bounds__(128) rescore_vec_kernel(CandBuf cb, const floa
     }
     if (lane == 0) {
         if (worst > 0.f) atomicMax(reinterpret_cast<int*>(screen_err_max), __float_as_int(worst));
-        if (warp == 0) atomicAdd(rescored, (unsigned long long)(cnt - first));
+        if (warp == 0 && blockIdx.y == 0) atomicAdd(rescored, (unsigned long long)(cnt - first));
     }
 }
 
 template <bool kNewOnly>
 static void launch_rescore_any(CandBuf cb, const float* q, int d, SegTable segs, int nq, float* screen_err_max,
                                unsigned long long* rescored, cudaStream_t s) {
+    // about 8 CTAs per SM in total: with few queries each shortlist is split over several CTAs
+    const dim3 grid((unsigned)nq, (unsigned)std::max(1, std::min(64, 1184 / std::max(nq, 1))));
     switch (d) {
-        case 128: rescore_vec_kernel<kNewOnly, 1><<<nq, 128, 0, s>>>(cb, q, segs, screen_err_max, rescored); break;
-        case 256: rescore_vec_kernel<kNewOnly, 2><<<nq, 128, 0, s>>>(cb, q, segs, screen_err_max, rescored); break;
-        case 512: rescore_vec_kernel<kNewOnly, 4><<<nq, 128, 0, s>>>(cb, q, segs, screen_err_max, rescored); break;
-        case 768: rescore_vec_kernel<kNewOnly, 6><<<nq, 128, 0, s>>>(cb, q, segs, screen_err_max, rescored); break;
-        case 1024: rescore_vec_kernel<kNewOnly, 8><<<nq, 128, 0, s>>>(cb, q, segs, screen_err_max, rescored); break;
+        case 128: rescore_vec_kernel<kNewOnly, 1><<<grid, 128, 0, s>>>(cb, q, segs, screen_err_max, rescored); break;
+        case 256: rescore_vec_kernel<kNewOnly, 2><<<grid, 128, 0, s>>>(cb, q, segs, screen_err_max, rescored); break;
+        case 512: rescore_vec_kernel<kNewOnly, 4><<<grid, 128, 0, s>>>(cb, q, segs, screen_err_max, rescored); break;
+        case 768: rescore_vec_kernel<kNewOnly, 6><<<grid, 128, 0, s>>>(cb, q, segs, screen_err_max, rescored); break;
+        case 1024: rescore_vec_kernel<kNewOnly, 8><<<grid, 128, 0, s>>>(cb, q, segs, screen_err_max, rescored); break;
         default: rescore_kernel<kNewOnly><<<nq, 256, 0, s>>>(cb, q, d, segs, screen_err_max, rescored); break;
     }
 }
@@ -583,6 +598,79 @@ void launch_gather_ids(const int64_t* table, int64_t table_n, const int64_t* ids
                        cudaStream_t s) {
     if (n <= 0) return;
     gather_ids_kernel<<<(int)std::min<int64_t>((n + 255) / 256, 1184), 256, 0, s>>>(table, table_n, ids, n, out);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Reciprocal rank of the first relevant passage per query - what trec_eval's `recip_rank` gives for the run
+// file the PRJ drivers write (test_PRJ_topiocqa.py:232-255 ranking, :290-299 run lines, :326-338 evaluation),
+// without writing or parsing a run file.  One CTA per query.  The ranking is the pids in first-occurrence order
+// (a pid seen before is skipped, :249-255); unfilled trailing slots are (0, 0) tuples, i.e. pid 0 at the last
+// rank, and because the evaluator's run dict keeps the LAST line of a repeated passage, a real pid 0 ranked
+// earlier moves to the end as well whenever padding exists.
+constexpr int kRrThreads = 128;
+__global__ void __launch_bounds__(kRrThreads) reciprocal_rank_kernel(const int64_t* __restrict__ pids, int k,
+                                                                     const int64_t* __restrict__ rel_ptr,
+                                                                     const int64_t* __restrict__ rel_pids,
+                                                                     float* __restrict__ rr_out,
+                                                                     int32_t* __restrict__ rank_out) {
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    int64_t* pid = reinterpret_cast<int64_t*>(smem_raw);            // [k]
+    uint8_t* first = reinterpret_cast<uint8_t*>(pid + k);           // [k]
+    __shared__ int s_distinct, s_best;
+    const int64_t q = blockIdx.x;
+    const int64_t r0 = rel_ptr[q], r1 = rel_ptr[q + 1];
+    if (threadIdx.x == 0) { s_distinct = 0; s_best = INT_MAX; }
+    for (int j = threadIdx.x; j < k; j += kRrThreads) pid[j] = pids[q * k + j];
+    __syncthreads();
+    int mine = 0;
+    for (int j = threadIdx.x; j < k; j += kRrThreads) {
+        const int64_t p = pid[j];
+        bool f = p >= 0;                                            // -1: unfilled search slot (k > ntotal)
+        for (int i = 0; f && i < j; ++i) f = pid[i] != p;
+        first[j] = f ? 1 : 0;
+        mine += f ? 1 : 0;
+    }
+    atomicAdd(&s_distinct, mine);
+    __syncthreads();
+    const bool padded = s_distinct < k;
+    int n_ranked = 0;                                               // distinct pids that keep their place
+    if (padded) {
+        for (int j = threadIdx.x; j < k; j += kRrThreads)
+            if (first[j] && pid[j] == 0) first[j] = 0;              // pid 0 is re-ranked behind everything
+        __syncthreads();
+    }
+    for (int j = threadIdx.x; j < k; j += kRrThreads) {
+        if (!first[j]) continue;
+        const int64_t p = pid[j];
+        bool rel = false;
+        for (int64_t r = r0; r < r1 && !rel; ++r) rel = rel_pids[r] == p;
+        if (rel) {
+            int rank = 1;
+            for (int i = 0; i < j; ++i) rank += first[i];
+            atomicMin(&s_best, rank);
+        }
+    }
+    if (padded && threadIdx.x == 0) {
+        bool rel0 = false;
+        for (int64_t r = r0; r < r1 && !rel0; ++r) rel0 = rel_pids[r] == 0;
+        if (rel0) {
+            for (int i = 0; i < k; ++i) n_ranked += first[i];
+            atomicMin(&s_best, n_ranked + 1);
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const int best = s_best;
+        rank_out[q] = best == INT_MAX ? 0 : best;
+        rr_out[q] = best == INT_MAX ? 0.f : 1.f / (float)best;
+    }
+}
+
+void launch_reciprocal_rank(const int64_t* pids, int64_t nq, int k, const int64_t* rel_ptr, const int64_t* rel_pids,
+                            float* rr_out, int32_t* rank_out, cudaStream_t s) {
+    if (nq <= 0) return;
+    const size_t smem = (size_t)k * (sizeof(int64_t) + 1);
+    reciprocal_rank_kernel<<<(unsigned)nq, kRrThreads, smem, s>>>(pids, k, rel_ptr, rel_pids, rr_out, rank_out);
 }
 
 }  // namespace hac

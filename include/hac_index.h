@@ -137,6 +137,15 @@ int hac_merge_topk_peers_device(int device, int n_lists, int64_t nq, int k, cons
 int hac_gather_ids_device(int device, const int64_t* table_dev, int64_t table_n, const int64_t* ids_dev,
                           int64_t n, int64_t* out_dev, void* stream);
 
+/* Reciprocal rank of the first relevant passage per query, fused on the device: what the PRJ drivers obtain by
+ * writing the run file (src/test_PRJ_topiocqa.py:232-255, :290-299) and evaluating `recip_rank` on it with
+ * pytrec_eval (:326-338), the per-query score `improve_judge` (:443-472) then compares.  pids [nq,k]: the
+ * offset -> pid translated result (hac_gather_ids_device); a pid already seen for the query is skipped and slots
+ * left unfilled by that count as pid 0 at the last rank, as in the run file.  rel_ptr [nq+1] / rel_pids: CSR list of
+ * each query's relevant pids.  rr_out [nq] = 1/rank or 0, rank_out [nq] = 1-based rank or 0.  Device pointers. */
+int hac_reciprocal_rank_device(int device, const int64_t* pids_dev, int64_t nq, int k, const int64_t* rel_ptr_dev,
+                               const int64_t* rel_pids_dev, float* rr_out_dev, int32_t* rank_out_dev, void* stream);
+
 /* ---- pinned staging (loader) -----------------------------------------------------------------
  * Page-locked host buffers the block-pickle loader reads file payloads into, so that
  * hac_add runs H2D at full PCIe rate without an extra host copy. */
@@ -150,6 +159,12 @@ int hac_pinned_free(void* host);
  *   "default_path"   the scan path HAC_PATH_AUTO resolves to (HAC_PATH_GEMV / _MMA / _I8)
  *   "build_i8"       1 = also keep an int8 image of the corpus (rows*d bytes of HBM) so that HAC_PATH_I8
  *                    can be used (default 0; without it HAC_PATH_I8 falls back to HAC_PATH_MMA); empty index only
+ *   "center_screen"  1 (default) = the f16 image holds x - c, c = column means of the first rows added after a
+ *                    reset, and the scan adds q.c back: embeddings with a large shared component (ANCE) get a
+ *                    margin made of the centred norms; results are unaffected (exact rescore); empty index only
+ *   "i8_auto_max_queries"  with the int8 image present, HAC_PATH_AUTO takes the int8 screen for batches of at most
+ *                    this many queries (default 48; 0 = never): small batches are HBM-bound and the int8 image is
+ *                    half the bytes of the f16 one
  *   "f16_drop_bits_corpus" / "f16_drop_bits_queries"  low mantissa bits of the f16 image forced to zero
  *                    (0..8, default 3 / 0): sparser operands draw less tensor-core power, the screen margin
  *                    is computed from the actual rounding error so exactness is unaffected; corpus: empty index only */

@@ -86,7 +86,42 @@ def make_prj():
          offset2pid=np.asarray(offset2pid, np.int64), qids=np.asarray(qids), run_text=np.asarray(run_text))
 
 
+def make_prj_judge():
+    """I. ``improve_judge`` of both PRJ drivers (`/root/reference/src/test_PRJ_topiocqa.py:443-472`,
+    `/root/reference/src/test_PRJ_qrecc.py:403-452`): pure Python over the sample ids and a per-sample score list."""
+    mod = ref_harness.load_reference_module("test_PRJ_topiocqa")
+    mod_q = ref_harness.load_reference_module("test_PRJ_qrecc")
+    rng = np.random.default_rng(4711)
+    ids = []
+    for conv in (1, 2, 5):
+        for turn in range(1, int(rng.integers(3, 6))):
+            ids.append("%d-%d-0" % (conv, turn))                       # base query of the turn
+            for hist in range(1, turn):
+                ids.append("%d-%d-%d" % (conv, turn, hist))            # one candidate history turn each
+    # two consecutive conversations ending / starting on the same turn id (the case the qrecc variant adds)
+    ids += ["7-2-0", "7-2-1", "8-2-0", "8-2-1"]
+    scores = [float(v) for v in rng.choice([0.0, 0.05, 0.1, 0.2, 0.25, 1.0 / 3, 0.5, 1.0], size=len(ids))]
+    qrel_ids = ["1-1", "1-2", "5-1", "8-2"]
+    with tempfile.TemporaryDirectory() as d:
+        qf, rf = os.path.join(d, "q.json"), os.path.join(d, "qrel.json")
+        with open(qf, "w") as f:
+            for s in ids:
+                f.write(json.dumps({"id": s}) + "\n")
+        with open(rf, "w") as f:
+            for s in qrel_ids:
+                f.write(json.dumps({"sample_id": s}) + "\n")
+        out_t = mod.improve_judge(qf, scores)
+        out_q = mod_q.improve_judge(qf, scores, rf)
+    path = os.path.join(HERE, "prj_improve_judge.json")
+    with open(path, "w") as f:
+        json.dump({"ids": ids, "scores": scores, "qrel_ids": qrel_ids,
+                   "topiocqa": list(out_t.items()), "qrecc": list(out_q.items())}, f)
+    print("%-34s %8.1f KiB" % ("prj_improve_judge.json", os.path.getsize(path) / 1024))
+
+
 def main():
+    if "--only-prj-judge" in sys.argv:
+        return make_prj_judge()
     if "--only-prj" in sys.argv:
         return make_prj()
     mod = ref_harness.load_reference_module("test_HAConvDR_topiocqa")
@@ -163,6 +198,7 @@ def main():
     save("trec_run_dedup_d64", x0=blocks[0], x1=blocks[1], q=q, k=np.int64(k), D=D, I=I,
          offset2pid=np.asarray(offset2pid, np.int64), qids=np.asarray(qids), run_text=np.asarray(run_text))
     make_prj()
+    make_prj_judge()
 
 
 if __name__ == "__main__":

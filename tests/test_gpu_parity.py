@@ -462,3 +462,92 @@ def test_offset2pid_gather_on_device():
     out = gather_ids_device(torch.from_numpy(table).cuda(), torch.from_numpy(ids).cuda()).cpu().numpy()
     want = np.where(ids >= 0, table[np.maximum(ids, 0)], -1)
     assert np.array_equal(out, want)
+
+
+def test_centred_screen_shrinks_the_margin_and_changes_nothing_else():
+    """ANCE-like rows share a large mean: the f16 image holds x - c, the scan adds q.c back.  Results are
+    bitwise those of the uncentred screen (both end in the exact fp32 rescore), the margin is several times
+    smaller, and far fewer rows need rescoring."""
+    hb = _engine()
+    rng = np.random.default_rng(77)
+    mu = (3.0 * rng.standard_normal(768)).astype(np.float32)
+    x = (mu + 0.3 * rng.standard_normal((80000, 768))).astype(np.float32)
+    q = (mu + 0.3 * rng.standard_normal((200, 768))).astype(np.float32)
+    out = {}
+    for centred in (1, 0):
+        idx = hb.FlatIPIndex(768)
+        idx.set_option("center_screen", centred)
+        idx.add(x[:50000])
+        idx.add(x[50000:])                               # later adds use the centre of the first one
+        D, I = idx.search(q, 100)
+        st = idx.stats()
+        assert st["screen_err_max"] <= st["margin_max"], st
+        out[centred] = (D, I, st)
+        idx.close()
+    assert np.array_equal(out[1][1], out[0][1]) and np.array_equal(out[1][0], out[0][0])
+    assert out[1][2]["margin_max"] < 0.5 * out[0][2]["margin_max"], (out[1][2], out[0][2])
+    assert out[1][2]["candidates_rescored"] <= out[0][2]["candidates_rescored"]
+    _check(q, x, 100, out[1][0], out[1][1])
+
+
+def test_centre_of_an_unrepresentative_first_add_stays_exact():
+    """Any centre keeps the bound rigorous: here it comes from a single outlier row, later blocks look nothing
+    like it, and a reset picks a new one."""
+    hb = _engine()
+    rng = np.random.default_rng(78)
+    x = rng.standard_normal((40000, 768), dtype=np.float32)
+    x[0] = 25.0
+    q = rng.standard_normal((70, 768), dtype=np.float32)
+    idx = hb.FlatIPIndex(768)
+    idx.add(x[:1])
+    idx.add(x[1:])
+    D, I = idx.search(q, 100)
+    st = idx.stats()
+    assert st["screen_err_max"] <= st["margin_max"], st
+    _check(q, x, 100, D, I)
+    idx.reset()
+    idx.add(x[1:])
+    D2, I2 = idx.search(q, 100)
+    assert idx.stats()["margin_max"] < st["margin_max"]
+    _check(q, x[1:], 100, D2, I2)
+
+
+def test_careful_mode_is_sticky_until_reset():
+    hb = _engine()
+    rng = np.random.default_rng(79)
+    v = rng.standard_normal(768).astype(np.float32)
+    x = np.concatenate([rng.standard_normal((5000, 768), dtype=np.float32), np.tile(v, (30000, 1))], 0)
+    q = (v * rng.uniform(0.5, 2.0, size=(40, 1)) + 0.05 * rng.standard_normal((40, 768))).astype(np.float32)
+    idx = hb.FlatIPIndex(768)
+    idx.add(x)
+    D, I = idx.search(q, 100)
+    assert idx.stats()["retries"] == 1
+    D2, I2 = idx.search(q, 100)
+    assert idx.stats()["retries"] == 0                   # started in careful mode: no wasted fast pass
+    assert np.array_equal(I, I2) and np.array_equal(D, D2)
+    assert np.array_equal(I, np.tile(np.arange(5000, 5100), (40, 1)))
+    idx.reset()
+    idx.add(x[:5000])
+    idx.search(q, 100)
+    assert idx.stats()["retries"] == 0
+
+
+@pytest.mark.parametrize("nq", [1, 4, 32, 49])
+def test_auto_path_takes_the_int8_screen_for_small_batches(nq):
+    hb = _engine()
+    rng = np.random.default_rng(80 + nq)
+    x = rng.standard_normal((90000, 768), dtype=np.float32)
+    q = rng.standard_normal((nq, 768), dtype=np.float32)
+    idx = hb.FlatIPIndex(768)
+    idx.set_option("build_i8", 1)
+    idx.add(x)
+    D, I = idx.search(q, 100)
+    st = idx.stats()
+    assert st["path"] == (hb.HAC_PATH_I8 if nq <= 48 else hb.HAC_PATH_MMA), st
+    assert st["candidates_rescored"] >= nq * 100
+    Dm, Im = idx.search(q, 100, path=hb.HAC_PATH_MMA)
+    assert np.array_equal(I, Im) and np.array_equal(D, Dm)
+    _check(q, x, 100, D, I, also_fp32_oracle=False)
+    idx.set_option("i8_auto_max_queries", 0)
+    idx.search(q, 100)
+    assert idx.stats()["path"] == hb.HAC_PATH_MMA
