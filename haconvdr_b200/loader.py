@@ -118,6 +118,145 @@ def parse_ndarray_pickle_header(path: str, max_header: int = 1 << 16) -> BlockHe
     return BlockHeader(shape, "<" + dt, payload_offset, payload_bytes)
 
 
+# ------------------------------------------------------------------------------------------------
+# Engine-native block file: what `gen_doc_embeddings.py:127-155` would write next to (or
+# instead of) the two pickles of a block.  One file per block, little endian:
+#
+#   [0, 4096)            header: magic "HACBLK01", u32 version, u32 d, u64 n_rows, u64 emb_offset, u64 ids_offset,
+#                        u32 ids_kind (0 = int64 array at ids_offset, 1 = contiguous range from id0), i64 id0
+#   [emb_offset, ...)    n_rows * d fp32, C order; emb_offset = 4096, the payload is zero-padded to a 4 KiB multiple
+#   [ids_offset, ...)    n_rows int64 (ids_kind 0), 4 KiB aligned
+#
+# Everything sits on 4 KiB boundaries and a group of 4 rows of d = 768 is 3 pages, so chunks can be read with
+# O_DIRECT straight into the page-locked staging buffers (no page-cache copy, no pickle walk).
+NATIVE_MAGIC = b"HACBLK01"
+NATIVE_ALIGN = 4096
+_NATIVE_HDR = struct.Struct("<8sIIQQQIq")
+
+
+def native_block_path(block_dir: str, block_id: int) -> str:
+    return os.path.join(block_dir, "passage_emb_block_%d.hacb" % block_id)
+
+
+def _pad(n: int) -> int:
+    return (n + NATIVE_ALIGN - 1) // NATIVE_ALIGN * NATIVE_ALIGN
+
+
+def write_native_block(path: str, emb, embid) -> str:
+    """Write one block (``emb`` float32 ``[n, d]``, ``embid`` int64 ``[n]``) in the native format.  Contiguous ids
+    (the non-distributed encoder's output, `/root/reference/src/utils.py:140-143`) are stored as a range."""
+    emb = np.ascontiguousarray(emb, dtype=np.float32)
+    embid = np.ascontiguousarray(embid, dtype=np.int64)
+    assert emb.ndim == 2 and embid.shape == (emb.shape[0],)
+    n, d = emb.shape
+    is_range = n == 0 or bool(np.array_equal(embid, np.arange(embid[0], embid[0] + n, dtype=np.int64)))
+    emb_off = NATIVE_ALIGN
+    ids_off = emb_off + _pad(n * d * 4)
+    hdr = _NATIVE_HDR.pack(NATIVE_MAGIC, 1, d, n, emb_off, 0 if is_range else ids_off, 1 if is_range else 0,
+                           int(embid[0]) if n else 0)
+    tmp = path + ".tmp"
+    with open(tmp, "wb") as f:
+        f.write(hdr.ljust(NATIVE_ALIGN, b"\0"))
+        f.write(memoryview(emb).cast("B"))
+        f.write(b"\0" * (_pad(n * d * 4) - n * d * 4))
+        if not is_range:
+            f.write(memoryview(embid).cast("B"))
+            f.write(b"\0" * (_pad(n * 8) - n * 8))
+    os.replace(tmp, path)
+    return path
+
+
+class NativeHeader:
+    def __init__(self, d, n_rows, emb_offset, ids_offset, ids_kind, id0):
+        self.d, self.n_rows, self.emb_offset = d, n_rows, emb_offset
+        self.ids_offset, self.ids_kind, self.id0 = ids_offset, ids_kind, id0
+        self.shape, self.dtype = (n_rows, d), np.dtype("<f4")
+        self.payload_offset, self.payload_bytes = emb_offset, n_rows * d * 4
+
+
+def read_native_header(path: str) -> NativeHeader:
+    with open(path, "rb") as f:
+        raw = f.read(_NATIVE_HDR.size)
+    if len(raw) < _NATIVE_HDR.size:
+        raise ValueError("%s is too short for a native block" % path)
+    magic, version, d, n, emb_off, ids_off, kind, id0 = _NATIVE_HDR.unpack(raw)
+    if magic != NATIVE_MAGIC or version != 1:
+        raise ValueError("%s is not a version-1 native block" % path)
+    need = emb_off + n * d * 4 if kind == 1 else ids_off + n * 8
+    if emb_off % NATIVE_ALIGN or (kind == 0 and ids_off % NATIVE_ALIGN) or kind not in (0, 1) or os.path.getsize(path) < need:
+        raise ValueError("%s has a corrupt or truncated native header" % path)
+    return NativeHeader(d, n, emb_off, ids_off, kind, id0)
+
+
+def load_native_embid(path: str, hdr: NativeHeader = None) -> np.ndarray:
+    hdr = hdr or read_native_header(path)
+    if hdr.ids_kind == 1:
+        return np.arange(hdr.id0, hdr.id0 + hdr.n_rows, dtype=np.int64)
+    with open(path, "rb") as f:
+        f.seek(hdr.ids_offset)
+        return np.fromfile(f, dtype="<i8", count=hdr.n_rows)
+
+
+def convert_block_to_native(block_dir: str, block_id: int, chunk_bytes: int = 64 << 20) -> str:
+    """Pickle pair -> native file, streaming the payload (never holds the 7.7 GB array in memory)."""
+    emb_path, embid_path = block_paths(block_dir, block_id)
+    out = native_block_path(block_dir, block_id)
+    try:
+        hdr = parse_ndarray_pickle_header(emb_path)
+        if hdr.dtype != np.dtype("<f4") or len(hdr.shape) != 2:
+            raise ValueError("unexpected layout")
+    except ValueError:
+        with open(emb_path, "rb") as h:
+            return write_native_block(out, pickle.load(h), load_embid(embid_path))
+    embid = load_embid(embid_path)
+    n, d = hdr.shape
+    assert embid.shape == (n,)
+    is_range = n == 0 or bool(np.array_equal(embid, np.arange(embid[0], embid[0] + n, dtype=np.int64)))
+    ids_off = NATIVE_ALIGN + _pad(n * d * 4)
+    head = _NATIVE_HDR.pack(NATIVE_MAGIC, 1, d, n, NATIVE_ALIGN, 0 if is_range else ids_off, 1 if is_range else 0,
+                            int(embid[0]) if n else 0)
+    tmp = out + ".tmp"
+    with open(emb_path, "rb") as src, open(tmp, "wb") as dst:
+        dst.write(head.ljust(NATIVE_ALIGN, b"\0"))
+        src.seek(hdr.payload_offset)
+        left = hdr.payload_bytes
+        while left:
+            buf = src.read(min(chunk_bytes, left))
+            if not buf:
+                raise IOError("short read in %s" % emb_path)
+            dst.write(buf)
+            left -= len(buf)
+        dst.write(b"\0" * (_pad(n * d * 4) - n * d * 4))
+        if not is_range:
+            dst.write(memoryview(embid).cast("B"))
+            dst.write(b"\0" * (_pad(n * 8) - n * 8))
+    os.replace(tmp, out)
+    return out
+
+
+def load_block_array(path: str) -> np.ndarray:
+    """The whole embedding array of a block file on the host (what ``pickle.load`` gives the reference)."""
+    if path.endswith(".hacb"):
+        hdr = read_native_header(path)
+        with open(path, "rb") as f:
+            f.seek(hdr.emb_offset)
+            return np.fromfile(f, dtype="<f4", count=hdr.n_rows * hdr.d).reshape(hdr.n_rows, hdr.d)
+    with open(path, "rb") as h:
+        return pickle.load(h)
+
+
+def find_block(block_dir: str, block_id: int):
+    """(embedding file, loader of its id array) of a block, preferring the native file; None when the block
+    is missing (the reference stops at the first missing block, `:94-95`)."""
+    nat = native_block_path(block_dir, block_id)
+    if os.path.isfile(nat):
+        return nat, (lambda: load_native_embid(nat))
+    emb_path, embid_path = block_paths(block_dir, block_id)
+    if os.path.isfile(emb_path) and os.path.isfile(embid_path):
+        return emb_path, (lambda: load_embid(embid_path))
+    return None
+
+
 class PinnedBuffer:
     def __init__(self, nbytes: int):
         self.ptr = ctypes.c_void_p()
@@ -141,16 +280,23 @@ def load_embid(path: str) -> np.ndarray:
         return np.ascontiguousarray(pickle.load(h), dtype=np.int64)
 
 
-def stream_block_into(index, emb_path: str, chunk_bytes: int = 64 << 20, buffers=None, row_range=None) -> int:
-    """Append the rows of one embedding block file to ``index`` (a FlatIPIndex) through pinned
-    staging.  ``row_range=(lo, hi)`` appends only rows [lo, hi) of the block (a rank's slice of a
-    block that straddles two shards).  Returns the number of rows appended.  Falls back to
-    ``pickle.load`` + ``add`` for pickles the header walker does not understand."""
+def stream_block_into(index, emb_path: str, chunk_bytes: int = 64 << 20, buffers=None, row_range=None,
+                      direct=None, stats=None) -> int:
+    """Append the rows of one embedding block file (pickle ``.pb`` or native ``.hacb``) to ``index`` (a
+    FlatIPIndex) through pinned staging.  ``row_range=(lo, hi)`` appends only rows [lo, hi) of the block (a
+    rank's slice of a block that straddles two shards).  Returns the number of rows appended.  Falls back to
+    ``pickle.load`` + ``add`` for pickles the header walker does not understand.  ``direct=True`` (or
+    ``HAC_LOADER_DIRECT=1``) reads native blocks with O_DIRECT when the file system allows it; ``stats`` (a dict)
+    receives ``{"direct": bool}``."""
+    stats = stats if stats is not None else {}
+    native = emb_path.endswith(".hacb")
     try:
-        hdr = parse_ndarray_pickle_header(emb_path)
+        hdr = read_native_header(emb_path) if native else parse_ndarray_pickle_header(emb_path)
         if hdr.dtype != np.dtype("<f4") or len(hdr.shape) != 2 or hdr.shape[1] != index.d:
             raise ValueError("unexpected block layout %s %s" % (hdr.dtype, hdr.shape))
     except ValueError:
+        if native:
+            raise
         with open(emb_path, "rb") as h:
             arr = pickle.load(h)
         if row_range is not None:
@@ -158,10 +304,15 @@ def stream_block_into(index, emb_path: str, chunk_bytes: int = 64 << 20, buffers
         index.add(arr)
         return int(arr.shape[0])
     row_bytes = hdr.shape[1] * 4
-    rows_per_chunk = max(1, chunk_bytes // row_bytes)
+    # chunks start on a multiple of `align_rows` rows, i.e. on a 4 KiB file boundary of a native block
+    align_rows = NATIVE_ALIGN // np.gcd(row_bytes, NATIVE_ALIGN)
+    rows_per_chunk = max(align_rows, chunk_bytes // row_bytes // align_rows * align_rows)
     own = buffers is None
-    bufs = buffers or [PinnedBuffer(rows_per_chunk * row_bytes) for _ in range(2)]
-    rows_per_chunk = min(rows_per_chunk, bufs[0].nbytes // row_bytes)
+    bufs = buffers or [PinnedBuffer(rows_per_chunk * row_bytes + NATIVE_ALIGN) for _ in range(2)]
+    rows_per_chunk = min(rows_per_chunk, max(1, (bufs[0].nbytes - NATIVE_ALIGN) // row_bytes // align_rows * align_rows))
+    if direct is None:
+        direct = os.environ.get("HAC_LOADER_DIRECT", "0") == "1"
+    direct = bool(direct and native and hasattr(os, "O_DIRECT") and bufs[0].ptr.value % NATIVE_ALIGN == 0)
     L = _lib.lib()
     lo, hi = (0, hdr.shape[0]) if row_range is None else (max(0, row_range[0]), min(hdr.shape[0], row_range[1]))
     n_rows = max(0, hi - lo)
@@ -185,13 +336,24 @@ def stream_block_into(index, emb_path: str, chunk_bytes: int = 64 << 20, buffers
     def reader():
         try:
             from concurrent.futures import ThreadPoolExecutor
-            fd = os.open(emb_path, os.O_RDONLY)
+            fd = -1
+            use_direct = direct and lo % align_rows == 0
+            if use_direct:
+                try:
+                    fd = os.open(emb_path, os.O_RDONLY | os.O_DIRECT)
+                except OSError:             # tmpfs and some overlay mounts refuse O_DIRECT
+                    use_direct = False
+            if fd < 0:
+                fd = os.open(emb_path, os.O_RDONLY)
+            stats["direct"] = use_direct
             try:
                 with ThreadPoolExecutor(n_readers) as pool:
                     for i, (r0, nr) in enumerate(chunks):
                         b = i % len(bufs)
                         freed[b].acquire()
-                        mv = memoryview(bufs[b].view).cast("B")[: nr * row_bytes]
+                        # O_DIRECT wants whole pages: the tail chunk reads into the file's zero padding
+                        want = _pad(nr * row_bytes) if use_direct else nr * row_bytes
+                        mv = memoryview(bufs[b].view).cast("B")[:want]
                         base = hdr.payload_offset + r0 * row_bytes
                         step = (len(mv) + n_readers - 1) // n_readers
                         step = (step + 4095) // 4096 * 4096

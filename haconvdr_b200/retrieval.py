@@ -18,8 +18,6 @@ search yields the global top-k - the first ``topN`` columns of the reference res
 from __future__ import annotations
 
 import logging
-import os
-import pickle
 import time
 
 import numpy as np
@@ -46,16 +44,16 @@ def search_one_by_one_with_faiss(args, passge_embeddings_dir, index, query_embed
     merged_s = merged_i = None
     for block_id in range(_block_num(args)):
         logger.info("Loading passage block " + str(block_id))
-        emb_path, embid_path = loader.block_paths(passge_embeddings_dir, block_id)
-        if not (os.path.isfile(emb_path) and os.path.isfile(embid_path)):
+        found = loader.find_block(passge_embeddings_dir, block_id)      # native .hacb if present, else the pickles
+        if found is None:
             break                      # reference: bare `except: break` on the first missing block (:94-95)
-        passage_embedding2id = loader.load_embid(embid_path)
+        emb_path, load_ids = found
+        passage_embedding2id = load_ids()
         impl = getattr(index, "_get", lambda: index)()
         if hasattr(impl, "_h"):
             loader.stream_block_into(impl, emb_path)
         else:
-            with open(emb_path, "rb") as handle:
-                index.add(pickle.load(handle))
+            index.add(loader.load_block_array(emb_path))
         logger.info("query embedding shape: " + str(query_embeddings.shape))
         tb = time.time()
         D, I = index.search(query_embeddings, topN)
@@ -86,10 +84,11 @@ def load_resident(index, passage_embeddings_dir, passage_block_num, row_range=No
     ids, n_blocks, seen = [], 0, 0
     impl = getattr(index, "_get", lambda: index)()
     for block_id in range(_block_num(passage_block_num)):
-        emb_path, embid_path = loader.block_paths(passage_embeddings_dir, block_id)
-        if not (os.path.isfile(emb_path) and os.path.isfile(embid_path)):
+        found = loader.find_block(passage_embeddings_dir, block_id)
+        if found is None:
             break
-        emb2id = loader.load_embid(embid_path)
+        emb_path, load_ids = found
+        emb2id = load_ids()
         nb = emb2id.shape[0]
         if row_range is None:
             loader.stream_block_into(impl, emb_path)

@@ -102,3 +102,47 @@ def test_faiss_compat_surface_builds_without_gpu():
     vres.push_back(res)
     idx = faiss.index_cpu_to_gpu_multiple(vres, vdev, faiss.IndexFlatIP(768), co)   # lazy: no device touched
     assert idx.d == 768 and idx.ntotal == 0
+
+
+def test_native_block_file_round_trip_and_conversion():
+    """Engine-native block files: header, 4 KiB alignment, contiguous ids stored as a range,
+    arbitrary ids as an array; converting the reference's pickle pair gives the same bytes as writing directly."""
+    rng = np.random.default_rng(12)
+    x = rng.standard_normal((1037, 768)).astype(np.float32)
+    with tempfile.TemporaryDirectory() as d:
+        p = loader.write_native_block(loader.native_block_path(d, 0), x, np.arange(500, 1537, dtype=np.int64))
+        h = loader.read_native_header(p)
+        assert (h.n_rows, h.d, h.ids_kind, h.id0, h.emb_offset) == (1037, 768, 1, 500, 4096)
+        assert os.path.getsize(p) % 4096 == 0
+        assert np.array_equal(loader.load_block_array(p), x)
+        assert np.array_equal(loader.load_native_embid(p), np.arange(500, 1537))
+        ids = rng.permutation(5000)[:1037].astype(np.int64)
+        p1 = loader.write_native_block(loader.native_block_path(d, 1), x, ids)
+        h1 = loader.read_native_header(p1)
+        assert h1.ids_kind == 0 and h1.ids_offset % 4096 == 0
+        assert np.array_equal(loader.load_native_embid(p1), ids)
+        # pickle pair -> native, streamed
+        write_blocks(d, [x, x[:10]], 500)
+        os.remove(p)
+        assert loader.convert_block_to_native(d, 0) == p
+        assert np.array_equal(loader.load_block_array(p), x) and loader.read_native_header(p).id0 == 500
+        with open(p, "r+b") as f:           # corrupt magic -> rejected
+            f.write(b"XXXX")
+        with pytest.raises(ValueError):
+            loader.read_native_header(p)
+
+
+@pytest.mark.parametrize("name", ["merge_3blocks_d64", "short_two_blocks_d64", "block_num_limit_d64"])
+def test_reference_loop_over_native_blocks_matches_golden(name):
+    """Same golden outputs when every block exists only as a native file (the pickles are deleted)."""
+    g = load_golden(name)
+    with tempfile.TemporaryDirectory() as d:
+        write_blocks(d, g["blocks"], g["id_start"])
+        for b in range(len(g["blocks"])):
+            loader.convert_block_to_native(d, b)
+            for p in loader.block_paths(d, b):
+                os.remove(p)
+        nb = int(g.get("block_num", len(g["blocks"]) + 3))
+        D, I = retrieval.search_one_by_one_with_faiss(nb, d, FlatIP(g["q"].shape[1]), g["q"], g["k"])
+    assert np.array_equal(I, g["I"])
+    np.testing.assert_allclose(D, g["D"], rtol=1e-6, atol=0)

@@ -551,3 +551,31 @@ def test_auto_path_takes_the_int8_screen_for_small_batches(nq):
     idx.set_option("i8_auto_max_queries", 0)
     idx.search(q, 100)
     assert idx.stats()["path"] == hb.HAC_PATH_MMA
+
+
+@pytest.mark.parametrize("direct", [False, True])
+def test_native_block_files_stream_into_the_index(direct):
+    """A native .hacb block streamed through pinned staging - with O_DIRECT where the file
+    system allows it - gives the same index as the pickle of the same rows, whole or as a row slice."""
+    hb = _engine()
+    from haconvdr_b200 import loader
+    rng = np.random.default_rng(31)
+    x = rng.standard_normal((45003, 768), dtype=np.float32)      # not a multiple of 4 rows: padded tail page
+    q = rng.standard_normal((20, 768), dtype=np.float32)
+    with tempfile.TemporaryDirectory() as tmp:
+        write_blocks(tmp, [x], 0)
+        nat = loader.convert_block_to_native(tmp, 0)
+        ref = hb.FlatIPIndex(768)
+        loader.stream_block_into(ref, loader.block_paths(tmp, 0)[0])
+        Dr, Ir = ref.search(q, 50)
+        idx = hb.FlatIPIndex(768)
+        st = {}
+        n = loader.stream_block_into(idx, nat, chunk_bytes=8 << 20, direct=direct, stats=st)
+        assert n == 45003 and idx.ntotal == 45003 and (not st["direct"] or direct)
+        D, I = idx.search(q, 50)
+        assert np.array_equal(I, Ir) and np.array_equal(D, Dr)
+        _check(q, x, 50, D, I, also_fp32_oracle=False)
+        idx.reset()
+        loader.stream_block_into(idx, nat, chunk_bytes=8 << 20, direct=direct, row_range=(10000, 30001))
+        D2, I2 = idx.search(q, 50)
+        _check(q, x[10000:30001], 50, D2, I2, also_fp32_oracle=False)
