@@ -48,7 +48,18 @@ def parse_args():
     ap.add_argument("--cpu-sample-rows", type=int, default=2_000_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--exchange", default="auto", choices=["auto", "p2p", "nccl"])
-    return ap.parse_args()
+    ap.add_argument("--workload", default="topiocqa", choices=["topiocqa", "qrecc"],
+                    help="qrecc = BASELINE.json configs[2]: 54 573 064 x 768, 8209 queries (needs >= 2 GPUs)")
+    args = ap.parse_args()
+    if args.workload == "qrecc":
+        global METRIC, WORKLOAD
+        METRIC = "queries/sec, exact top-100, 54.6Mx768"
+        WORKLOAD = "qrecc-scale synthetic 54.6Mx768 fp32, 8209 queries, top_k=100 (BASELINE.json configs[2])"
+        if args.rows == N_ROWS:
+            args.rows = 54_573_064
+        if args.queries == N_QUERIES:
+            args.queries = 8209
+    return args
 
 
 # ------------------------------------------------------------------------------------------------

@@ -45,26 +45,29 @@ def main():
     ap.add_argument("--only", default="small,ksweep,qrecc")
     args = ap.parse_args()
     import torch
-    from haconvdr_b200 import FlatIPIndex, HAC_PATH_GEMV, HAC_PATH_MMA
+    from haconvdr_b200 import FlatIPIndex, HAC_PATH_GEMV, HAC_PATH_I8, HAC_PATH_MMA
     from haconvdr_b200.index import synth_rows_device
     pk, kind = peaks()
     only = set(args.only.split(","))
     d = 768
-    names = {HAC_PATH_GEMV: "gemv_fp32", HAC_PATH_MMA: "mma_f16_screen"}
+    names = {HAC_PATH_GEMV: "gemv_fp32", HAC_PATH_MMA: "mma_f16_screen", HAC_PATH_I8: "mma_i8_screen"}
+    bytes_per_elem = {HAC_PATH_GEMV: 4, HAC_PATH_MMA: 2, HAC_PATH_I8: 1}
 
     if only & {"small", "ksweep"}:
-        idx = FlatIPIndex(d, 0, reserve=args.rows)
+        idx = FlatIPIndex(d, 0)
+        idx.set_option("build_i8", 1)        # + rows*768 B of HBM: the int8 image the small-batch screen streams
+        idx.reserve(args.rows)
         idx.add_synthetic(args.rows, seed=42)
         n = idx.ntotal
         if "small" in only:
-            for nq, paths in ((1, (HAC_PATH_GEMV, HAC_PATH_MMA)), (4, (HAC_PATH_GEMV, HAC_PATH_MMA)),
-                              (32, (HAC_PATH_MMA,))):
+            for nq, paths in ((1, (HAC_PATH_GEMV, HAC_PATH_MMA, HAC_PATH_I8)), (4, (HAC_PATH_GEMV, HAC_PATH_MMA, HAC_PATH_I8)),
+                              (32, (HAC_PATH_MMA, HAC_PATH_I8))):
                 q = synth_rows_device(nq, d, seed=4242)
                 for path in paths:
                     med, best = timed(lambda: idx.search(q, 100, path=path), args.reps)
                     st = idx.stats()
-                    # bytes the scan has to stream once: fp32 rows (GEMV, SURVEY 8d: N*768*4) or the f16 shadow
-                    moved = n * d * (4 if path == HAC_PATH_GEMV else 2)
+                    # bytes the scan has to stream once: fp32 rows (GEMV, SURVEY 8d: N*768*4), the f16 or the int8 image
+                    moved = n * d * bytes_per_elem[path]
                     algo_bytes = moved
                     print(json.dumps({
                         "config": "turn latency Q=%d over %dx768, k=100" % (nq, n), "path": names[path],
@@ -74,9 +77,11 @@ def main():
                                      "peak": pk["hbm_gbs"], "unit": "GB/s",
                                      "frac": algo_bytes / (st["scan_ms"] * 1e-3) / 1e9 / pk["hbm_gbs"],
                                      "bytes_per_batch": moved, "fp32_corpus_bytes": n * d * 4,
+                                     "survey_8d_gbs": n * d * 4 / (med * 1e-3) / 1e9,   # N*768*4 B per batch / whole latency
                                      "peak_source": kind + " hbm_gbs (copy = half reads, half writes; a pure read "
                                                            "stream can exceed it)"},
-                        "n_chunks": st["n_chunks"], "launches": st["kernel_launches"]}), flush=True)
+                        "n_chunks": st["n_chunks"], "launches": st["kernel_launches"],
+                        "candidates_rescored": st["candidates_rescored"]}), flush=True)
         if "ksweep" in only:
             q = synth_rows_device(2514, d, seed=4242)
             for k in (1, 10, 100, 1000):

@@ -754,6 +754,8 @@ int hac_create(int d, int device, hac_index** out) {
     idx->device = device;
     idx->sm_count = prop.multiProcessorCount;
     if (const char* cg = getenv("HAC_MMA_CTA_GROUP")) idx->mma_cta_group = atoi(cg) == 2 ? 2 : 1;
+    // opt-in to the int8 image without touching the caller's code (the reference builds its index through faiss names)
+    if (const char* b8 = getenv("HAC_BUILD_I8")) idx->build_i8 = atoi(b8) != 0 && d % kBlockK8 == 0;
     cudaError_t e = cudaStreamCreateWithFlags(&idx->stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaMalloc(&idx->corpus_stats, sizeof(OperandStats));
     if (e == cudaSuccess) e = cudaMalloc(&idx->add_scratch, 4 * sizeof(float));
