@@ -243,7 +243,7 @@ int add_rows(hac_index* idx, int64_t n, const float* src, RowSource kind, cudaSt
             // whole tiles are rebuilt from the fp32 rows (an append into a partly filled tile changes its scale)
             launch_convert_tiles_i8(seg->rows, end, d, seg->n_rows / kTileRows,
                                     std::min(round_up(end, kRowAlign), seg->cap_rows) / kTileRows, seg->shadow8,
-                                    seg->tiles8, seg->stats, s);
+                                    seg->tiles8, seg->stats, center, s);
         }
         merge_stats_kernel<<<1, 1, 0, s>>>(idx->corpus_stats, seg->stats);
         CU(cudaGetLastError());
@@ -378,9 +378,14 @@ int search_batch_i8(hac_index* idx, int nq, int nq_pad, const float* q_dev, int 
             w.pair_buckets = need_buckets;
         }
     }
+    const float* center = idx->center_valid ? idx->center : nullptr;
     cudaEventRecord(idx->ev[0], s);
     launch_init_search(cb, w.tau, w.thr, nq, nq_pad, s);
     launch_convert_queries_i8(q_dev, nq, nq_pad, d, w.q_shadow8, w.q_consts, s);
+    if (center != nullptr) {
+        launch_query_shift(q_dev, nq, nq_pad, d, center, w.q_shift, s);
+        ++launches;
+    }
     launch_margins(nullptr, nullptr, nullptr, nullptr, d, w.margin, w.scalars + 1, nq, s);   // refresh margin = 0 (exact scores)
     launch_margins_i8(w.q_consts, idx->corpus_stats, d, w.q_norm /*scratch*/, w.scalars + 1, nq, s);   // statistics
     cudaMemsetAsync(w.scalars + 2, 0, sizeof(float), s);
@@ -405,7 +410,8 @@ int search_batch_i8(hac_index* idx, int nq, int nq_pad, const float* q_dev, int 
             a.x_shadow = seg.shadow8;
             a.q_stats = nullptr;
             a.x_stats = nullptr;
-            a.q_shift = nullptr;
+            a.q_shift = center != nullptr ? w.q_shift : nullptr;
+            a.center_norm = center != nullptr ? center + d : nullptr;
             a.x_tiles = seg.tiles8;
             a.q_consts = w.q_consts;
             a.thr = w.thr;
@@ -555,6 +561,7 @@ int search_batch(hac_index* idx, int nq, const float* q_dev, int k, float* D_dev
                 a.q_stats = w.q_stats;
                 a.x_stats = seg.stats;
                 a.q_shift = center != nullptr ? w.q_shift : nullptr;
+                a.center_norm = nullptr;
                 a.thr = w.thr;
                 a.d = d;
                 a.n_qtiles = nq_pad / kTileRows;

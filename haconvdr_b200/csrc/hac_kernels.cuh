@@ -66,8 +66,9 @@ void launch_column_mean(const float* x, int64_t n, int d, double* accum, float* 
 void launch_query_shift(const float* q, int nq, int nq_pad, int d, const float* center, float* shift, cudaStream_t s);
 void launch_synth(float* out, int64_t n, int d, uint64_t seed, int64_t row0, int dist, cudaStream_t s);
 // int8 images: whole 128-row tiles [tile0, tile1) of a segment are (re)built from its fp32 rows (n_rows valid)
+// center: nullptr or the screen centre (the image and the tile norms are then those of x - c)
 void launch_convert_tiles_i8(const float* rows, int64_t n_rows, int d, int64_t tile0, int64_t tile1, uint8_t* shadow8,
-                             TileQ8* tiles, OperandStats* stats, cudaStream_t s);
+                             TileQ8* tiles, OperandStats* stats, const float* center, cudaStream_t s);
 // diagnostic: margin[q] = eps_q*beta_max + nhat_q*gamma_max + slack, the loosest per-tile int8 margin of query q
 void launch_margins_i8(const QueryQ8* q_consts, const OperandStats* corpus, int d, float* margin, float* margin_max,
                        int nq, cudaStream_t s);
@@ -116,7 +117,8 @@ struct MmaScanArgs {
     const TileQ8* x_tiles;      // int8 path: per-128-row-tile constants of the segment (else nullptr)
     const QueryQ8* q_consts;    // int8 path: per-query constants
     const float* thr;       // [n_qtiles*128] unscaled emission thresholds
-    const float* q_shift;   // f16 path: [n_qtiles*128] q . c of a centred corpus image, or nullptr
+    const float* q_shift;   // [n_qtiles*128] q . c of a centred corpus image, or nullptr
+    const float* center_norm;   // int8 path: pointer to ||c|| (device), or nullptr
     int d;
     int n_qtiles;
     int64_t ct0, ct1;       // 256-row tiles of the segment

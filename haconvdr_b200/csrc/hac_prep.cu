@@ -237,14 +237,24 @@ __device__ __forceinline__ int quant_i8(float x, float inv, float alpha, float& 
     return q;
 }
 // quantise the 16 elements of chunk c16 of one row and store them into the swizzled piece image
-__device__ __forceinline__ void convert_chunk_i8(const float* __restrict__ row, int c16, float inv, float alpha,
-                                                 uint8_t* dst, float& sx, float& se) {
+__device__ __forceinline__ float4 ld4_centred(const float4* src, const float4* center) {
+    float4 v = __ldg(src);
+    if (center != nullptr) {
+        const float4 c = __ldg(center);
+        v.x -= c.x; v.y -= c.y; v.z -= c.z; v.w -= c.w;
+    }
+    return v;
+}
+__device__ __forceinline__ void convert_chunk_i8(const float* __restrict__ row, const float* __restrict__ center,
+                                                 int c16, float inv, float alpha, uint8_t* dst, float& sx,
+                                                 float& se) {
     const float4* src = reinterpret_cast<const float4*>(row + c16 * 16);
+    const float4* csrc = center != nullptr ? reinterpret_cast<const float4*>(center + c16 * 16) : nullptr;
     uint4 out;
     uint32_t w[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-        const float4 v = __ldg(src + i);
+        const float4 v = ld4_centred(src + i, csrc != nullptr ? csrc + i : nullptr);
         w[i] = pack4_i8(quant_i8(v.x, inv, alpha, sx, se), quant_i8(v.y, inv, alpha, sx, se),
                         quant_i8(v.z, inv, alpha, sx, se), quant_i8(v.w, inv, alpha, sx, se));
     }
@@ -255,7 +265,8 @@ __device__ __forceinline__ void convert_chunk_i8(const float* __restrict__ row, 
 __global__ void __launch_bounds__(256) convert_tiles_i8_kernel(const float* __restrict__ rows, int64_t n_rows, int d,
                                                                int64_t tile0, uint8_t* __restrict__ shadow8,
                                                                TileQ8* __restrict__ tiles,
-                                                               OperandStats* __restrict__ stats) {
+                                                               OperandStats* __restrict__ stats,
+                                                               const float* __restrict__ center) {
     __shared__ int s_absmax, s_beta, s_gamma;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t tile = tile0 + blockIdx.x;
@@ -268,8 +279,9 @@ __global__ void __launch_bounds__(256) convert_tiles_i8_kernel(const float* __re
         const int64_t r = row_base + rr;
         if (r >= n_rows) break;
         const float4* src = reinterpret_cast<const float4*>(rows + (size_t)r * d);
+        const float4* csrc = reinterpret_cast<const float4*>(center);
         for (int i = lane; i < (d >> 2); i += 32) {
-            const float4 v = __ldg(src + i);
+            const float4 v = ld4_centred(src + i, center != nullptr ? csrc + i : nullptr);   // the image holds x - c
             m = fmaxf(m, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
         }
     }
@@ -286,7 +298,7 @@ __global__ void __launch_bounds__(256) convert_tiles_i8_kernel(const float* __re
         float sx = 0.f, se = 0.f;
         for (int c = lane; c < chunks; c += 32) {
             uint8_t* dst = shadow8 + shadow8_chunk_offset(r, c, d);
-            if (r < n_rows) convert_chunk_i8(rows + (size_t)r * d, c, inv, alpha, dst, sx, se);
+            if (r < n_rows) convert_chunk_i8(rows + (size_t)r * d, center, c, inv, alpha, dst, sx, se);
             else *reinterpret_cast<uint4*>(dst) = make_uint4(0u, 0u, 0u, 0u);
         }
         if (r < n_rows) {
@@ -314,9 +326,10 @@ __global__ void __launch_bounds__(256) convert_tiles_i8_kernel(const float* __re
 }
 
 void launch_convert_tiles_i8(const float* rows, int64_t n_rows, int d, int64_t tile0, int64_t tile1, uint8_t* shadow8,
-                             TileQ8* tiles, OperandStats* stats, cudaStream_t s) {
+                             TileQ8* tiles, OperandStats* stats, const float* center, cudaStream_t s) {
     if (tile1 <= tile0) return;
-    convert_tiles_i8_kernel<<<(unsigned)(tile1 - tile0), 256, 0, s>>>(rows, n_rows, d, tile0, shadow8, tiles, stats);
+    convert_tiles_i8_kernel<<<(unsigned)(tile1 - tile0), 256, 0, s>>>(rows, n_rows, d, tile0, shadow8, tiles, stats,
+                                                                      center);
 }
 
 // queries: one warp per query, one scale per query
@@ -345,7 +358,7 @@ __global__ void __launch_bounds__(256) convert_queries_i8_kernel(const float* __
     const float t = usable ? m / 127.f : 1.f, inv = usable ? 127.f / m : 0.f;
     float sx = 0.f, se = 0.f;
     for (int c = lane; c < chunks; c += 32)
-        convert_chunk_i8(row, c, inv, t, q_shadow8 + shadow8_chunk_offset(r, c, d), sx, se);
+        convert_chunk_i8(row, nullptr, c, inv, t, q_shadow8 + shadow8_chunk_offset(r, c, d), sx, se);
     sx = warp_sum(sx);
     se = warp_sum(se);
     if (lane == 0) {

@@ -69,14 +69,17 @@ __device__ __forceinline__ void wait_or_trap(uint64_t* bar, uint32_t parity) {
     __trap();
 }
 
-// integer emission threshold of the int8 screen for one (query, 128-row tile):
-//   exact score s <= t*alpha*A + eps*beta + nhat*gamma (+ slack)  [Cauchy-Schwarz on the two quantisation errors],
-//   so a row can only matter if  A >= (thr - eps*beta - nhat*gamma - slack) / (t*alpha).
-__device__ __forceinline__ int i8_threshold(float thr, const QueryQ8& qc, const TileQ8& tile, int d) {
+// integer emission threshold of the int8 screen for one (query, 128-row tile).  The image holds v = fl(x - c)
+// (c = 0 without a centre), q ~= t*qi, v ~= alpha*xi, A = qi.xi (exact s32):
+//   fl32(q.x) <= t*alpha*A + shift + eps*beta + nhat*gamma + E      [Cauchy-Schwarz on the two quantisation errors]
+//   E <= ((d/32 + 8) * 2^-23 + 2^-23) * ||q|| * (beta + ||c||)      [rounding of the exact fp32 dot, of x - c, of q.c]
+// so a row can only matter if  A >= (thr - shift - eps*beta - nhat*gamma - E) / (t*alpha).
+__device__ __forceinline__ int i8_threshold(float thr, float shift, float cnorm, const QueryQ8& qc, const TileQ8& tile,
+                                            int d) {
     if (thr == INFINITY) return INT_MAX;                 // padded query: never emits
     if (thr == -INFINITY) return INT_MIN;                // no threshold yet: everything is emitted
-    const float slack = (float)d * 2.4e-7f * qc.norm * tile.beta + 1e-6f * fabsf(thr);   // fp32 rounding of s (d * 2^-22)
-    const float num = thr - (qc.eps * tile.beta + qc.nhat * tile.gamma) - slack;
+    const float slack = (float)(d / 32 + 16) * 1.2e-7f * qc.norm * (tile.beta + cnorm) + 1e-6f * (fabsf(thr) + fabsf(shift));
+    const float num = thr - shift - (qc.eps * tile.beta + qc.nhat * tile.gamma) - slack;
     const float den = qc.t * tile.alpha;
     if (!(den > 0.f)) return num <= 0.f ? INT_MIN : INT_MAX;
     float tf = num / den;
@@ -204,6 +207,10 @@ __global__ void __launch_bounds__(kThreads, 1) scan_mma_kernel(const MmaScanArgs
             scale = a.q_stats->scale * a.x_stats->scale;
             inv_scale = a.q_stats->inv_scale * a.x_stats->inv_scale;
         }
+        float cnorm = 0.f;
+        if constexpr (kI8) {
+            if (a.center_norm != nullptr) cnorm = *a.center_norm;
+        }
         unsigned long long emitted = 0;
         uint32_t it = 0;
         // Survivors are first stashed per thread (local memory) and appended to the shortlist only
@@ -231,7 +238,7 @@ __global__ void __launch_bounds__(kThreads, 1) scan_mma_kernel(const MmaScanArgs
         // hidden behind the TMEM drain of the current tile.
         struct UnitConsts {
             float thr;
-            float shift;             // q . c of a centred corpus image (f16 path), else 0
+            float shift;             // q . c of a centred corpus image, else 0
             QueryQ8 qc;
             TileQ8 t0, t1;
         };
@@ -240,10 +247,7 @@ __global__ void __launch_bounds__(kThreads, 1) scan_mma_kernel(const MmaScanArgs
             const int64_t ct = a.ct0 + u / n_qgroups;
             const int q = ((int)(u % n_qgroups) * kCG + (int)cta_rank) * kTileM + quarter * 32 + lane;
             c.thr = a.thr[q];
-            c.shift = 0.f;
-            if constexpr (!kI8) {
-                if (a.q_shift != nullptr) c.shift = a.q_shift[q];
-            }
+            c.shift = a.q_shift != nullptr ? a.q_shift[q] : 0.f;
             if constexpr (kI8) {
                 c.qc = a.q_consts[q];
                 c.t0 = a.x_tiles[2 * ct];
@@ -270,8 +274,8 @@ __global__ void __launch_bounds__(kThreads, 1) scan_mma_kernel(const MmaScanArgs
             int thr_i[2] = {0, 0};
             float deq[2] = {0.f, 0.f};
             if constexpr (kI8) {
-                thr_i[0] = i8_threshold(cur.thr, cur.qc, cur.t0, a.d);
-                thr_i[1] = i8_threshold(cur.thr, cur.qc, cur.t1, a.d);
+                thr_i[0] = i8_threshold(cur.thr, shift, cnorm, cur.qc, cur.t0, a.d);
+                thr_i[1] = i8_threshold(cur.thr, shift, cnorm, cur.qc, cur.t1, a.d);
                 deq[0] = cur.qc.t * cur.t0.alpha;
                 deq[1] = cur.qc.t * cur.t1.alpha;
             }
@@ -287,7 +291,7 @@ __global__ void __launch_bounds__(kThreads, 1) scan_mma_kernel(const MmaScanArgs
                     else return __uint_as_float(bits) >= thr_s;
                 };
                 auto value = [&](uint32_t bits) {
-                    if constexpr (kI8) return (float)(int)bits * out_scale;
+                    if constexpr (kI8) return fmaf((float)(int)bits, out_scale, shift);
                     else return fmaf(__uint_as_float(bits), out_scale, shift);
                 };
                 bool any = false;

@@ -579,3 +579,29 @@ def test_native_block_files_stream_into_the_index(direct):
         loader.stream_block_into(idx, nat, chunk_bytes=8 << 20, direct=direct, row_range=(10000, 30001))
         D2, I2 = idx.search(q, 50)
         _check(q, x[10000:30001], 50, D2, I2, also_fp32_oracle=False)
+
+
+def test_int8_screen_on_anisotropic_rows_needs_the_centre():
+    """x = mu + 0.3*eps: uncentred, the int8 margin (~14 score units) dwarfs the score spread (~9) and nearly every
+    row is emitted; centred, the int8 screen prunes as on isotropic data and stays on its own path."""
+    hb = _engine()
+    rng = np.random.default_rng(91)
+    mu = rng.standard_normal(768).astype(np.float32)
+    x = (mu + 0.3 * rng.standard_normal((200000, 768))).astype(np.float32)
+    q = (mu + 0.3 * rng.standard_normal((8, 768))).astype(np.float32)
+    res = {}
+    for centred in (1, 0):
+        idx = hb.FlatIPIndex(768)
+        idx.set_option("build_i8", 1)
+        idx.set_option("center_screen", centred)
+        idx.add(x)
+        D, I = idx.search(q, 100, path=hb.HAC_PATH_I8)
+        res[centred] = (D, I, idx.stats())
+        idx.close()
+    st = res[1][2]
+    assert st["path"] == hb.HAC_PATH_I8 and st["retries"] == 0, st
+    assert st["screen_err_max"] <= st["margin_max"], st
+    assert st["candidates_rescored"] < 8 * 40000, st                 # a fraction of the 200 000 rows per query
+    assert res[0][2]["candidates_rescored"] > 2 * st["candidates_rescored"] or res[0][2]["retries"] >= 1, res[0][2]
+    assert np.array_equal(res[1][1], res[0][1]) and np.array_equal(res[1][0], res[0][0])
+    _check(q, x, 100, res[1][0], res[1][1], also_fp32_oracle=False)
