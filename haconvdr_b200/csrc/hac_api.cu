@@ -107,7 +107,7 @@ struct hac_index {
     bool i8_rescore_by_row = true;          // int8 path: rescore each chunk's emitted rows in row order
     bool build_i8 = false;                  // keep an int8 image of the corpus too (rows*d bytes; HAC_PATH_I8)
     int default_path = HAC_PATH_MMA;        // what HAC_PATH_AUTO resolves to
-    int i8_auto_max_queries = 48;           // HAC_PATH_AUTO takes the int8 screen up to this batch size when the image exists
+    int i8_auto_max_queries = 128;          // HAC_PATH_AUTO takes the int8 screen up to this batch size when the image exists
 };
 
 namespace {

@@ -120,9 +120,9 @@ void launch_margins(const float* q_norm, const float* q_err, const OperandStats*
 // true top-k row then has screen score >= tau - 2m, so entries below thr = tau - 2m are dropped
 // (block-wide stream compaction, in place) and later chunks only emit rows with score >= thr.
 // No sort: the shortlist stays unordered until the final select.
-constexpr int kRefreshThreads = 256;
+constexpr int kRefreshMaxThreads = 1024;   // 256 per query for large batches, 1024 when a few queries must finish fast
 
-__global__ void __launch_bounds__(kRefreshThreads) refresh_kernel(CandBuf cb, int k,
+__global__ void __launch_bounds__(kRefreshMaxThreads) refresh_kernel(CandBuf cb, int k,
                                                                   const float* __restrict__ margin,
                                                                   float* __restrict__ tau,
                                                                   float* __restrict__ thr) {
@@ -130,27 +130,28 @@ __global__ void __launch_bounds__(kRefreshThreads) refresh_kernel(CandBuf cb, in
     uint32_t* keys = reinterpret_cast<uint32_t*>(smem_raw);          // [cap]
     __shared__ uint32_t hist[256];
     __shared__ uint32_t s_prefix, s_want;
-    __shared__ uint32_t warp_cnt[kRefreshThreads / 32];
+    __shared__ uint32_t warp_cnt[kRefreshMaxThreads / 32];
     __shared__ uint32_t s_base;
     const int q = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int n_threads = blockDim.x;
     const uint32_t raw = cb.count[q];
     const int cnt = (int)min(raw, cb.cap);
     if (raw > cb.cap && tid == 0) *cb.overflow = 1u;
     if ((uint32_t)cnt == cb.sorted[q]) return;   // nothing new since the last refresh (uniform per block)
     float* sc = cb.score + (size_t)q * cb.cap;
     uint32_t* rw = cb.row + (size_t)q * cb.cap;
-    for (int i = tid; i < cnt; i += kRefreshThreads) keys[i] = float_key(sc[i]);
+    for (int i = tid; i < cnt; i += n_threads) keys[i] = float_key(sc[i]);
     float tau_new = tau[q];
     if (cnt >= k) {
         if (tid == 0) { s_prefix = 0u; s_want = (uint32_t)k; }
         uint32_t mask = 0u;
 #pragma unroll 1
         for (int shift = 24; shift >= 0; shift -= 8) {
-            hist[tid] = 0u;                                           // kRefreshThreads == 256 bins
+            if (tid < 256) hist[tid] = 0u;
             __syncthreads();
             const uint32_t prefix = s_prefix;
-            for (int i = tid; i < cnt; i += kRefreshThreads) {
+            for (int i = tid; i < cnt; i += n_threads) {
                 const uint32_t key = keys[i];
                 if ((key & mask) == prefix) atomicAdd(&hist[(key >> shift) & 255u], 1u);
             }
@@ -189,11 +190,11 @@ __global__ void __launch_bounds__(kRefreshThreads) refresh_kernel(CandBuf cb, in
         thr_new = tau_new - 2.f * margin[q];
         thr_new -= fabsf(thr_new) * 1e-6f;       // keep the cut conservative under fp32 rounding
     }
-    // in-place compaction of entries with score >= thr_new, one round of kRefreshThreads entries at a time
+    // in-place compaction of entries with score >= thr_new, one round of blockDim.x entries at a time
     const uint32_t thr_key = float_key(thr_new);
     if (tid == 0) s_base = 0u;
     __syncthreads();
-    for (int r0 = 0; r0 < cnt; r0 += kRefreshThreads) {
+    for (int r0 = 0; r0 < cnt; r0 += n_threads) {
         const int i = r0 + tid;
         uint32_t key = 0u, row = 0u;
         bool keep = false;
@@ -215,7 +216,7 @@ __global__ void __launch_bounds__(kRefreshThreads) refresh_kernel(CandBuf cb, in
         __syncthreads();
         if (tid == 0) {
             uint32_t t = 0;
-            for (int w = 0; w < kRefreshThreads / 32; ++w) t += warp_cnt[w];
+            for (int w = 0; w < (n_threads >> 5); ++w) t += warp_cnt[w];
             s_base += t;
         }
         __syncthreads();
@@ -232,7 +233,7 @@ void launch_refresh(CandBuf cb, int k, const float* margin, float* tau, float* t
     const size_t smem = (size_t)cb.cap * sizeof(uint32_t);
     // the attribute is per device (several devices per process are possible), so it is set per launch
     if (smem > 40 * 1024) cudaFuncSetAttribute(refresh_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    refresh_kernel<<<nq, kRefreshThreads, smem, s>>>(cb, k, margin, tau, thr);
+    refresh_kernel<<<nq, nq <= 64 ? kRefreshMaxThreads : 256, smem, s>>>(cb, k, margin, tau, thr);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -295,7 +296,15 @@ __global__ void __launch_bounds__(128) rescore_vec_kernel(CandBuf cb, const floa
     // gridDim.y CTAs share one query's shortlist (small batches: the pairs, not the queries, fill the GPU)
     for (int slot = first + 2 * (warp + n_warps * (int)blockIdx.y); slot < cnt; slot += 2 * n_warps * (int)gridDim.y) {
         const bool has_b = slot + 1 < cnt;
+        const size_t o = (size_t)q * cb.cap + slot;
+        // row indices and the screen scores they are compared with: independent loads, issued together so that
+        // only ONE global-memory latency precedes the row fetch
         const uint32_t ra = rows[slot], rb = has_b ? rows[slot + 1] : ra;
+        float old_a = 0.f, old_b = 0.f;
+        if (lane == 0) {
+            old_a = cb.score[o];
+            old_b = has_b ? cb.score[o + 1] : 0.f;
+        }
         const float4* pa = reinterpret_cast<const float4*>(seg_row_ptr(segs, ra, d));
         const float4* pb = reinterpret_cast<const float4*>(seg_row_ptr(segs, rb, d));
         float4 xa[VPL], xb[VPL];
@@ -313,13 +322,12 @@ __global__ void __launch_bounds__(128) rescore_vec_kernel(CandBuf cb, const floa
         a = warp_sum(a);
         b = warp_sum(b);
         if (lane == 0) {
-            const size_t o = (size_t)q * cb.cap + slot;
             cb.exact[o] = a;
-            worst = fmaxf(worst, fabsf(a - cb.score[o]));
+            worst = fmaxf(worst, fabsf(a - old_a));
             if (kNewOnly) cb.score[o] = a;
             if (has_b) {
                 cb.exact[o + 1] = b;
-                worst = fmaxf(worst, fabsf(b - cb.score[o + 1]));
+                worst = fmaxf(worst, fabsf(b - old_b));
                 if (kNewOnly) cb.score[o + 1] = b;
             }
         }
@@ -333,8 +341,11 @@ __global__ void __launch_bounds__(128) rescore_vec_kernel(CandBuf cb, const floa
 template <bool kNewOnly>
 static void launch_rescore_any(CandBuf cb, const float* q, int d, SegTable segs, int nq, float* screen_err_max,
                                unsigned long long* rescored, cudaStream_t s) {
-    // about 8 CTAs per SM in total: with few queries each shortlist is split over several CTAs
-    const dim3 grid((unsigned)nq, (unsigned)std::max(1, std::min(64, 1184 / std::max(nq, 1))));
+    // about 32 CTAs of 4 warps per SM in total (all resident at once): with few queries each shortlist is split over
+    // many CTAs, so a chunk's few thousand new pairs are fetched in one or two latencies instead of a serial loop
+    // (measured at Q=1: 45-86 us per chunk with 64 CTAs, the largest non-scan item of the search)
+    const int per_query = (int)std::min<int64_t>(4736 / std::max(nq, 1), ((int64_t)cb.cap + 7) / 8);
+    const dim3 grid((unsigned)nq, (unsigned)std::max(1, per_query));
     switch (d) {
         case 128: rescore_vec_kernel<kNewOnly, 1><<<grid, 128, 0, s>>>(cb, q, segs, screen_err_max, rescored); break;
         case 256: rescore_vec_kernel<kNewOnly, 2><<<grid, 128, 0, s>>>(cb, q, segs, screen_err_max, rescored); break;

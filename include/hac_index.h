@@ -163,7 +163,7 @@ int hac_pinned_free(void* host);
  *                    reset, and the scan adds q.c back: embeddings with a large shared component (ANCE) get a
  *                    margin made of the centred norms; results are unaffected (exact rescore); empty index only
  *   "i8_auto_max_queries"  with the int8 image present, HAC_PATH_AUTO takes the int8 screen for batches of at most
- *                    this many queries (default 48; 0 = never): small batches are HBM-bound and the int8 image is
+ *                    this many queries (default 128; 0 = never): small batches are HBM-bound and the int8 image is
  *                    half the bytes of the f16 one
  *   "f16_drop_bits_corpus" / "f16_drop_bits_queries"  low mantissa bits of the f16 image forced to zero
  *                    (0..8, default 3 / 0): sparser operands draw less tensor-core power, the screen margin

@@ -532,7 +532,7 @@ def test_careful_mode_is_sticky_until_reset():
     assert idx.stats()["retries"] == 0
 
 
-@pytest.mark.parametrize("nq", [1, 4, 32, 49])
+@pytest.mark.parametrize("nq", [1, 4, 32, 129])
 def test_auto_path_takes_the_int8_screen_for_small_batches(nq):
     hb = _engine()
     rng = np.random.default_rng(80 + nq)
@@ -543,7 +543,7 @@ def test_auto_path_takes_the_int8_screen_for_small_batches(nq):
     idx.add(x)
     D, I = idx.search(q, 100)
     st = idx.stats()
-    assert st["path"] == (hb.HAC_PATH_I8 if nq <= 48 else hb.HAC_PATH_MMA), st
+    assert st["path"] == (hb.HAC_PATH_I8 if nq <= 128 else hb.HAC_PATH_MMA), st
     assert st["candidates_rescored"] >= nq * 100
     Dm, Im = idx.search(q, 100, path=hb.HAC_PATH_MMA)
     assert np.array_equal(I, Im) and np.array_equal(D, Dm)
