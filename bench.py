@@ -162,7 +162,7 @@ def run_ours(args):
     import numpy as np
     import torch
     import torch.distributed as dist
-    from haconvdr_b200 import FlatIPIndex, HAC_PATH_MMA
+    from haconvdr_b200 import FlatIPIndex, HAC_PATH_I8, HAC_PATH_MMA
     from haconvdr_b200.index import synth_rows_device
     from haconvdr_b200.sharded import ShardedFlatIPIndex
 
@@ -308,7 +308,8 @@ def run_ours(args):
 
     # ---- sanity: results are plausible for the N(0,1) corpus (rank-100 score ~ 4.5 sigma) ----------
     st = index.local.stats()
-    assert st["path"] == HAC_PATH_MMA and st["retries"] == 0, st
+    assert st["path"] in (HAC_PATH_I8, HAC_PATH_MMA) and st["retries"] == 0, st
+    i8 = st["path"] == HAC_PATH_I8
     assert st["screen_err_max"] <= st["margin_max"], st
 
     if rank != 0:
@@ -319,16 +320,29 @@ def run_ours(args):
     peaks, peak_kind = measured_peaks()
     flops_per_launch_set = 2.0 * args.queries * shard_rows * DIM        # algorithmic, per search per rank
     achieved = flops_per_launch_set / (scan_ms_step * 1e-3) / 1e12
-    peak = float(peaks.get("bf16_tflops_sustained", 1400.0))
-    # DRAM traffic of the scan kernel from the committed `ncu --set full` capture
-    # (profiles/r01_final_ncu_scan_mma_summary.txt): 29.70 GB read + 0.05 GB written by the launch that covers
-    # 19 300 592 rows, i.e. 1539 B per corpus row against 1536 B algorithmic (f16 row): the corpus is read once.
-    traffic = 1539.0 * shard_rows
-    roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                "traffic": traffic, "traffic_note": "DRAM bytes per search per GPU, scaled from the ncu capture of the "
-                "largest launch (29.70 GB for 19.3M rows); algorithmic operand bytes %.2f GB" % (shard_rows * 1536 / 1e9), "peak_source": "%s bf16_tflops_sustained (f16 and bf16 share the tensor-pipe rate)" % peak_kind,
-                "kernel": "scan_mma_kernel", "kernel_ms_per_step": scan_ms_step,
-                "kernel_share_of_step": scan_ms_step / ms_per_step}
+    bf16_peak = float(peaks.get("bf16_tflops_sustained", 1400.0))
+    if i8:
+        # the scan runs tcgen05.mma.kind::i8: the int8 dense rate of the tensor pipe is twice the bf16 rate and
+        # MEASURED_PEAKS.json holds no int8 figure, so the denominator is 2 x the measured sustained bf16 number.
+        # DRAM traffic from the committed `ncu --set full` capture of the largest launch
+        # (profiles/r01b_ncu_scan_i8_q2514_summary.txt): 12.02 GB read + 0.04 GB written for 15 622 896 rows of 768 B.
+        peak, bytes_row, traffic_row = 2.0 * bf16_peak, 768.0, 772.0
+        peak_src = "2 x %s bf16_tflops_sustained (kind::i8 runs at twice the bf16 tensor-pipe rate; no int8 entry in MEASURED_PEAKS.json)" % peak_kind
+        cap_note = "12.06 GB for 15.6M rows"
+    else:
+        # f16 screen; ncu capture profiles/r01_final_ncu_scan_mma_summary.txt: 29.70 GB read + 0.05 GB written by the
+        # launch that covers 19 300 592 rows, i.e. 1539 B per corpus row against 1536 B algorithmic: read once.
+        peak, bytes_row, traffic_row = bf16_peak, 1536.0, 1539.0
+        peak_src = "%s bf16_tflops_sustained (f16 and bf16 share the tensor-pipe rate)" % peak_kind
+        cap_note = "29.70 GB for 19.3M rows"
+    traffic = traffic_row * shard_rows
+    roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                "frac": achieved / peak, "traffic": traffic,
+                "traffic_note": "DRAM bytes per search per GPU, scaled from the ncu capture of the largest launch "
+                                "(%s); algorithmic operand bytes %.2f GB" % (cap_note, shard_rows * bytes_row / 1e9),
+                "peak_source": peak_src, "frac_of_bf16_peak": achieved / bf16_peak,
+                "kernel": "scan_mma_kernel<2, int8>" if i8 else "scan_mma_kernel<1, f16>",
+                "kernel_ms_per_step": scan_ms_step, "kernel_share_of_step": scan_ms_step / ms_per_step}
 
     cpu_baseline = None
     if not args.no_cpu_baseline and world == 1:
@@ -344,12 +358,13 @@ def run_ours(args):
     line = {
         "metric": METRIC, "value": qps, "unit": "queries/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
-        "vs_baseline": None, "dtype": "f16 screen (f32 accumulate) + f32 exact rescore", "data": "synthetic",
+        "vs_baseline": None, "dtype": ("int8 screen (s32 accumulate)" if i8 else "f16 screen (f32 accumulate)") + " + f32 exact rescore",
+        "data": "synthetic",
         "config": {"workload": WORKLOAD, "rows": args.rows, "rows_per_gpu": shard_rows, "queries": args.queries,
                    "k": args.k, "dim": DIM, "parallelism": "corpus-shard x%d" % world,
                    "exchange": ("p2p symmetric-memory merge" if index._symm is not None else "nccl all-gather + merge") if world > 1 else None,
-                   "l2": "inputs larger than L2 (%.1f GB of operands streamed per step per GPU)" % (
-                       shard_rows * DIM * 2 / 1e9)},
+                   "l2": "inputs larger than L2 (%.1f GB of screen operands + the rescored fp32 rows streamed per step per GPU)" % (
+                       shard_rows * bytes_row / 1e9)},
         "e2e": {"value": e2e_qps, "unit": "queries/s", "h2d_bytes_per_step": int(q_host.nbytes),
                 "d2h_bytes_per_step": int(args.queries * args.k * 12), "ms_per_step": e2e_s * 1e3},
         "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu_baseline, "clocks": clocks,

@@ -19,10 +19,18 @@ def main():
     idx.reserve(args.rows)
     idx.add_synthetic(args.rows, seed=42)
     q = synth_rows_device(args.queries, 768, seed=4242)
-    res = {"f16": [], "i8": []}
+    # (name, path, options)
+    variants = (("f16", HAC_PATH_MMA, {}), ("i8", HAC_PATH_I8, {}),
+                ("i8_growth_1.0", HAC_PATH_I8, {"i8_chunk_growth_x100": 100}),
+                ("i8_growth_0.6", HAC_PATH_I8, {"i8_chunk_growth_x100": 60}),
+                ("i8_growth_0.35", HAC_PATH_I8, {"i8_chunk_growth_x100": 35}))
+    defaults = {"scan_tile_major": -1, "i8_cta_group": 2, "i8_chunk_growth_x100": 0}
+    res = {v[0]: [] for v in variants}
     ref = None
     for r in range(args.rounds + 1):
-        for name, path in (("f16", HAC_PATH_MMA), ("i8", HAC_PATH_I8)):
+        for name, path, opts in variants:
+            for key, val in {**defaults, **opts}.items():
+                idx.set_option(key, val)
             for _ in range(3):
                 D, I = idx.search(q, args.k, path=path)
                 st = idx.stats()

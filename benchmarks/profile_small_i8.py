@@ -10,11 +10,13 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--rows", type=int, default=25_700_592)
     ap.add_argument("--queries", type=int, default=1)
+    ap.add_argument("--cta-group", type=int, default=1)
     args = ap.parse_args()
     from haconvdr_b200 import FlatIPIndex, HAC_PATH_I8
     from haconvdr_b200.index import synth_rows_device
     idx = FlatIPIndex(768, 0)
     idx.set_option("build_i8", 1)
+    idx.set_option("i8_cta_group", args.cta_group)
     idx.reserve(args.rows)
     idx.add_synthetic(args.rows, seed=42)
     q = synth_rows_device(args.queries, 768, seed=4242)

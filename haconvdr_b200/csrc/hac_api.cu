@@ -92,6 +92,10 @@ struct hac_index {
     float* center = nullptr;
     double* center_accum = nullptr;
     bool center_enabled = true, center_valid = false;
+    // unit order of the tensor-core scans (hac_scan_mma.cu UnitSchedule): -1 = per path (tile-major for the int8
+    // screen, striped for the f16 one: measured 57.2 vs 61.1 ms and 83.1 vs 75.2 ms per search), 0 / 1 = forced
+    int scan_tile_major = -1;
+    int i8_cta_group = 2;                   // int8 screen: 2 = CTA pairs (a third less operand traffic from L2): 50.3 vs 56.9 ms
     int sticky_level = 0;                   // searches start in careful mode once the fast mode overflowed (until reset)
     Workspace ws;
     hac_stats stats{};
@@ -104,10 +108,19 @@ struct hac_index {
     // core draws less with sparser mantissas: 3 dropped corpus bits (an 8-bit significand) run the scan 5 %
     // faster (76.3 -> 72.0 ms measured); the margin grows 0.76 -> 2.3 and 1.6x more rows are rescored (0.2 ms).
     int drop_bits_x = 3, drop_bits_q = 0;
-    bool i8_rescore_by_row = true;          // int8 path: rescore each chunk's emitted rows in row order
-    bool build_i8 = false;                  // keep an int8 image of the corpus too (rows*d bytes; HAC_PATH_I8)
+    // int8 path: rescore each chunk's emitted rows in row order.  Off: since the per-query rescore kernel hides its
+    // latencies (indices prefetched one iteration ahead, loads hoisted) it reads the random 3 KB rows at 6.7 TB/s
+    // (12 ms for 26.4M pairs), faster than bucketing them first (75.6 vs 61.6 ms per search).
+    bool i8_rescore_by_row = false;
+    // keep an int8 image of the corpus too (rows*d bytes of HBM; HAC_PATH_I8).  On by default when d % 128 == 0: its
+    // screen is the fastest path for k <= 128 at every batch size (50.3 vs 75.1 ms per search at 25.7M x 2514, k=100;
+    // 3.0 vs 5.5 ms at one query); "build_i8" = 0 / HAC_BUILD_I8=0 saves the memory.
+    bool build_i8 = true;
+    bool i8_overflowed = false;             // the int8 screen overflowed on this corpus: AUTO stops choosing it (until reset)
+    double i8_chunk_growth = 0.0;           // int8 chunk schedule: chunk = growth * rows seen so far (0 = by batch size and k)
+    int i8_auto_max_k = 128;                // HAC_PATH_AUTO takes the int8 screen up to this k (its shortlist grows with k * e^(m8*z/sigma))
     int default_path = HAC_PATH_MMA;        // what HAC_PATH_AUTO resolves to
-    int i8_auto_max_queries = 128;          // HAC_PATH_AUTO takes the int8 screen up to this batch size when the image exists
+    int i8_auto_max_queries = kMaxQueryBatch;          // HAC_PATH_AUTO takes the int8 screen up to this batch size when the image exists
 };
 
 namespace {
@@ -393,7 +406,11 @@ int search_batch_i8(hac_index* idx, int nq, int nq_pad, const float* q_dev, int 
     launches += 4;
     // the first chunk is emitted unfiltered and rescored exactly, so it is kept small; later chunks grow with the
     // rows seen so far: a chunk is expected to emit about growth * k * exp(m8 * z / sigma) rows per query
-    const double growth = few ? 4.0 : (k <= 128 ? 2.0 : 1.0);
+    // large batches: rescoring the emitted pairs is a fifth of the search, and fresher thresholds emit fewer of them
+    // (measured at 25.7M x 2514, k=100: growth 2.0 -> 26.4M pairs, 53.5 ms; 1.0 -> 21.9M, 48.8 ms; 0.6 -> 19.9M,
+    // 47.2 ms; 0.35 -> 18.5M, 46.9 ms); smaller batches keep few chunks (each costs ~40 us of latency)
+    const double growth = idx->i8_chunk_growth > 0.0 ? idx->i8_chunk_growth
+                          : few ? 4.0 : (nq >= 512 && k <= 128) ? 0.6 : (k <= 128 ? 2.0 : 1.0);
     const int64_t first = few ? cap / 2 : std::min<int64_t>(cap / 2, std::max<int64_t>(512, round_up(2 * (int64_t)k, kRowAlign)));
     int64_t rows_done = 0;
     for (size_t si = 0; si < idx->segs.size(); ++si) {
@@ -416,13 +433,14 @@ int search_batch_i8(hac_index* idx, int nq, int nq_pad, const float* q_dev, int 
             a.q_consts = w.q_consts;
             a.thr = w.thr;
             a.d = d;
+            a.tile_major = idx->scan_tile_major < 0 ? 1 : idx->scan_tile_major;
             a.n_qtiles = nq_pad / kTileRows;
             a.ct0 = r / kRowAlign;
             a.ct1 = (r1 + kRowAlign - 1) / kRowAlign;
             a.seg_rows = std::min(seg.n_rows, r1);
             a.row_id_base = seg.base;
             a.cb = cb;
-            CU(launch_scan_mma_i8(a, idx->sm_count, s));
+            CU(launch_scan_mma_i8(a, idx->sm_count, idx->i8_cta_group, s));
             if (timed) {
                 cudaEventRecord(idx->ev[n_ev + 1], s);
                 n_ev += 2;
@@ -480,10 +498,13 @@ int search_batch(hac_index* idx, int nq, const float* q_dev, int k, float* D_dev
     bool have_i8 = !idx->segs.empty();
     for (const auto& sg : idx->segs) have_i8 = have_i8 && sg.shadow8 != nullptr;
     if (path == HAC_PATH_AUTO) {
-        // small batches are HBM-bound: when the int8 image exists its scan streams half the bytes of the f16 one
-        // (measured Q=1: 2.8 ms vs 5.4 ms over 25.7M rows) and rescoring its ~10^4 emitted rows per query is cheap
-        path = (have_i8 && idx->default_path == HAC_PATH_MMA && nq <= idx->i8_auto_max_queries) ? HAC_PATH_I8
-                                                                                                  : idx->default_path;
+        // with the int8 image present its screen wins whenever the shortlist stays small (k <= 128): large batches run
+        // the tensor pipe at the int8 rate (38.5 vs 74.4 ms of scan at 25.7M x 2514), small ones stream half the bytes
+        // (Q=1: 2.8 vs 5.4 ms); rescoring its ~10^4 emitted rows per query runs at the HBM rate.  Larger k and corpora
+        // that overflowed it go to the f16 screen.
+        const bool take_i8 = have_i8 && idx->default_path == HAC_PATH_MMA && !idx->i8_overflowed &&
+                             k <= idx->i8_auto_max_k && nq <= idx->i8_auto_max_queries;
+        path = take_i8 ? HAC_PATH_I8 : idx->default_path;
     }
     if (path == HAC_PATH_I8 && !have_i8) path = HAC_PATH_MMA;      // d % 128 != 0 or int8 image disabled
     if (path == HAC_PATH_GEMV && nq > 4) return fail(HAC_E_INVALID, "GEMV path takes at most 4 queries per batch");
@@ -508,6 +529,7 @@ int search_batch(hac_index* idx, int nq, const float* q_dev, int k, float* D_dev
     if (path == HAC_PATH_I8) {
         const int rc8 = search_batch_i8(idx, nq, nq_pad, q_dev, k, D_dev, I_dev, s, segs);
         if (rc8 <= 0) return rc8;
+        idx->i8_overflowed = true;
         path = HAC_PATH_MMA;            // shortlist overflow: redo with the f16 screen (and its careful mode)
         st.path = path;
         st.retries = 1;
@@ -564,6 +586,7 @@ int search_batch(hac_index* idx, int nq, const float* q_dev, int k, float* D_dev
                 a.center_norm = nullptr;
                 a.thr = w.thr;
                 a.d = d;
+                a.tile_major = idx->scan_tile_major < 0 ? 0 : idx->scan_tile_major;
                 a.n_qtiles = nq_pad / kTileRows;
                 a.ct0 = r / kRowAlign;
                 a.ct1 = (r1 + kRowAlign - 1) / kRowAlign;
@@ -707,7 +730,7 @@ int search_common(hac_index* idx, int64_t nq, const float* q, bool q_on_host, in
     float margin_max = 0.f, err_max = 0.f;
     for (int64_t q0 = 0; q0 < nq; q0 += max_batch) {
         const int nb = (int)std::min<int64_t>(max_batch, nq - q0);
-        const int nb_pad = (int)round_up(nb, kTileRows * idx->mma_cta_group);
+        const int nb_pad = (int)round_up(nb, kTileRows * std::max(idx->mma_cta_group, idx->i8_cta_group));
         int rc = ensure_workspace(idx, nb_pad, cap_for_k(k, 0), (q_on_host || out_on_host) ? (int64_t)nb * k : 0);
         if (rc != HAC_OK) return rc;
         const float* qd = q + (size_t)q0 * idx->d;
@@ -762,7 +785,8 @@ int hac_create(int d, int device, hac_index** out) {
     idx->sm_count = prop.multiProcessorCount;
     if (const char* cg = getenv("HAC_MMA_CTA_GROUP")) idx->mma_cta_group = atoi(cg) == 2 ? 2 : 1;
     // opt-in to the int8 image without touching the caller's code (the reference builds its index through faiss names)
-    if (const char* b8 = getenv("HAC_BUILD_I8")) idx->build_i8 = atoi(b8) != 0 && d % kBlockK8 == 0;
+    if (const char* b8 = getenv("HAC_BUILD_I8")) idx->build_i8 = atoi(b8) != 0;
+    if (d % kBlockK8 != 0) idx->build_i8 = false;
     cudaError_t e = cudaStreamCreateWithFlags(&idx->stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaMalloc(&idx->corpus_stats, sizeof(OperandStats));
     if (e == cudaSuccess) e = cudaMalloc(&idx->add_scratch, 4 * sizeof(float));
@@ -872,6 +896,7 @@ int hac_reset(hac_index* idx) {
     idx->ntotal = 0;
     idx->center_valid = false;      // the next block gets its own centre
     idx->sticky_level = 0;
+    idx->i8_overflowed = false;
     CU(cudaStreamSynchronize(idx->stream));
     return HAC_OK;
 }
@@ -1000,6 +1025,12 @@ int hac_set_option(hac_index* idx, const char* name, int64_t value) {
         }
         return HAC_OK;
     }
+    if (strcmp(name, "scan_tile_major") == 0) { idx->scan_tile_major = value < 0 ? -1 : (value != 0); return HAC_OK; }
+    if (strcmp(name, "i8_cta_group") == 0) {
+        if (value != 1 && value != 2) return fail(HAC_E_INVALID, "i8_cta_group must be 1 or 2");
+        idx->i8_cta_group = (int)value;
+        return HAC_OK;
+    }
     if (strcmp(name, "center_screen") == 0) {
         if (idx->ntotal != 0) return fail(HAC_E_STATE, "center_screen must be set on an empty index");
         idx->center_enabled = value != 0;
@@ -1007,6 +1038,16 @@ int hac_set_option(hac_index* idx, const char* name, int64_t value) {
         return HAC_OK;
     }
     if (strcmp(name, "i8_rescore_by_row") == 0) { idx->i8_rescore_by_row = value != 0; return HAC_OK; }
+    if (strcmp(name, "i8_chunk_growth_x100") == 0) {
+        if (value != 0 && (value < 10 || value > 1600)) return fail(HAC_E_INVALID, "i8_chunk_growth_x100 must be 0 or in [10, 1600]");
+        idx->i8_chunk_growth = (double)value / 100.0;
+        return HAC_OK;
+    }
+    if (strcmp(name, "i8_auto_max_k") == 0) {
+        if (value < 0 || value > HAC_MAX_K) return fail(HAC_E_INVALID, "i8_auto_max_k out of range");
+        idx->i8_auto_max_k = (int)value;
+        return HAC_OK;
+    }
     if (strcmp(name, "i8_auto_max_queries") == 0) {
         if (value < 0 || value > kMaxQueryBatch) return fail(HAC_E_INVALID, "i8_auto_max_queries out of range");
         idx->i8_auto_max_queries = (int)value;
@@ -1014,7 +1055,7 @@ int hac_set_option(hac_index* idx, const char* name, int64_t value) {
     }
     if (strcmp(name, "build_i8") == 0) {
         if (idx->ntotal != 0 || !idx->segs.empty()) return fail(HAC_E_STATE, "build_i8 must be set on an empty index");
-        idx->build_i8 = value != 0;
+        idx->build_i8 = value != 0 && idx->d % kBlockK8 == 0;
         return HAC_OK;
     }
     if (strcmp(name, "chunk_growth_x100") == 0) {

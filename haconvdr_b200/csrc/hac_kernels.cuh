@@ -121,6 +121,7 @@ struct MmaScanArgs {
     const float* center_norm;   // int8 path: pointer to ||c|| (device), or nullptr
     int d;
     int n_qtiles;
+    int tile_major;         // 1: every CTA walks whole corpus tiles (all query tiles back to back); 0: units striped
     int64_t ct0, ct1;       // 256-row tiles of the segment
     int64_t seg_rows;       // valid rows of the segment
     uint32_t row_id_base;
@@ -129,7 +130,7 @@ struct MmaScanArgs {
 // cta_group = 1: one CTA per tile; 2: CTA pairs (cluster of 2) sharing each MMA; needs an even n_qtiles
 cudaError_t launch_scan_mma(const MmaScanArgs& a, int sm_count, int cta_group, cudaStream_t s);
 // int8 screen (kind::i8, s32 accumulators, integer thresholds); x_tiles / q_consts must be set
-cudaError_t launch_scan_mma_i8(const MmaScanArgs& a, int sm_count, cudaStream_t s);
+cudaError_t launch_scan_mma_i8(const MmaScanArgs& a, int sm_count, int cta_group, cudaStream_t s);
 cudaError_t scan_mma_configure();
 
 // ---- merge / gather ---------------------------------------------------------------------------

@@ -14,11 +14,11 @@
 //            operand reads per FLOP drop by a third; 6 stages of 32 KiB.  The pair's leader issues
 //            the MMAs; the peer forwards "my half has landed" to the leader through a remote
 //            mbarrier arrive; tcgen05.commit multicasts slot-free / accumulator-ready to both CTAs.
-// Warp roles (192 threads, persistent): warp 0 = copy producer, warp 1 = MMA issuer (leader) or
-// forwarder (peer) and owner of the TMEM allocation, warps 2..5 = epilogue (TMEM lane quarter =
-// warp % 4, one query per thread).
-// Tile order: consecutive CTAs take the query tiles of the same 256-row corpus tile, so a corpus
-// tile is pulled from HBM once and re-read from L2 by the other query tiles.
+// Warp roles (320 threads, persistent): warp 0 = copy producer, warp 1 = MMA issuer (leader) or
+// forwarder (peer) and owner of the TMEM allocation, warps 2..9 = epilogue (TMEM lane quarter =
+// warp % 4, one query per thread; warps 2..5 drain columns 0..127 of a tile, warps 6..9 columns 128..255).
+// Tile order (UnitSchedule): every CTA takes whole 256-row corpus tiles and runs all query tiles of a tile back to
+// back, so a corpus tile is pulled from HBM once and re-read from L2 by the same SM.
 // Roofline: tensor pipe; algorithmic FLOPs = 2 * queries * rows * d per launch.
 #include <limits.h>
 
@@ -31,7 +31,7 @@ namespace {
 
 constexpr int kTileM = 128;                                // queries per CTA tile (TMEM lanes)
 constexpr int kTileN = 256;                                // corpus rows per tile (TMEM columns)
-constexpr int kThreads = 192;
+constexpr int kThreads = 320;                              // producer warp, MMA warp, 8 epilogue warps
 constexpr int kStash = 8;                                  // per-thread survivors kept until the TMEM buffer is released
 constexpr int kMaxStages = 6;
 
@@ -89,9 +89,47 @@ __device__ __forceinline__ int i8_threshold(float thr, float shift, float cnorm,
     return (int)floorf(tf);
 }
 
+// 3-input float max (FMNMX3 on sm_100); NaNs are ignored like fmaxf, so a NaN score never passes a threshold
+__device__ __forceinline__ float fmax3(float a, float b, float c) {
+    float d;
+    asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+    return d;
+}
+
+// Order in which one CTA group walks its share of the (corpus tile, query group) units of a launch.
+// Body: the corpus tiles are dealt out whole - group b takes tiles b, b+G, b+2G, ... and runs ALL query groups of a
+// tile back to back, so a tile is pulled from HBM once and re-read from L2 by the same SM a few microseconds later,
+// whatever the other CTAs are doing.  (Striping the units of one tile over 20 neighbouring CTAs relies on those CTAs
+// staying in step; the int8 scan, whose units are half as long, drifted apart and re-fetched every tile ~7 times:
+// ncu DRAM read 93.6 GB for 13.2 GB of rows, L2 hit rate 64 %.)
+// Tail: the last (n_ct mod G) tiles, fewer than one per group, are striped unit by unit for load balance.
+struct UnitSchedule {
+    int64_t G, b, body_rounds, body_units, n_mine;
+    int n_qg;
+    __device__ UnitSchedule(int64_t n_ct, int n_qgroups, int64_t n_groups, int64_t group, bool tile_major) {
+        G = n_groups; b = group; n_qg = n_qgroups;
+        body_rounds = tile_major ? n_ct / G : 0;
+        body_units = body_rounds * n_qg;
+        const int64_t tail_units = (n_ct - body_rounds * G) * n_qg;
+        n_mine = body_units + (tail_units > b ? (tail_units - b + G - 1) / G : 0);
+    }
+    // i-th unit of this group -> (corpus tile relative to ct0, query group)
+    __device__ __forceinline__ void get(int64_t i, int64_t& ct_rel, int& qg) const {
+        if (i < body_units) {
+            const int64_t r = i / n_qg;
+            ct_rel = r * G + b;
+            qg = (int)(i - r * n_qg);
+        } else {
+            const int64_t u = b + (i - body_units) * G;
+            const int64_t t = u / n_qg;
+            ct_rel = body_rounds * G + t;
+            qg = (int)(u - t * n_qg);
+        }
+    }
+};
+
 template <int kCG, bool kI8>
 __global__ void __launch_bounds__(kThreads, 1) scan_mma_kernel(const MmaScanArgs a) {
-    static_assert(!kI8 || kCG == 1, "the int8 screen exists for the single-CTA variant only");
     using C = Cfg<kCG>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -103,8 +141,7 @@ __global__ void __launch_bounds__(kThreads, 1) scan_mma_kernel(const MmaScanArgs
     const bool leader = cta_rank == 0;
     // work unit: (corpus tile of 256 rows) x (query tile of 128*kCG queries); one unit per CTA group
     const int n_qgroups = a.n_qtiles / kCG;
-    const int64_t n_units = (a.ct1 - a.ct0) * n_qgroups;
-    const int64_t unit0 = blockIdx.x / kCG, unit_step = gridDim.x / kCG;
+    const UnitSchedule sched(a.ct1 - a.ct0, n_qgroups, gridDim.x / kCG, blockIdx.x / kCG, a.tile_major != 0);
 
     if constexpr (kCG == 2) cluster_sync_all();          // both CTAs resident before any cross-CTA traffic
     if (threadIdx.x == 0) {
@@ -115,7 +152,7 @@ __global__ void __launch_bounds__(kThreads, 1) scan_mma_kernel(const MmaScanArgs
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&bars->tmem_full[i], 1);
-            mbar_init(&bars->tmem_empty[i], 128 * kCG);
+            mbar_init(&bars->tmem_empty[i], 256 * kCG);      // every epilogue thread of the CTA group arrives
         }
         fence_barrier_init();
     }
@@ -129,9 +166,12 @@ __global__ void __launch_bounds__(kThreads, 1) scan_mma_kernel(const MmaScanArgs
         // ---------------- producer: shadow pieces -> shared memory ----------------
         if (elect_one()) {
             uint32_t stage = 0, phase = 0;
-            for (int64_t u = unit0; u < n_units; u += unit_step) {
-                const int64_t ct = a.ct0 + u / n_qgroups;
-                const int qt = (int)(u % n_qgroups) * kCG + (int)cta_rank;
+            for (int64_t i = 0; i < sched.n_mine; ++i) {
+                int64_t ct_rel;
+                int qg;
+                sched.get(i, ct_rel, qg);
+                const int64_t ct = a.ct0 + ct_rel;
+                const int qt = qg * kCG + (int)cta_rank;
                 const uint8_t* srcA = a.q_shadow + (size_t)qt * kb_count * kPieceBytes;
                 // kCG = 1: both 128-row halves of the corpus tile; kCG = 2: this CTA's half only
                 const uint8_t* srcB = a.x_shadow + (size_t)(2 * ct + (kCG == 2 ? cta_rank : 0)) * kb_count * kPieceBytes;
@@ -153,9 +193,9 @@ __global__ void __launch_bounds__(kThreads, 1) scan_mma_kernel(const MmaScanArgs
         if (leader) {
             // ---------------- MMA issuer ----------------
             if (elect_one()) {
-                constexpr uint32_t idesc = kI8 ? umma_idesc_i8(kTileM, kTileN) : umma_idesc_f16(kTileM * kCG, kTileN);
+                constexpr uint32_t idesc = kI8 ? umma_idesc_i8(kTileM * kCG, kTileN) : umma_idesc_f16(kTileM * kCG, kTileN);
                 uint32_t stage = 0, phase = 0, it = 0;
-                for (int64_t u = unit0; u < n_units; u += unit_step, ++it) {
+                for (int64_t i = 0; i < sched.n_mine; ++i, ++it) {
                     const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
                     wait_or_trap(&bars->tmem_empty[acc], acc_phase ^ 1);
                     tc_fence_after();
@@ -171,7 +211,7 @@ __global__ void __launch_bounds__(kThreads, 1) scan_mma_kernel(const MmaScanArgs
                         for (int k = 0; k < 4; ++k) {
                             // advance 32 B along K inside the swizzle atom (16 f16 or 32 int8 elements): +2 in the
                             // >>4 address field
-                            if constexpr (kI8) umma_i8(tmem_d, descA + 2 * k, descB + 2 * k, idesc, (kb | k) != 0);
+                            if constexpr (kI8) umma_i8<kCG>(tmem_d, descA + 2 * k, descB + 2 * k, idesc, (kb | k) != 0);
                             else umma_f16<kCG>(tmem_d, descA + 2 * k, descB + 2 * k, idesc, (kb | k) != 0);
                         }
                         // slot free / accumulator ready, signalled when the MMAs above retire
@@ -190,7 +230,7 @@ __global__ void __launch_bounds__(kThreads, 1) scan_mma_kernel(const MmaScanArgs
             // ---------------- peer forwarder: my half of the stage has landed ----------------
             if (elect_one()) {
                 uint32_t stage = 0, phase = 0;
-                for (int64_t u = unit0; u < n_units; u += unit_step) {
+                for (int64_t i = 0; i < sched.n_mine; ++i) {
                     for (int kb = 0; kb < kb_count; ++kb) {
                         wait_or_trap(&bars->full[stage], phase);
                         mbar_arrive_cluster(&bars->peer_full[stage], 0);
@@ -202,6 +242,7 @@ __global__ void __launch_bounds__(kThreads, 1) scan_mma_kernel(const MmaScanArgs
     } else {
         // ---------------- epilogue: fused threshold filter ----------------
         const int quarter = warp & 3;                    // TMEM lanes [32*quarter, 32*quarter+32)
+        const int half = (warp - 2) >> 2;                // columns [128*half, 128*half+128) of every tile
         float scale = 1.f, inv_scale = 1.f;
         if constexpr (!kI8) {
             scale = a.q_stats->scale * a.x_stats->scale;
@@ -242,10 +283,13 @@ __global__ void __launch_bounds__(kThreads, 1) scan_mma_kernel(const MmaScanArgs
             QueryQ8 qc;
             TileQ8 t0, t1;
         };
-        auto fetch = [&](int64_t u) {
+        auto fetch = [&](int64_t i) {
             UnitConsts c;
-            const int64_t ct = a.ct0 + u / n_qgroups;
-            const int q = ((int)(u % n_qgroups) * kCG + (int)cta_rank) * kTileM + quarter * 32 + lane;
+            int64_t ct_rel;
+            int qg;
+            sched.get(i, ct_rel, qg);
+            const int64_t ct = a.ct0 + ct_rel;
+            const int q = (qg * kCG + (int)cta_rank) * kTileM + quarter * 32 + lane;
             c.thr = a.thr[q];
             c.shift = a.q_shift != nullptr ? a.q_shift[q] : 0.f;
             if constexpr (kI8) {
@@ -256,11 +300,14 @@ __global__ void __launch_bounds__(kThreads, 1) scan_mma_kernel(const MmaScanArgs
             return c;
         };
         UnitConsts cur{};
-        if (unit0 < n_units) cur = fetch(unit0);
-        for (int64_t u = unit0; u < n_units; u += unit_step, ++it) {
+        if (sched.n_mine > 0) cur = fetch(0);
+        for (int64_t i = 0; i < sched.n_mine; ++i, ++it) {
             const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
-            const int64_t ct = a.ct0 + u / n_qgroups;
-            const int qt = (int)(u % n_qgroups) * kCG + (int)cta_rank;
+            int64_t ct_rel;
+            int qg;
+            sched.get(i, ct_rel, qg);
+            const int64_t ct = a.ct0 + ct_rel;
+            const int qt = qg * kCG + (int)cta_rank;
             const int q = qt * kTileM + quarter * 32 + lane;
             // threshold in accumulator units (power-of-two scale); the accumulator lacks the per-query constant
             // q.c of a centred image, so it is taken off the threshold (rounded down: may only lower it) and added
@@ -280,7 +327,7 @@ __global__ void __launch_bounds__(kThreads, 1) scan_mma_kernel(const MmaScanArgs
                 deq[1] = cur.qc.t * cur.t1.alpha;
             }
             UnitConsts nxt{};
-            if (u + unit_step < n_units) nxt = fetch(u + unit_step);
+            if (i + 1 < sched.n_mine) nxt = fetch(i + 1);
             uint32_t stash_n = 0;
             // one 32-column group of this thread's query: compare, stash or append the survivors
             auto process = [&](const uint32_t (&v)[32], int c) {
@@ -294,9 +341,23 @@ __global__ void __launch_bounds__(kThreads, 1) scan_mma_kernel(const MmaScanArgs
                     if constexpr (kI8) return fmaf((float)(int)bits, out_scale, shift);
                     else return fmaf(__uint_as_float(bits), out_scale, shift);
                 };
-                bool any = false;
+                // the common case is "no survivor in these 32 columns": one 3-input max per two columns and a single
+                // compare (16 + 1 instructions instead of a compare and a predicate-or per column) - at int8 rates the
+                // epilogue warps have only ~3000 cycles per tile and were co-limiting the scan
+                bool any;
+                if constexpr (kI8) {
+                    int m = (int)v[0];
 #pragma unroll
-                for (int j = 0; j < 32; ++j) any |= passes(v[j]);
+                    for (int j = 1; j + 1 < 32; j += 2) m = __vimax3_s32(m, (int)v[j], (int)v[j + 1]);
+                    m = max(m, (int)v[31]);
+                    any = m >= thr_c;
+                } else {
+                    float m = __uint_as_float(v[0]);
+#pragma unroll
+                    for (int j = 1; j + 1 < 32; j += 2) m = fmax3(m, __uint_as_float(v[j]), __uint_as_float(v[j + 1]));
+                    m = fmaxf(m, __uint_as_float(v[31]));
+                    any = m >= thr_s;
+                }
                 if (any) {
                     uint32_t mask = 0;
 #pragma unroll
@@ -334,16 +395,22 @@ __global__ void __launch_bounds__(kThreads, 1) scan_mma_kernel(const MmaScanArgs
             wait_or_trap(&bars->tmem_full[acc], acc_phase);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * kTileN;
+            // Two epilogue warps share each TMEM lane quarter, one per 128-column half of the tile: the drain of a tile
+            // is a chain of TMEM-load latencies (ncu, int8 scan with one warp per quarter: tensor pipe 72 % active in
+            // both CTA-group variants - the MMAs of a tile take 3072 cycles, its drain ~4300), so halving the chain per
+            // warp is what takes the epilogue off the critical path.
             // two register buffers: the next 32 columns are in flight while the current ones are compared
+            constexpr int kGroupsPerWarp = kTileN / 32 / 2;
+            const int c0 = half * kGroupsPerWarp;
             uint32_t va[32], vb[32];
-            tmem_ld_32x32(taddr, va);
+            tmem_ld_32x32(taddr + c0 * 32, va);
             tmem_ld_wait();
 #pragma unroll 1
-            for (int c = 0; c < kTileN / 32; c += 2) {
+            for (int c = c0; c < c0 + kGroupsPerWarp; c += 2) {
                 tmem_ld_32x32(taddr + (c + 1) * 32, vb);
                 process(va, c);
                 tmem_ld_wait();
-                if (c + 2 < kTileN / 32) tmem_ld_32x32(taddr + (c + 2) * 32, va);
+                if (c + 2 < c0 + kGroupsPerWarp) tmem_ld_32x32(taddr + (c + 2) * 32, va);
                 process(vb, c + 1);
                 tmem_ld_wait();
             }
@@ -376,14 +443,39 @@ cudaError_t scan_mma_configure() {
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(scan_mma_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<1>::kSmemBytes);
     if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(scan_mma_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<2>::kSmemBytes);
+    if (e != cudaSuccess) return e;
     return cudaFuncSetAttribute(scan_mma_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 Cfg<2>::kSmemBytes);
 }
 
-cudaError_t launch_scan_mma_i8(const MmaScanArgs& a, int sm_count, cudaStream_t s) {
+namespace {
+// cluster-of-2 launch: one CTA pair per unit, pairs <= sm_count / 2
+template <bool kI8>
+cudaError_t launch_pairs(const MmaScanArgs& a, int sm_count, cudaStream_t s) {
+    const int64_t n_units = (a.ct1 - a.ct0) * (a.n_qtiles / 2);
+    const int pairs = (int)(n_units < sm_count / 2 ? n_units : sm_count / 2);
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(2 * pairs);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = Cfg<2>::kSmemBytes;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, scan_mma_kernel<2, kI8>, a);
+}
+}  // namespace
+
+cudaError_t launch_scan_mma_i8(const MmaScanArgs& a, int sm_count, int cta_group, cudaStream_t s) {
     const int64_t n_units = (a.ct1 - a.ct0) * a.n_qtiles;
     if (n_units <= 0) return cudaSuccess;
     if (a.x_tiles == nullptr || a.q_consts == nullptr || a.d % kBlockK8 != 0) return cudaErrorInvalidValue;
+    if (cta_group == 2 && (a.n_qtiles % 2) == 0) return launch_pairs<true>(a, sm_count, s);
     const int grid = (int)(n_units < sm_count ? n_units : sm_count);
     scan_mma_kernel<1, true><<<grid, kThreads, Cfg<1>::kSmemBytes, s>>>(a);
     return cudaGetLastError();
@@ -392,23 +484,7 @@ cudaError_t launch_scan_mma_i8(const MmaScanArgs& a, int sm_count, cudaStream_t 
 cudaError_t launch_scan_mma(const MmaScanArgs& a, int sm_count, int cta_group, cudaStream_t s) {
     const int64_t n_ctiles = a.ct1 - a.ct0;
     if (n_ctiles <= 0 || a.n_qtiles <= 0) return cudaSuccess;
-    if (cta_group == 2 && (a.n_qtiles % 2) == 0) {
-        const int64_t n_units = n_ctiles * (a.n_qtiles / 2);
-        const int pairs = (int)(n_units < sm_count / 2 ? n_units : sm_count / 2);
-        cudaLaunchConfig_t cfg{};
-        cfg.gridDim = dim3(2 * pairs);
-        cfg.blockDim = dim3(kThreads);
-        cfg.dynamicSmemBytes = Cfg<2>::kSmemBytes;
-        cfg.stream = s;
-        cudaLaunchAttribute attr[1];
-        attr[0].id = cudaLaunchAttributeClusterDimension;
-        attr[0].val.clusterDim.x = 2;
-        attr[0].val.clusterDim.y = 1;
-        attr[0].val.clusterDim.z = 1;
-        cfg.attrs = attr;
-        cfg.numAttrs = 1;
-        return cudaLaunchKernelEx(&cfg, scan_mma_kernel<2, false>, a);
-    }
+    if (cta_group == 2 && (a.n_qtiles % 2) == 0) return launch_pairs<false>(a, sm_count, s);
     const int64_t n_units = n_ctiles * a.n_qtiles;
     const int grid = (int)(n_units < sm_count ? n_units : sm_count);
     scan_mma_kernel<1, false><<<grid, kThreads, Cfg<1>::kSmemBytes, s>>>(a);

@@ -293,26 +293,38 @@ __global__ void __launch_bounds__(128) rescore_vec_kernel(CandBuf cb, const floa
     for (int i = 0; i < VPL; ++i) qv[i] = __ldg(reinterpret_cast<const float4*>(qmat + (size_t)q * d) + i * 32 + lane);
     const uint32_t* rows = cb.row + (size_t)q * cb.cap;
     float worst = 0.f;
-    // gridDim.y CTAs share one query's shortlist (small batches: the pairs, not the queries, fill the GPU)
-    for (int slot = first + 2 * (warp + n_warps * (int)blockIdx.y); slot < cnt; slot += 2 * n_warps * (int)gridDim.y) {
+    // gridDim.y CTAs share one query's shortlist (small batches: the pairs, not the queries, fill the GPU).
+    // The row indices and the screen scores of the NEXT iteration are fetched while the current rows are in flight,
+    // so one global-memory latency per iteration is exposed, not two.
+    const int step = 2 * n_warps * (int)gridDim.y;
+    int slot = first + 2 * (warp + n_warps * (int)blockIdx.y);
+    uint32_t ra = 0, rb = 0;
+    float old_a = 0.f, old_b = 0.f;
+    auto fetch_meta = [&](int sl) {
+        if (sl < cnt) {
+            const bool hb = sl + 1 < cnt;
+            ra = rows[sl];
+            rb = hb ? rows[sl + 1] : ra;
+            if (lane == 0) {
+                old_a = cb.score[(size_t)q * cb.cap + sl];
+                old_b = hb ? cb.score[(size_t)q * cb.cap + sl + 1] : 0.f;
+            }
+        }
+    };
+    fetch_meta(slot);
+    for (; slot < cnt; slot += step) {
         const bool has_b = slot + 1 < cnt;
         const size_t o = (size_t)q * cb.cap + slot;
-        // row indices and the screen scores they are compared with: independent loads, issued together so that
-        // only ONE global-memory latency precedes the row fetch
-        const uint32_t ra = rows[slot], rb = has_b ? rows[slot + 1] : ra;
-        float old_a = 0.f, old_b = 0.f;
-        if (lane == 0) {
-            old_a = cb.score[o];
-            old_b = has_b ? cb.score[o + 1] : 0.f;
-        }
         const float4* pa = reinterpret_cast<const float4*>(seg_row_ptr(segs, ra, d));
         const float4* pb = reinterpret_cast<const float4*>(seg_row_ptr(segs, rb, d));
+        const float cur_a = old_a, cur_b = old_b;
         float4 xa[VPL], xb[VPL];
 #pragma unroll
         for (int i = 0; i < VPL; ++i) {
             xa[i] = __ldg(pa + i * 32 + lane);
             xb[i] = __ldg(pb + i * 32 + lane);
         }
+        fetch_meta(slot + step);
         float a = 0.f, b = 0.f;
 #pragma unroll
         for (int i = 0; i < VPL; ++i) {
@@ -323,11 +335,11 @@ __global__ void __launch_bounds__(128) rescore_vec_kernel(CandBuf cb, const floa
         b = warp_sum(b);
         if (lane == 0) {
             cb.exact[o] = a;
-            worst = fmaxf(worst, fabsf(a - old_a));
+            worst = fmaxf(worst, fabsf(a - cur_a));
             if (kNewOnly) cb.score[o] = a;
             if (has_b) {
                 cb.exact[o + 1] = b;
-                worst = fmaxf(worst, fabsf(b - old_b));
+                worst = fmaxf(worst, fabsf(b - cur_b));
                 if (kNewOnly) cb.score[o + 1] = b;
             }
         }
@@ -765,10 +777,22 @@ __global__ void __launch_bounds__(256) rescore_pairs_kernel(CandBuf cb, const ui
     const uint32_t gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
     const uint32_t n = *total;
     float worst = 0.f;
-    for (uint32_t p = gw; p < n; p += n_warps) {                 // consecutive warps take consecutive (row-ordered) pairs
-        const uint2 pr = pairs[p];
-        const uint32_t q = pr.y / cb.cap;
-        const float4* xrow = reinterpret_cast<const float4*>(seg_row_ptr(segs, pr.x, d));
+    // consecutive warps take consecutive (row-ordered) pairs; the next pair and its screen score are fetched while the
+    // current row is in flight (one exposed global-memory latency per iteration instead of two)
+    uint2 pr = make_uint2(0u, 0u);
+    float old = 0.f;
+    auto fetch_meta = [&](uint32_t p) {
+        if (p < n) {
+            pr = pairs[p];
+            if (lane == 0) old = cb.score[pr.y];
+        }
+    };
+    fetch_meta(gw);
+    for (uint32_t p = gw; p < n; p += n_warps) {
+        const uint2 cur = pr;
+        const float cur_old = old;
+        const uint32_t q = cur.y / cb.cap;
+        const float4* xrow = reinterpret_cast<const float4*>(seg_row_ptr(segs, cur.x, d));
         const float4* qrow = reinterpret_cast<const float4*>(qmat + (size_t)q * d);
         float4 xv[VPL], qv[VPL];
 #pragma unroll
@@ -776,14 +800,15 @@ __global__ void __launch_bounds__(256) rescore_pairs_kernel(CandBuf cb, const ui
             xv[i] = __ldg(xrow + i * 32 + lane);
             qv[i] = __ldg(qrow + i * 32 + lane);
         }
+        fetch_meta(p + n_warps);
         float a = 0.f;
 #pragma unroll
         for (int i = 0; i < VPL; ++i) a = lane_fma4(a, qv[i], xv[i]);
         a = warp_sum(a);
         if (lane == 0) {
-            worst = fmaxf(worst, fabsf(a - cb.score[pr.y]));
-            cb.exact[pr.y] = a;
-            cb.score[pr.y] = a;
+            worst = fmaxf(worst, fabsf(a - cur_old));
+            cb.exact[cur.y] = a;
+            cb.score[cur.y] = a;
         }
     }
     if (lane == 0) {

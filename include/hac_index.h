@@ -42,7 +42,7 @@ extern "C" {
 #define HAC_MAX_K 1024       /* faiss-gpu caps k at 2048; BASELINE's sweep tops out at 1000 */
 
 /* scan paths (hac_search*_ex `path` argument / hac_stats.path) */
-#define HAC_PATH_AUTO 0
+#define HAC_PATH_AUTO 0      /* int8 screen when its image exists and k <= 128, else the f16 screen */
 #define HAC_PATH_GEMV 1      /* exact fp32 HBM-streaming scan, small query batches */
 #define HAC_PATH_MMA 2       /* tcgen05 f16 screen + exact fp32 rescore of the shortlist */
 #define HAC_PATH_I8 3        /* tcgen05 int8 screen (s32 accumulate) + exact fp32 rescore of every emitted row */
@@ -157,14 +157,18 @@ int hac_pinned_free(void* host);
  *   "mma_cta_group"  1 = one CTA per scan tile, 2 = CTA pairs sharing each MMA (cta_group::2)
  *   "chunk_growth_x100"  corpus-chunk growth factor of the threshold schedule, in percent (default 400)
  *   "default_path"   the scan path HAC_PATH_AUTO resolves to (HAC_PATH_GEMV / _MMA / _I8)
- *   "build_i8"       1 = also keep an int8 image of the corpus (rows*d bytes of HBM) so that HAC_PATH_I8
- *                    can be used (default 0; without it HAC_PATH_I8 falls back to HAC_PATH_MMA); empty index only
- *   "center_screen"  1 (default) = the f16 image holds x - c, c = column means of the first rows added after a
+ *   "build_i8"       1 (default when d % 128 == 0) = also keep an int8 image of the corpus (rows*d bytes of HBM) for
+ *                    HAC_PATH_I8, 0 = save the memory (HAC_PATH_I8 then falls back to HAC_PATH_MMA); empty index
+ *                    only; the environment variable HAC_BUILD_I8 sets the default of new handles
+ *   "scan_tile_major"  unit order of the tensor-core scans: 1 = every CTA group walks whole 256-row corpus tiles (all
+ *                    query tiles of a tile back to back: one HBM fetch per tile, L2 re-reads from the same SMs), 0 = units
+ *                    striped over the CTAs, -1 (default) = per path (1 for the int8 screen, 0 for the f16 one)
+ *   "i8_cta_group"   2 (default) = CTA pairs share each int8 MMA (cta_group::2), 1 = one CTA per tile
+ *   "center_screen"  1 (default) = the f16 / int8 images hold x - c, c = column means of the first rows added after a
  *                    reset, and the scan adds q.c back: embeddings with a large shared component (ANCE) get a
  *                    margin made of the centred norms; results are unaffected (exact rescore); empty index only
- *   "i8_auto_max_queries"  with the int8 image present, HAC_PATH_AUTO takes the int8 screen for batches of at most
- *                    this many queries (default 128; 0 = never): small batches are HBM-bound and the int8 image is
- *                    half the bytes of the f16 one
+ *   "i8_auto_max_k" / "i8_auto_max_queries"  with the int8 image present, HAC_PATH_AUTO takes the int8 screen for
+ *                    k <= 128 and any batch size by default (its shortlist grows with k); 0 = never
  *   "f16_drop_bits_corpus" / "f16_drop_bits_queries"  low mantissa bits of the f16 image forced to zero
  *                    (0..8, default 3 / 0): sparser operands draw less tensor-core power, the screen margin
  *                    is computed from the actual rounding error so exactness is unaffected; corpus: empty index only */

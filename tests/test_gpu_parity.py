@@ -102,7 +102,7 @@ def test_large_batch_mma_path(nq, n, k):
     q = rng.standard_normal((nq, 768), dtype=np.float32)
     idx = hb.FlatIPIndex(768)
     idx.add(x)
-    D, I = idx.search(q, k)
+    D, I = idx.search(q, k, path=hb.HAC_PATH_MMA)
     st = idx.stats()
     assert st["path"] == hb.HAC_PATH_MMA and st["retries"] == 0
     assert st["screen_err_max"] <= st["margin_max"], st      # the rigorous margin really bounds the screen error
@@ -307,10 +307,11 @@ def test_operand_scaling_extreme_magnitudes():
         x, q = (base_x * np.float32(sx)), (base_q * np.float32(sq))
         idx = hb.FlatIPIndex(768)
         idx.add(x)
-        D, I = idx.search(q, 50)
-        st = idx.stats()
-        assert st["retries"] == 0 and st["screen_err_max"] <= st["margin_max"], (sx, sq, st)
-        _check(q, x, 50, D, I, also_fp32_oracle=False)
+        for path in (hb.HAC_PATH_MMA, hb.HAC_PATH_I8):
+            D, I = idx.search(q, 50, path=path)
+            st = idx.stats()
+            assert st["path"] == path and st["retries"] == 0 and st["screen_err_max"] <= st["margin_max"], (sx, sq, st)
+            _check(q, x, 50, D, I, also_fp32_oracle=False)
 
 
 def test_all_zero_corpus_is_one_big_tie():
@@ -479,7 +480,7 @@ def test_centred_screen_shrinks_the_margin_and_changes_nothing_else():
         idx.set_option("center_screen", centred)
         idx.add(x[:50000])
         idx.add(x[50000:])                               # later adds use the centre of the first one
-        D, I = idx.search(q, 100)
+        D, I = idx.search(q, 100, path=hb.HAC_PATH_MMA)
         st = idx.stats()
         assert st["screen_err_max"] <= st["margin_max"], st
         out[centred] = (D, I, st)
@@ -520,37 +521,65 @@ def test_careful_mode_is_sticky_until_reset():
     q = (v * rng.uniform(0.5, 2.0, size=(40, 1)) + 0.05 * rng.standard_normal((40, 768))).astype(np.float32)
     idx = hb.FlatIPIndex(768)
     idx.add(x)
-    D, I = idx.search(q, 100)
+    D, I = idx.search(q, 100, path=hb.HAC_PATH_MMA)
     assert idx.stats()["retries"] == 1
-    D2, I2 = idx.search(q, 100)
+    D2, I2 = idx.search(q, 100, path=hb.HAC_PATH_MMA)
     assert idx.stats()["retries"] == 0                   # started in careful mode: no wasted fast pass
     assert np.array_equal(I, I2) and np.array_equal(D, D2)
     assert np.array_equal(I, np.tile(np.arange(5000, 5100), (40, 1)))
     idx.reset()
     idx.add(x[:5000])
-    idx.search(q, 100)
+    idx.search(q, 100, path=hb.HAC_PATH_MMA)
     assert idx.stats()["retries"] == 0
 
 
-@pytest.mark.parametrize("nq", [1, 4, 32, 129])
-def test_auto_path_takes_the_int8_screen_for_small_batches(nq):
+@pytest.mark.parametrize("nq,k", [(1, 100), (4, 100), (32, 10), (129, 128), (300, 100), (64, 129), (40, 1000)])
+def test_auto_path_policy(nq, k):
+    """The int8 image is built by default; AUTO takes its screen for k <= 128 at every batch size and the f16 screen
+    for larger k (the int8 shortlist grows with k).  Same results either way."""
     hb = _engine()
     rng = np.random.default_rng(80 + nq)
     x = rng.standard_normal((90000, 768), dtype=np.float32)
     q = rng.standard_normal((nq, 768), dtype=np.float32)
     idx = hb.FlatIPIndex(768)
-    idx.set_option("build_i8", 1)
     idx.add(x)
-    D, I = idx.search(q, 100)
+    D, I = idx.search(q, k)
     st = idx.stats()
-    assert st["path"] == (hb.HAC_PATH_I8 if nq <= 128 else hb.HAC_PATH_MMA), st
-    assert st["candidates_rescored"] >= nq * 100
-    Dm, Im = idx.search(q, 100, path=hb.HAC_PATH_MMA)
+    assert st["path"] == (hb.HAC_PATH_I8 if k <= 128 else hb.HAC_PATH_MMA) and st["retries"] == 0, st
+    assert st["bytes_shadow"] >= 90000 * 768 * 3               # f16 + int8 images
+    Dm, Im = idx.search(q, k, path=hb.HAC_PATH_MMA)
     assert np.array_equal(I, Im) and np.array_equal(D, Dm)
-    _check(q, x, 100, D, I, also_fp32_oracle=False)
-    idx.set_option("i8_auto_max_queries", 0)
-    idx.search(q, 100)
+    _check(q, x, k, D, I, also_fp32_oracle=False)
+    idx.set_option("i8_auto_max_k", 0)
+    idx.search(q, k)
     assert idx.stats()["path"] == hb.HAC_PATH_MMA
+    # without the image: the f16 screen, and an explicit HAC_PATH_I8 request falls back to it
+    idx2 = hb.FlatIPIndex(768)
+    idx2.set_option("build_i8", 0)
+    idx2.add(x[:20000])
+    D2, I2 = idx2.search(q, min(k, 128), path=hb.HAC_PATH_I8)
+    assert idx2.stats()["path"] == hb.HAC_PATH_MMA and idx2.stats()["bytes_shadow"] < 20224 * 768 * 3
+    _check(q, x[:20000], min(k, 128), D2, I2, also_fp32_oracle=False)
+
+
+def test_int8_overflow_is_remembered_until_reset():
+    hb = _engine()
+    rng = np.random.default_rng(21)
+    v = rng.standard_normal(768).astype(np.float32)
+    x = np.concatenate([rng.standard_normal((5000, 768), dtype=np.float32), np.tile(v, (30000, 1))], 0)
+    q = (v * rng.uniform(0.5, 2.0, size=(40, 1)) + 0.05 * rng.standard_normal((40, 768))).astype(np.float32)
+    idx = hb.FlatIPIndex(768)
+    idx.add(x)
+    D, I = idx.search(q, 100)                            # int8 screen overflows, f16 fast mode overflows, careful mode
+    assert idx.stats()["path"] == hb.HAC_PATH_MMA and idx.stats()["retries"] >= 2
+    D2, I2 = idx.search(q, 100)                          # straight to the f16 screen in careful mode
+    assert idx.stats()["path"] == hb.HAC_PATH_MMA and idx.stats()["retries"] == 0
+    assert np.array_equal(I, I2) and np.array_equal(D, D2)
+    assert np.array_equal(I, np.tile(np.arange(5000, 5100), (40, 1)))
+    idx.reset()
+    idx.add(x[:5000])
+    idx.search(q, 100)
+    assert idx.stats()["path"] == hb.HAC_PATH_I8 and idx.stats()["retries"] == 0
 
 
 @pytest.mark.parametrize("direct", [False, True])
@@ -605,3 +634,28 @@ def test_int8_screen_on_anisotropic_rows_needs_the_centre():
     assert res[0][2]["candidates_rescored"] > 2 * st["candidates_rescored"] or res[0][2]["retries"] >= 1, res[0][2]
     assert np.array_equal(res[1][1], res[0][1]) and np.array_equal(res[1][0], res[0][0])
     _check(q, x, 100, res[1][0], res[1][1], also_fp32_oracle=False)
+
+
+@pytest.mark.parametrize("nq,n,k", [(130, 50000, 100), (300, 120001, 100), (256, 4096, 1), (64, 70000, 1000),
+                                    (700, 90000, 10)])
+def test_int8_screen_cta_pairs_and_unit_schedules(nq, n, k):
+    """cta_group::2 int8 scan (CTA pairs share each MMA) and both unit schedules: bitwise the same results."""
+    hb = _engine()
+    rng = np.random.default_rng(nq + n + k)
+    x = rng.standard_normal((n, 768), dtype=np.float32)
+    q = rng.standard_normal((nq, 768), dtype=np.float32)
+    idx = hb.FlatIPIndex(768)
+    idx.set_option("build_i8", 1)
+    idx.add(x)
+    Dm, Im = idx.search(q, k, path=hb.HAC_PATH_MMA)
+    for cg in (1, 2):
+        for tile_major in (0, 1):
+            idx.set_option("i8_cta_group", cg)
+            idx.set_option("scan_tile_major", tile_major)
+            D8, I8 = idx.search(q, k, path=hb.HAC_PATH_I8)
+            st = idx.stats()
+            assert st["path"] == hb.HAC_PATH_I8 and st["retries"] == 0, (cg, tile_major, st)
+            assert np.array_equal(I8, Im) and np.array_equal(D8, Dm), (cg, tile_major)
+            Df, If = idx.search(q, k, path=hb.HAC_PATH_MMA)          # the f16 scan under the same schedule
+            assert np.array_equal(If, Im) and np.array_equal(Df, Dm), (cg, tile_major)
+    _check(q, x, k, Dm, Im, also_fp32_oracle=False)
