@@ -325,10 +325,10 @@ def run_ours(args):
         # the scan runs tcgen05.mma.kind::i8: the int8 dense rate of the tensor pipe is twice the bf16 rate and
         # MEASURED_PEAKS.json holds no int8 figure, so the denominator is 2 x the measured sustained bf16 number.
         # DRAM traffic from the committed `ncu --set full` capture of the largest launch
-        # (profiles/r01b_ncu_scan_i8_q2514_summary.txt): 12.02 GB read + 0.04 GB written for 15 622 896 rows of 768 B.
+        # (profiles/r01b_ncu_scan_i8_q2514_summary.txt): 7.227 GB read + 0.024 GB written for 9 392 880 rows of 768 B.
         peak, bytes_row, traffic_row = 2.0 * bf16_peak, 768.0, 772.0
         peak_src = "2 x %s bf16_tflops_sustained (kind::i8 runs at twice the bf16 tensor-pipe rate; no int8 entry in MEASURED_PEAKS.json)" % peak_kind
-        cap_note = "12.06 GB for 15.6M rows"
+        cap_note = "7.25 GB for 9.39M rows"
     else:
         # f16 screen; ncu capture profiles/r01_final_ncu_scan_mma_summary.txt: 29.70 GB read + 0.05 GB written by the
         # launch that covers 19 300 592 rows, i.e. 1539 B per corpus row against 1536 B algorithmic: read once.

@@ -409,8 +409,12 @@ int search_batch_i8(hac_index* idx, int nq, int nq_pad, const float* q_dev, int 
     // large batches: rescoring the emitted pairs is a fifth of the search, and fresher thresholds emit fewer of them
     // (measured at 25.7M x 2514, k=100: growth 2.0 -> 26.4M pairs, 53.5 ms; 1.0 -> 21.9M, 48.8 ms; 0.6 -> 19.9M,
     // 47.2 ms; 0.35 -> 18.5M, 46.9 ms); smaller batches keep few chunks (each costs ~40 us of latency)
+    // and small shards (8-GPU slices) gain less from pruning than the extra chunks cost
     const double growth = idx->i8_chunk_growth > 0.0 ? idx->i8_chunk_growth
-                          : few ? 4.0 : (nq >= 512 && k <= 128) ? 0.6 : (k <= 128 ? 2.0 : 1.0);
+                          : few ? 4.0
+                          : (nq >= 512 && k <= 128 && idx->ntotal >= (8ll << 20)) ? 0.6
+                          : (nq >= 512 && k <= 128 && idx->ntotal >= (1ll << 20)) ? 1.0
+                          : (k <= 128 ? 2.0 : 1.0);
     const int64_t first = few ? cap / 2 : std::min<int64_t>(cap / 2, std::max<int64_t>(512, round_up(2 * (int64_t)k, kRowAlign)));
     int64_t rows_done = 0;
     for (size_t si = 0; si < idx->segs.size(); ++si) {
