@@ -58,6 +58,7 @@ SIGNATURES = {
     "hac_merge_topk_peers_device": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, c_i64, ctypes.c_int,
                                                    ctypes.POINTER(_VP), ctypes.POINTER(_VP), ctypes.c_int, _VP, _VP, _VP]),
     "hac_gather_ids_device": (ctypes.c_int, [ctypes.c_int, _VP, c_i64, _VP, c_i64, _VP, _VP]),
+    "hac_set_threshold_exchange": (ctypes.c_int, [_VP, _VP, ctypes.POINTER(_VP), ctypes.c_int, c_i64]),
     "hac_reciprocal_rank_device": (ctypes.c_int, [ctypes.c_int, _VP, c_i64, ctypes.c_int, _VP, _VP, _VP, _VP, _VP]),
     "hac_pinned_alloc": (ctypes.c_int, [ctypes.c_size_t, ctypes.POINTER(_VP)]),
     "hac_pinned_free": (ctypes.c_int, [_VP]),

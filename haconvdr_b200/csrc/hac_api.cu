@@ -96,6 +96,11 @@ struct hac_index {
     // screen, striped for the f16 one: measured 57.2 vs 61.1 ms and 83.1 vs 75.2 ms per search), 0 / 1 = forced
     int scan_tile_major = -1;
     int i8_cta_group = 2;                   // int8 screen: 2 = CTA pairs (a third less operand traffic from L2): 50.3 vs 56.9 ms
+    // cross-shard threshold exchange (hac_set_threshold_exchange): buffers, and the epoch of the next searches (0 = off)
+    ThrExchange exchange{};
+    int64_t exchange_capacity = 0;
+    int64_t exchange_epoch = 0;
+    int cur_batch = 0;                      // index of the query batch inside the current search call
     int sticky_level = 0;                   // searches start in careful mode once the fast mode overflowed (until reset)
     Workspace ws;
     hac_stats stats{};
@@ -392,6 +397,10 @@ int search_batch_i8(hac_index* idx, int nq, int nq_pad, const float* q_dev, int 
         }
     }
     const float* center = idx->center_valid ? idx->center : nullptr;
+    // threshold exchange with the other shards: on when the caller armed an epoch for this search
+    ThrExchange ex = idx->exchange;
+    const bool use_ex = ex.n_peers > 0 && idx->exchange_epoch > 0 && nq <= idx->exchange_capacity && idx->cur_batch < 16;
+    ex.tag = (uint32_t)(((uint64_t)idx->exchange_epoch << 4) | (uint64_t)idx->cur_batch);
     cudaEventRecord(idx->ev[0], s);
     launch_init_search(cb, w.tau, w.thr, nq, nq_pad, s);
     launch_convert_queries_i8(q_dev, nq, nq_pad, d, w.q_shadow8, w.q_consts, s);
@@ -458,7 +467,7 @@ int search_batch_i8(hac_index* idx, int nq, int nq_pad, const float* q_dev, int 
                                                    w.pair_hist + 2 * w.pair_buckets, w.pairs, idx->sm_count,
                                                    w.scalars + 2, w.counters + 1, s);
             if (!by_row) launch_rescore_new(cb, q_dev, d, segs, nq, w.scalars + 2, w.counters + 1, s);
-            launch_refresh(cb, k, w.margin, w.tau, w.thr, nq, s);
+            launch_refresh(cb, k, w.margin, w.tau, w.thr, nq, s, use_ex ? &ex : nullptr);
             launches += by_row ? 6 : 3;
             ++n_chunks;
             rows_done += r1 - r;
@@ -733,6 +742,7 @@ int search_common(hac_index* idx, int64_t nq, const float* q, bool q_on_host, in
     int launches = 0, retries = 0;
     float margin_max = 0.f, err_max = 0.f;
     for (int64_t q0 = 0; q0 < nq; q0 += max_batch) {
+        idx->cur_batch = (int)(q0 / max_batch);
         const int nb = (int)std::min<int64_t>(max_batch, nq - q0);
         const int nb_pad = (int)round_up(nb, kTileRows * std::max(idx->mma_cta_group, idx->i8_cta_group));
         int rc = ensure_workspace(idx, nb_pad, cap_for_k(k, 0), (q_on_host || out_on_host) ? (int64_t)nb * k : 0);
@@ -983,6 +993,24 @@ int hac_gather_ids_device(int device, const int64_t* table_dev, int64_t table_n,
     return HAC_OK;
 }
 
+int hac_set_threshold_exchange(hac_index* idx, uint64_t* mine_dev, const uint64_t* const* peers_dev, int n_peers,
+                               int64_t capacity) {
+    if (idx == nullptr) return fail(HAC_E_INVALID, "set_threshold_exchange: null index");
+    if (n_peers < 0 || n_peers > kMaxPeerLists - 1 || capacity < 0 || (n_peers > 0 && (!mine_dev || !peers_dev)))
+        return fail(HAC_E_INVALID, "set_threshold_exchange: bad argument");
+    idx->exchange = ThrExchange{};
+    idx->exchange_capacity = 0;
+    if (n_peers == 0) return HAC_OK;
+    for (int i = 0; i < n_peers; ++i) {
+        if (!peers_dev[i]) return fail(HAC_E_INVALID, "set_threshold_exchange: null peer pointer");
+        idx->exchange.peers[i] = reinterpret_cast<const unsigned long long*>(peers_dev[i]);
+    }
+    idx->exchange.mine = reinterpret_cast<unsigned long long*>(mine_dev);
+    idx->exchange.n_peers = n_peers;
+    idx->exchange_capacity = capacity;
+    return HAC_OK;
+}
+
 int hac_reciprocal_rank_device(int device, const int64_t* pids_dev, int64_t nq, int k, const int64_t* rel_ptr_dev,
                                const int64_t* rel_pids_dev, float* rr_out_dev, int32_t* rank_out_dev, void* stream) {
     if (!pids_dev || !rel_ptr_dev || !rr_out_dev || !rank_out_dev || nq < 0 || k <= 0 || k > 4096)
@@ -1042,6 +1070,11 @@ int hac_set_option(hac_index* idx, const char* name, int64_t value) {
         return HAC_OK;
     }
     if (strcmp(name, "i8_rescore_by_row") == 0) { idx->i8_rescore_by_row = value != 0; return HAC_OK; }
+    if (strcmp(name, "exchange_epoch") == 0) {
+        if (value < 0 || value > 0x0FFFFFFF) return fail(HAC_E_INVALID, "exchange_epoch out of range");
+        idx->exchange_epoch = value;
+        return HAC_OK;
+    }
     if (strcmp(name, "i8_chunk_growth_x100") == 0) {
         if (value != 0 && (value < 10 || value > 1600)) return fail(HAC_E_INVALID, "i8_chunk_growth_x100 must be 0 or in [10, 1600]");
         idx->i8_chunk_growth = (double)value / 100.0;

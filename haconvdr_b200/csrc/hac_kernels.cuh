@@ -44,6 +44,18 @@ struct CandBuf {
     uint32_t cap;
 };
 
+// Cross-shard threshold exchange (one process per GPU, corpus sharded): every shard publishes, per query, its
+// ceil(k/G)-th best exact score so far into a buffer its peers can read over NVLink; the minimum over all shards is a
+// lower bound on the GLOBAL k-th best (refresh_kernel), to which every shard raises its threshold.  Entries are
+// (tag << 32 | float bits); a reader ignores entries whose tag is not the current search's, so no barrier or reset is
+// needed between searches.
+struct ThrExchange {
+    unsigned long long* mine;                          // [capacity] this shard's published bounds (peer-readable)
+    const unsigned long long* peers[kMaxPeerLists];    // the other shards' buffers (peer-mapped device pointers)
+    int n_peers;                                       // 0 = no exchange
+    uint32_t tag;
+};
+
 struct SegTable {
     int n;
     uint32_t base[kMaxSegments];     // index-local row of the segment's first row
@@ -82,7 +94,9 @@ void launch_init_search(CandBuf cb, float* tau, float* thr, int nq, int nq_pad, 
 void launch_margins(const float* q_norm, const float* q_err, const OperandStats* corpus, const float* center_norm,
                     int d, float* margin, float* margin_max, int nq, cudaStream_t s);
 // per query: sort the shortlist, raise tau to the k-th best screen score, drop entries below tau - 2m
-void launch_refresh(CandBuf cb, int k, const float* margin, float* tau, float* thr, int nq, cudaStream_t s);
+// ex: optional threshold exchange (exact-score shortlists only, i.e. the int8 path); nullptr = none
+void launch_refresh(CandBuf cb, int k, const float* margin, float* tau, float* thr, int nq, cudaStream_t s,
+                    const ThrExchange* ex = nullptr);
 // exact fp32 scores of every shortlisted pair
 void launch_rescore(CandBuf cb, const float* q, int d, SegTable segs, int nq, float* screen_err_max,
                     unsigned long long* rescored, cudaStream_t s);

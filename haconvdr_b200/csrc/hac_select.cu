@@ -125,26 +125,36 @@ constexpr int kRefreshMaxThreads = 1024;   // 256 per query for large batches, 1
 __global__ void __launch_bounds__(kRefreshMaxThreads) refresh_kernel(CandBuf cb, int k,
                                                                   const float* __restrict__ margin,
                                                                   float* __restrict__ tau,
-                                                                  float* __restrict__ thr) {
+                                                                  float* __restrict__ thr, const ThrExchange ex) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     uint32_t* keys = reinterpret_cast<uint32_t*>(smem_raw);          // [cap]
     __shared__ uint32_t hist[256];
     __shared__ uint32_t s_prefix, s_want;
     __shared__ uint32_t warp_cnt[kRefreshMaxThreads / 32];
     __shared__ uint32_t s_base;
+    __shared__ uint32_t s_peer_key, s_peer_have, s_own_key;
     const int q = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int n_threads = blockDim.x;
+    // peers' published bounds (and this shard's own previous one): the loads cross NVLink (~2 us), so they are issued
+    // first and consumed last
+    unsigned long long peer_word = 0ull;
+    if (tid < ex.n_peers)
+        asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(peer_word) : "l"(ex.peers[tid] + q) : "memory");
+    else if (tid == ex.n_peers && ex.n_peers > 0)
+        asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(peer_word) : "l"(ex.mine + q) : "memory");
+    if (tid == 0) { s_peer_key = 0xFFFFFFFFu; s_peer_have = 0u; s_own_key = 0u; }
     const uint32_t raw = cb.count[q];
     const int cnt = (int)min(raw, cb.cap);
     if (raw > cb.cap && tid == 0) *cb.overflow = 1u;
-    if ((uint32_t)cnt == cb.sorted[q]) return;   // nothing new since the last refresh (uniform per block)
+    if ((uint32_t)cnt == cb.sorted[q] && ex.n_peers == 0) return;   // nothing new since the last refresh (uniform per block)
     float* sc = cb.score + (size_t)q * cb.cap;
     uint32_t* rw = cb.row + (size_t)q * cb.cap;
     for (int i = tid; i < cnt; i += n_threads) keys[i] = float_key(sc[i]);
-    float tau_new = tau[q];
-    if (cnt >= k) {
-        if (tid == 0) { s_prefix = 0u; s_want = (uint32_t)k; }
+    // key of the want-th best entry (1-based, want <= cnt): 8-bit MSB radix select; every thread of the block calls it
+    auto select_kth = [&](uint32_t want_rank) -> uint32_t {
+        __syncthreads();
+        if (tid == 0) { s_prefix = 0u; s_want = want_rank; }
         uint32_t mask = 0u;
 #pragma unroll 1
         for (int shift = 24; shift >= 0; shift -= 8) {
@@ -168,7 +178,7 @@ __global__ void __launch_bounds__(kRefreshMaxThreads) refresh_kernel(CandBuf cb,
                     if (lane >= o) incl += v;
                 }
                 const uint32_t excl = incl - sum, want = s_want;
-                if (excl < want && want <= incl) {                    // the k-th best falls into this lane's bins
+                if (excl < want && want <= incl) {                    // the wanted entry falls into this lane's bins
                     uint32_t cum = excl;
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
@@ -183,7 +193,36 @@ __global__ void __launch_bounds__(kRefreshMaxThreads) refresh_kernel(CandBuf cb,
             mask |= 0xFFu << shift;
             __syncthreads();
         }
-        tau_new = fmaxf(tau_new, key_float(s_prefix));
+        return s_prefix;
+    };
+    float tau_new = tau[q];
+    if (cnt >= k) tau_new = fmaxf(tau_new, key_float(select_kth((uint32_t)k)));
+    if (ex.n_peers > 0) {
+        // Share rule: if each of the G shards holds at least ks = ceil(k / G) rows scoring >= L_r, then at least k rows
+        // score >= min_r L_r globally.  This shard publishes L = its ks-th best exact score so far; once every peer has
+        // published for this search, min over all shards is a lower bound on the global k-th best - for evenly mixed
+        // shards about the global k-th best itself, where a shard's own k-th best only knows 1/G of the rows.
+        const int ks = (k + ex.n_peers) / (ex.n_peers + 1);
+        float L = -INFINITY;
+        if (cnt >= ks) L = key_float(select_kth((uint32_t)ks));
+        __syncthreads();
+        if ((uint32_t)(peer_word >> 32) == ex.tag) {
+            if (tid < ex.n_peers) {
+                atomicMin(&s_peer_key, float_key(__uint_as_float((uint32_t)peer_word)));
+                atomicAdd(&s_peer_have, 1u);
+            } else if (tid == ex.n_peers) {
+                s_own_key = float_key(__uint_as_float((uint32_t)peer_word));   // what this shard published before
+            }
+        }
+        __syncthreads();
+        if (s_own_key != 0u) L = fmaxf(L, key_float(s_own_key));        // an earlier claim stays true
+        if (L > -INFINITY) {
+            if (tid == 0) {
+                const unsigned long long w = ((unsigned long long)ex.tag << 32) | (unsigned long long)__float_as_uint(L);
+                asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(ex.mine + q), "l"(w) : "memory");
+            }
+            if (s_peer_have == (uint32_t)ex.n_peers) tau_new = fmaxf(tau_new, fminf(L, key_float(s_peer_key)));
+        }
     }
     float thr_new = -INFINITY;
     if (tau_new > -INFINITY) {
@@ -229,11 +268,13 @@ __global__ void __launch_bounds__(kRefreshMaxThreads) refresh_kernel(CandBuf cb,
     }
 }
 
-void launch_refresh(CandBuf cb, int k, const float* margin, float* tau, float* thr, int nq, cudaStream_t s) {
+void launch_refresh(CandBuf cb, int k, const float* margin, float* tau, float* thr, int nq, cudaStream_t s,
+                    const ThrExchange* ex) {
     const size_t smem = (size_t)cb.cap * sizeof(uint32_t);
     // the attribute is per device (several devices per process are possible), so it is set per launch
     if (smem > 40 * 1024) cudaFuncSetAttribute(refresh_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    refresh_kernel<<<nq, nq <= 64 ? kRefreshMaxThreads : 256, smem, s>>>(cb, k, margin, tau, thr);
+    ThrExchange none{};
+    refresh_kernel<<<nq, nq <= 64 ? kRefreshMaxThreads : 256, smem, s>>>(cb, k, margin, tau, thr, ex ? *ex : none);
 }
 
 // ---------------------------------------------------------------------------------------------

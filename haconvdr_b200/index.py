@@ -135,6 +135,13 @@ class FlatIPIndex:
                                       int(path)), "hac_search")
         return D, I
 
+    def set_threshold_exchange(self, mine_ptr: int, peer_ptrs, capacity: int):
+        """Cross-shard threshold exchange buffers (raw device pointers; see ``hac_set_threshold_exchange``)."""
+        n = len(peer_ptrs)
+        arr = (ctypes.c_void_p * max(n, 1))(*peer_ptrs)
+        check(self._lib.hac_set_threshold_exchange(self._h, mine_ptr, arr, n, int(capacity)),
+              "hac_set_threshold_exchange")
+
     def set_option(self, name: str, value: int):
         check(self._lib.hac_set_option(self._h, name.encode(), int(value)), "hac_set_option")
 

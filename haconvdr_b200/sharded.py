@@ -54,6 +54,9 @@ class ShardedFlatIPIndex:
         self._pinned_out = None    # page-locked staging for host results
         self.exchange = exchange   # "auto" | "p2p" | "nccl"
         self._symm = None          # (handle, buffer, nq, k) of the symmetric result buffer
+        self._thr = None           # (handle, buffer, capacity) of the symmetric threshold-exchange buffer
+        self._epoch = 0            # search counter, identical on all ranks (tags the exchanged thresholds)
+        self.threshold_exchange = True   # p2p path: shards share their k-th-best bounds while they scan
         self._symm_failed = False
         self._step = 0
         self.profile = False       # True: record per-phase CUDA-event times of each search (diagnostics)
@@ -132,7 +135,17 @@ class ShardedFlatIPIndex:
             off = slot * slot_bytes
             D_loc = buf[off:off + d_bytes].view(torch.float32).view(nq, k)
             I_loc = buf[off + d_bytes:off + d_bytes + i_bytes].view(torch.int64).view(nq, k)
-            self.local.search(q, k, out=(D_loc, I_loc))          # results land in the symmetric buffer
+            # the shards publish their ceil(k/G)-th best scores to each other while they scan; the minimum bounds the
+            # GLOBAL k-th best, so every shard emits / rescores ~1/G of the candidates it would alone; its list then
+            # holds only its share of the global top-k (fillers behind), which is all the merge below needs
+            self._epoch += 1
+            armed = self.threshold_exchange and self._ensure_thr(nq)
+            self.local.set_option("exchange_epoch", self._epoch if armed else 0)
+            try:
+                self.local.search(q, k, out=(D_loc, I_loc))      # results land in the symmetric buffer
+            finally:
+                if armed:
+                    self.local.set_option("exchange_epoch", 0)
             if prof:
                 ev[1].record()
             hdl.barrier(channel=0)                               # every rank's lists are complete
@@ -210,6 +223,32 @@ class ShardedFlatIPIndex:
             self._symm_failed = True
             import warnings
             warnings.warn("symmetric memory unavailable (%s); using the NCCL all-gather exchange" % (e,))
+            return False
+
+    def _ensure_thr(self, nq: int) -> bool:
+        """Symmetric-memory buffer of per-query threshold words, registered with the local engine."""
+        if self._thr is not None and self._thr[2] >= nq:
+            return True
+        torch, dist = self._torch, self._dist
+        try:
+            import torch.distributed._symmetric_memory as symm_mem
+            cap = max(int(nq), 4096)
+            with torch.cuda.device(self._device()):
+                buf = symm_mem.empty((cap,), dtype=torch.int64, device=self._device())
+                buf.zero_()
+                hdl = symm_mem.rendezvous(buf, self.group if self.group is not None else dist.group.WORLD)
+            torch.cuda.synchronize(self._device())
+            hdl.barrier(channel=1)                               # every rank's buffer is zeroed before anyone reads it
+            ptrs = list(hdl.buffer_ptrs)
+            mine = ptrs[self.rank]
+            peers = [p for r, p in enumerate(ptrs) if r != self.rank]
+            self.local.set_threshold_exchange(mine, peers, cap)
+            self._thr = (hdl, buf, cap)
+            return True
+        except Exception as e:          # not available: every shard keeps its own thresholds (still exact)
+            import warnings
+            warnings.warn("threshold exchange unavailable (%s)" % (e,))
+            self.threshold_exchange = False
             return False
 
     def _on_gpu(self) -> bool:

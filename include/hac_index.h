@@ -132,6 +132,22 @@ int hac_merge_topk_peers_device(int device, int n_lists, int64_t nq, int k, cons
                                 const int64_t* const* I_list_ptrs, int k_out, float* D_out_dev,
                                 int64_t* I_out_dev, void* stream);
 
+/* Cross-shard threshold exchange (one process per GPU, corpus sharded; optional).  A shard alone only knows the k-th
+ * best score of its own 1/G of the rows, so it emits and rescores as many candidates as a whole-corpus search would.
+ * With the exchange every shard publishes per query L_r = its ceil(k/G)-th best exact score so far into `mine_dev` and
+ * reads what its peers published through `peers_dev` (HOST array of n_peers = G-1 <= 15 peer-mapped DEVICE pointers,
+ * e.g. symmetric memory read over NVLink): at least k rows score >= min_r L_r globally, so that minimum is a lower
+ * bound on the GLOBAL k-th best and every shard raises its threshold to it.  Buffers hold `capacity` u64 entries
+ * (tag << 32 | float bits), zero-initialised by the caller.  The exchange is armed per search with
+ * hac_set_option(idx, "exchange_epoch", e): e > 0 must be the same on all shards for the same search and different
+ * from the previous searches' (stale entries are ignored by tag, no barrier or reset between searches), e = 0
+ * switches it off.  With it armed a shard's result holds only its candidates for the GLOBAL top-k (possibly fewer
+ * than k, the rest filled with -FLT_MAX / -1): it is meant to be followed by hac_merge_topk_*.  Applies to the int8
+ * screen (exact-score shortlists).  n_peers = 0 clears the buffers.
+ * Replaces nothing in the reference: faiss IndexShards searches its shards independently. */
+int hac_set_threshold_exchange(hac_index* idx, uint64_t* mine_dev, const uint64_t* const* peers_dev, int n_peers,
+                               int64_t capacity);
+
 /* offset -> pid gather on the device (src/test_HAConvDR_topiocqa.py:250): out[i] =
  * table[ids[i]] for ids >= 0, -1 otherwise.  table/ids/out are device pointers. */
 int hac_gather_ids_device(int device, const int64_t* table_dev, int64_t table_n, const int64_t* ids_dev,
@@ -167,6 +183,7 @@ int hac_pinned_free(void* host);
  *   "center_screen"  1 (default) = the f16 / int8 images hold x - c, c = column means of the first rows added after a
  *                    reset, and the scan adds q.c back: embeddings with a large shared component (ANCE) get a
  *                    margin made of the centred norms; results are unaffected (exact rescore); empty index only
+ *   "exchange_epoch"  arms the cross-shard threshold exchange for the next searches (see hac_set_threshold_exchange)
  *   "i8_auto_max_k" / "i8_auto_max_queries"  with the int8 image present, HAC_PATH_AUTO takes the int8 screen for
  *                    k <= 128 and any batch size by default (its shortlist grows with k); 0 = never
  *   "f16_drop_bits_corpus" / "f16_drop_bits_queries"  low mantissa bits of the f16 image forced to zero
