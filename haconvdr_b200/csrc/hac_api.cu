@@ -505,9 +505,8 @@ int search_batch(hac_index* idx, int nq, const float* q_dev, int k, float* D_dev
                  int path) {
     const int d = idx->d;
     const int nq_pad = (int)round_up(nq, kTileRows);
-    // AUTO: the tensor-core screens stream 1/4 (int8) or 1/2 (f16) of the bytes of the fp32 rows, so they win
-    // at every batch size (measured: Q=1 5.4 ms f16 vs 11.3 ms fp32 over 25.7M rows); all paths end in the
-    // same exact fp32 scores.
+    // all paths end in the same exact fp32 scores; the tensor-core screens stream 1/4 (int8) or 1/2 (f16) of the
+    // bytes of the fp32 rows, so they also win at the smallest batches (Q=1: 3.0 / 5.4 / 11.3 ms over 25.7M rows)
     bool have_i8 = !idx->segs.empty();
     for (const auto& sg : idx->segs) have_i8 = have_i8 && sg.shadow8 != nullptr;
     if (path == HAC_PATH_AUTO) {

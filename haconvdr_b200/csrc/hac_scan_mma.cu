@@ -1,25 +1,28 @@
-// Large-batch scan: f16 screen scores on the 5th-gen tensor cores with a fused threshold filter.
+// Tensor-core screens: int8 (default) or f16 scores on the 5th-gen tensor cores with a fused threshold filter.
 //
-//   D[queries x 256 rows] (fp32, TMEM) += Qhat[queries x 64] * Xhat[256 x 64]^T   per K block,
-//   12 K blocks for d = 768, operands staged global -> shared by 16 KiB bulk async copies of the
-//   pre-swizzled shadow tiles (hac_common.cuh), tcgen05.mma issued by one thread, accumulators
-//   double-buffered in TMEM (2 x 256 columns), epilogue warps read them back with tcgen05.ld and
-//   compare every score against the owning query's emission threshold - only the (rare) survivors
-//   are appended to the shortlist in HBM, the score tile itself never leaves the SM.
+//   f16 : D[queries x 256 rows] (fp32, TMEM) += Qhat[queries x 64]  * Xhat[256 x 64]^T   per K block, 12 blocks for d = 768
+//   int8: D[queries x 256 rows] (s32,  TMEM) += Qi  [queries x 128] * Xi  [256 x 128]^T  per K block,  6 blocks for d = 768
+//   operands staged global -> shared by 16 KiB bulk async copies of the pre-swizzled shadow tiles (hac_common.cuh),
+//   tcgen05.mma issued by one thread, accumulators double-buffered in TMEM (2 x 256 columns), epilogue warps read
+//   them back with tcgen05.ld and compare every score against the owning query's emission threshold (int8: one
+//   integer threshold per query and 128-row tile) - only the (rare) survivors are appended to the shortlist in HBM,
+//   the score tile itself never leaves the SM.
 //
-// Two variants of one kernel (template kCG):
+// Template kCG (CTA group) x kI8 (operand kind):
 //   kCG = 1  one CTA per SM works alone: tile 128 queries x 256 rows, 4 stages of 48 KiB.
 //   kCG = 2  a CTA pair (cluster of 2, one TPC) shares each MMA (cta_group::2, M = 256): every CTA
 //            stages its own 128 queries and HALF of the 256 corpus rows, so shared-memory fills and
 //            operand reads per FLOP drop by a third; 6 stages of 32 KiB.  The pair's leader issues
 //            the MMAs; the peer forwards "my half has landed" to the leader through a remote
 //            mbarrier arrive; tcgen05.commit multicasts slot-free / accumulator-ready to both CTAs.
+//   Defaults: int8 -> kCG = 2 (single-tile batches run kCG = 1), f16 -> kCG = 1 (power-bound either way).
 // Warp roles (320 threads, persistent): warp 0 = copy producer, warp 1 = MMA issuer (leader) or
 // forwarder (peer) and owner of the TMEM allocation, warps 2..9 = epilogue (TMEM lane quarter =
 // warp % 4, one query per thread; warps 2..5 drain columns 0..127 of a tile, warps 6..9 columns 128..255).
-// Tile order (UnitSchedule): every CTA takes whole 256-row corpus tiles and runs all query tiles of a tile back to
-// back, so a corpus tile is pulled from HBM once and re-read from L2 by the same SM.
-// Roofline: tensor pipe; algorithmic FLOPs = 2 * queries * rows * d per launch.
+// Unit order (UnitSchedule): tile-major for int8 (every CTA group takes whole 256-row corpus tiles and runs all
+// query tiles of a tile back to back: one HBM fetch per tile, L2 re-reads from the same SMs), striped for f16
+// (consecutive CTAs take the query tiles of one corpus tile) - each measured faster for its kind.
+// Roofline: tensor pipe (HBM for batches of one query tile); algorithmic work = 2 * queries * rows * d per launch.
 #include <limits.h>
 
 #include "hac_common.cuh"
