@@ -46,6 +46,16 @@ for _ in range(3):                      # alternating slots
     Dp, Ip = idx.search(q, 100)
     assert np.array_equal(Ip, I) and np.array_equal(Dp, D)
 idx.exchange = "auto"
+# threshold exchange over NVLink during the scan: same merged result, never more rescoring than without it
+st_on = idx.local.stats()
+idx.threshold_exchange = False
+Dx, Ix = idx.search(q, 100)
+st_off = idx.local.stats()
+assert np.array_equal(Ix, I) and np.array_equal(Dx, D)
+assert st_on["candidates_rescored"] <= st_off["candidates_rescored"], (st_on, st_off)
+idx.threshold_exchange = True
+Dx, Ix = idx.search(q, 100)
+assert np.array_equal(Ix, I) and np.array_equal(Dx, D)
 # faiss-style preallocated outputs, page-locked and ordinary
 Dp = torch.empty((150, 100), dtype=torch.float32).pin_memory().numpy(); Ip = torch.empty((150, 100), dtype=torch.int64).pin_memory().numpy()
 r = idx.search(q, 100, D=Dp, I=Ip)

@@ -104,3 +104,27 @@ def test_shard_bounds_cover_rows_exactly():
             b = shard_bounds(n, g)
             assert b[0] == 0 and b[-1] == n and all(b[i] <= b[i + 1] for i in range(g))
             assert max(b[i + 1] - b[i] for i in range(g)) - min(b[i + 1] - b[i] for i in range(g)) <= 1
+
+
+def test_share_rule_bounds_the_global_kth_best():
+    """The bound the shards exchange while they scan (hac_set_threshold_exchange): if every one of G shards holds at
+    least ceil(k/G) rows scoring >= L_r, then min_r L_r <= the global k-th best score - for any split of the rows,
+    and with equality-ish tightness for evenly mixed shards."""
+    rng = np.random.default_rng(11)
+    for G, k, n in ((2, 100, 5000), (8, 100, 4000), (8, 10, 999), (3, 7, 50), (16, 100, 3000)):
+        s = rng.standard_normal(n).astype(np.float32)
+        ks = -(-k // G)
+        for split in ("even", "skewed"):
+            if split == "even":
+                shards = np.array_split(rng.permutation(s), G)
+            else:                                   # all the best rows in one shard: the bound must stay valid (if weak)
+                order = np.sort(s)[::-1]
+                cuts = np.sort(rng.choice(np.arange(ks * 2, n - ks * 2), G - 1, replace=False))
+                shards = np.split(order, cuts)
+            if any(len(x) < ks for x in shards):
+                continue
+            bound = min(np.sort(x)[::-1][ks - 1] for x in shards)
+            kth = np.sort(s)[::-1][k - 1]
+            assert bound <= kth
+            if split == "even" and n >= 50 * k:
+                assert np.sum(s >= bound) <= 4 * k     # close to the k-th best for mixed shards
