@@ -31,6 +31,8 @@ def test_library_is_sm100a_with_tcgen05_and_bulk_copy():
         pytest.skip("cuobjdump unavailable")
     assert "sm_100a" in sass
     assert "UTCHMMA" in sass and "LDTM" in sass and "UBLKCP" in sass
+    # the default scan: int8 tensor-core MMA issued by CTA pairs, 3-input max in the epilogue
+    assert "UTCIMMA.2CTA" in sass and "VIMNMX3" in sass and "FMNMX3" in sass
 
 
 @pytest.mark.parametrize("proto", [3, 4])
