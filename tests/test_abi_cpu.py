@@ -148,3 +148,20 @@ def test_reference_loop_over_native_blocks_matches_golden(name):
         D, I = retrieval.search_one_by_one_with_faiss(nb, d, FlatIP(g["q"].shape[1]), g["q"], g["k"])
     assert np.array_equal(I, g["I"])
     np.testing.assert_allclose(D, g["D"], rtol=1e-6, atol=0)
+
+
+@pytest.mark.parametrize("d,n", [(64, 1), (64, 1000), (192, 77), (1024, 5)])
+def test_native_block_file_other_dimensions(d, n):
+    rng = np.random.default_rng(d + n)
+    x = rng.standard_normal((n, d)).astype(np.float32)
+    ids = (np.arange(n, dtype=np.int64) * 3 + 7)              # not a contiguous range: stored as an array
+    with tempfile.TemporaryDirectory() as tmp:
+        p = loader.write_native_block(loader.native_block_path(tmp, 4), x, ids)
+        h = loader.read_native_header(p)
+        assert (h.n_rows, h.d) == (n, d) and h.emb_offset == 4096 and os.path.getsize(p) % 4096 == 0
+        assert h.ids_kind == (1 if n == 1 else 0)             # a single id is trivially a range
+        assert np.array_equal(loader.load_block_array(p), x)
+        assert np.array_equal(loader.load_native_embid(p), ids)
+        found = loader.find_block(tmp, 4)
+        assert found is not None and found[0] == p and np.array_equal(found[1](), ids)
+        assert loader.find_block(tmp, 5) is None
