@@ -1,0 +1,85 @@
+#!/usr/bin/env python
+"""Round-2 A/B on one GPU (full TopiOCQA-scale corpus by default): the pipelined int8 search (scans back to back,
+rescore + refresh on a side stream beside the next scan) against the chunk-synchronous schedule of round 1, for the
+headline batch and for the small turn batches, alternating in one process.
+
+One JSON line per (batch, variant).  Usage: python benchmarks/ab_pipeline.py [--rows N] [--reps R] [--only big,small]
+"""
+import argparse, json, os, sys, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+
+def med(xs):
+    xs = sorted(xs)
+    return xs[len(xs) // 2]
+
+
+VARIANTS = [
+    # name, options
+    ("sync", {"i8_pipeline": 0}),
+    ("pipe", {"i8_pipeline": 1}),
+    ("pipe_g250", {"i8_pipeline": 1, "i8_pipe_growth_x1000": 250}),
+    ("pipe_g60", {"i8_pipeline": 1, "i8_pipe_growth_x1000": 60}),
+    ("pipe_min2x", {"i8_pipeline": 1, "i8_pipe_min_rows": 151552}),
+    ("pipe_dist1", {"i8_pipeline": 1, "i8_pipe_dist": 1}),
+]
+DEFAULTS = {"i8_pipeline": 1, "i8_pipe_growth_x1000": 125, "i8_pipe_min_rows": 0, "i8_pipe_dist": 2}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--rows", type=int, default=25_700_592)
+    ap.add_argument("--reps", type=int, default=5)
+    ap.add_argument("--only", default="big,small")
+    ap.add_argument("--variants", default="")
+    args = ap.parse_args()
+    import torch
+    from haconvdr_b200 import FlatIPIndex
+    from haconvdr_b200.index import synth_rows_device
+    d = 768
+    idx = FlatIPIndex(d, 0)
+    idx.reserve(args.rows)
+    idx.add_synthetic(args.rows, seed=42)
+    variants = [v for v in VARIANTS if not args.variants or v[0] in args.variants.split(",")]
+    batches = []
+    if "big" in args.only:
+        batches.append(2514)
+    if "small" in args.only:
+        batches += [1, 4, 32, 128]
+    for nq in batches:
+        q = synth_rows_device(nq, d, seed=4242)
+        ref = None
+        acc = {name: [] for name, _ in variants}
+        wall = {name: [] for name, _ in variants}
+        for r in range(args.reps + 1):
+            for name, opts in variants:
+                for kk, vv in {**DEFAULTS, **opts}.items():
+                    idx.set_option(kk, vv)
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                D, I = idx.search(q, 100)
+                torch.cuda.synchronize()
+                dt = (time.perf_counter() - t0) * 1e3
+                if ref is None:
+                    ref = (D.clone(), I.clone())
+                assert torch.equal(I, ref[1]) and torch.equal(D, ref[0]), name
+                if r >= 1:
+                    acc[name].append(idx.stats())
+                    wall[name].append(dt)
+        for name, _ in variants:
+            sts = acc[name]
+            st = sts[-1]
+            print(json.dumps({"exp": "pipeline", "Q": nq, "variant": name, "total_ms": med(s["total_ms"] for s in sts),
+                              "best_ms": min(s["total_ms"] for s in sts), "wall_ms": med(wall[name]),
+                              "scan_ms": med(s["scan_ms"] for s in sts), "tail_ms": med(s["tail_ms"] for s in sts),
+                              "chunks": st["n_chunks"], "sync_chunks": st["n_sync_chunks"],
+                              "launches": st["kernel_launches"], "emitted": med(s["candidates_emitted"] for s in sts),
+                              "rescored": med(s["candidates_rescored"] for s in sts), "retries": st["retries"],
+                              "path": st["path"]}), flush=True)
+    for kk, vv in DEFAULTS.items():
+        idx.set_option(kk, vv)
+    idx.close()
+
+
+if __name__ == "__main__":
+    main()

@@ -17,6 +17,8 @@ CSRC = os.path.join(_HERE, "csrc")
 HAC_PATH_AUTO, HAC_PATH_GEMV, HAC_PATH_MMA, HAC_PATH_I8 = 0, 1, 2, 3
 HAC_MAX_K = 1024
 
+HAC_ABI_VERSION = 2
+
 c_i64 = ctypes.c_int64
 c_f32p = ctypes.POINTER(ctypes.c_float)
 c_i64p = ctypes.POINTER(ctypes.c_int64)
@@ -29,6 +31,8 @@ class HacStats(ctypes.Structure):
         ("candidates_rescored", ctypes.c_int64), ("margin_max", ctypes.c_float),
         ("screen_err_max", ctypes.c_float), ("scan_ms", ctypes.c_float), ("total_ms", ctypes.c_float),
         ("ntotal", ctypes.c_int64), ("bytes_fp32", ctypes.c_int64), ("bytes_shadow", ctypes.c_int64),
+        ("bytes_i8", ctypes.c_int64), ("n_sync_chunks", ctypes.c_int32), ("pipelined", ctypes.c_int32),
+        ("tail_ms", ctypes.c_float), ("reserved0", ctypes.c_float),
     ]
 
     def as_dict(self):

@@ -37,13 +37,15 @@ int fail_cuda(cudaError_t e, const char* what) {
 
 constexpr int64_t kRowAlign = 256;          // scan tile width: segment capacities and chunk edges
 constexpr int kMaxQueryBatch = 16384;
-constexpr int kMaxEvents = 96;
+constexpr int kMaxChunks = 64;                  // corpus chunks (threshold refresh points) of one search
+constexpr int kMaxEvents = 2 + 2 * kMaxChunks;  // timing events: search begin / end + one pair per scan launch
 
 int64_t round_up(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
 
 struct Segment {
     float* rows = nullptr;        // [cap_rows][d] fp32
-    uint8_t* shadow = nullptr;    // f16 tiled image of the same rows
+    uint8_t* shadow = nullptr;    // f16 tiled image of the same rows (allocated on first use when lazy)
+    int64_t f16_rows = 0;         // rows [0, f16_rows) of the segment are present in the f16 image
     uint8_t* shadow8 = nullptr;   // int8 tiled image (d % 128 == 0 only)
     TileQ8* tiles8 = nullptr;     // per-128-row-tile constants of the int8 image
     OperandStats* stats = nullptr;
@@ -61,9 +63,11 @@ struct Workspace {
     uint8_t* q_shadow = nullptr;
     uint8_t* q_shadow8 = nullptr;
     QueryQ8* q_consts = nullptr;
-    uint2* pairs = nullptr;       // int8 path: (row, slot) pairs of one chunk in row order
-    uint32_t* pair_hist = nullptr;   // [2 * pair_buckets + 1]: histogram, cursors, total
-    int64_t pairs_cap = 0, pair_buckets = 0;
+    // int8 path: two log shortlists the scans append to (chunk i -> lg[i & 1]); the side-stream worker rescores a
+    // log exactly and moves what can still reach the top-k into `cb`
+    CandBuf lg[2] = {};
+    int log_nq_pad = 0;
+    uint32_t log_cap = 0;
     OperandStats* q_stats = nullptr;
     float *q_norm = nullptr, *q_err = nullptr, *margin = nullptr, *tau = nullptr, *thr = nullptr;
     float* q_shift = nullptr;     // q . centre per query (f16 path)
@@ -80,7 +84,12 @@ struct Workspace {
 
 struct hac_index {
     int d = 0, device = 0, sm_count = 148;
-    cudaStream_t stream = nullptr;
+    // stream: the handle's own stream (host API) and the stream every int8 scan runs on - highest priority, so that
+    // the persistent scan CTAs are placed before the side stream's worker CTAs.  side: lowest priority; rescore /
+    // refresh / final select of the pipelined int8 search, co-resident with the scan of the following chunk.
+    cudaStream_t stream = nullptr, side = nullptr;
+    cudaEvent_t wdone[kMaxChunks] = {};     // worker (rescore + refresh) of chunk i finished; no timing
+    cudaEvent_t ev_in = nullptr, ev_out = nullptr, ev_join = nullptr;
     std::vector<Segment> segs;
     int64_t ntotal = 0;
     int64_t id_base = 0;
@@ -113,16 +122,26 @@ struct hac_index {
     // core draws less with sparser mantissas: 3 dropped corpus bits (an 8-bit significand) run the scan 5 %
     // faster (76.3 -> 72.0 ms measured); the margin grows 0.76 -> 2.3 and 1.6x more rows are rescored (0.2 ms).
     int drop_bits_x = 3, drop_bits_q = 0;
-    // int8 path: rescore each chunk's emitted rows in row order.  Off: since the per-query rescore kernel hides its
-    // latencies (indices prefetched one iteration ahead, loads hoisted) it reads the random 3 KB rows at 6.7 TB/s
-    // (12 ms for 26.4M pairs), faster than bucketing them first (75.6 vs 61.6 ms per search).
-    bool i8_rescore_by_row = false;
     // keep an int8 image of the corpus too (rows*d bytes of HBM; HAC_PATH_I8).  On by default when d % 128 == 0: its
     // screen is the fastest path for k <= 128 at every batch size (50.3 vs 75.1 ms per search at 25.7M x 2514, k=100;
     // 3.0 vs 5.5 ms at one query); "build_i8" = 0 / HAC_BUILD_I8=0 saves the memory.
     bool build_i8 = true;
     bool i8_overflowed = false;             // the int8 screen overflowed on this corpus: AUTO stops choosing it (until reset)
-    double i8_chunk_growth = 0.0;           // int8 chunk schedule: chunk = growth * rows seen so far (0 = by batch size and k)
+    double i8_chunk_growth = 0.0;           // int8 chunk schedule, synchronous chunks: chunk = growth * rows seen so far (0 = by batch size and k)
+    // Pipelined int8 search (option "i8_pipeline").  After a short synchronous prelude (thresholds must exist before chunks can be
+    // large) the scans run back to back on `stream` while chunk i's rescore + refresh run on `side` beside the scan of
+    // chunk i+1: scan i only waits for the worker of chunk i - i8_pipe_dist.  A stale threshold is a valid lower
+    // bound, so nothing but the number of emitted rows depends on the overlap.
+    // int8 CTA-pair scan: ring slots (16 KiB) that keep the corpus tile resident across its query groups (0 = off: both
+    // operands streamed per unit).  8 leaves no room for a co-resident worker CTA; the pipelined search uses 7.
+    int i8_b_slots = 8;
+    bool i8_pipeline = false;               // measured on one GPU: 47.1 ms pipelined vs 46.2 ms synchronous (the scan is power-bound: co-running rescores slow it by what they save)
+    int i8_pipe_dist = 2;                   // 1 = every scan waits for the previous chunk's worker (no overlap)
+    double i8_pipe_growth = 0.125;          // pipelined chunks: max(i8_pipe_min_rows, growth * rows seen so far)
+    int64_t i8_pipe_min_rows = 0;           // 0 = by batch size (about 75 us of scan per chunk)
+    // the f16 image (rows*d*2 bytes) is only read by the f16 screen (k > i8_auto_max_k, int8 overflow fallback, forced
+    // HAC_PATH_MMA): with the int8 image present it is built on first use instead of on add (25.7M rows: 138 -> 99 GB)
+    int lazy_f16 = -1;                      // -1 = lazy exactly when the int8 image is built; 0 / 1 = forced
     int i8_auto_max_k = 128;                // HAC_PATH_AUTO takes the int8 screen up to this k (its shortlist grows with k * e^(m8*z/sigma))
     int default_path = HAC_PATH_MMA;        // what HAC_PATH_AUTO resolves to
     int i8_auto_max_queries = kMaxQueryBatch;          // HAC_PATH_AUTO takes the int8 screen up to this batch size when the image exists
@@ -161,11 +180,15 @@ void free_segment(Segment& s) {
     s = Segment{};
 }
 
+bool f16_is_lazy(const hac_index* idx) {
+    return idx->lazy_f16 < 0 ? (idx->build_i8 && idx->d % kBlockK8 == 0) : idx->lazy_f16 != 0;
+}
+
 int alloc_segment(hac_index* idx, int64_t cap_rows, Segment* out) {
     Segment s;
     s.cap_rows = round_up(std::max<int64_t>(cap_rows, kRowAlign), kRowAlign);
     cudaError_t e = cudaMalloc(&s.rows, (size_t)s.cap_rows * idx->d * sizeof(float));
-    if (e == cudaSuccess) e = cudaMalloc(&s.shadow, (size_t)shadow_bytes(s.cap_rows, idx->d));
+    if (e == cudaSuccess && !f16_is_lazy(idx)) e = cudaMalloc(&s.shadow, (size_t)shadow_bytes(s.cap_rows, idx->d));
     if (e == cudaSuccess) e = cudaMalloc(&s.stats, sizeof(OperandStats));
     if (e == cudaSuccess && idx->d % kBlockK8 == 0 && idx->build_i8) {
         e = cudaMalloc(&s.shadow8, (size_t)shadow8_bytes(s.cap_rows, idx->d));
@@ -175,7 +198,7 @@ int alloc_segment(hac_index* idx, int64_t cap_rows, Segment* out) {
         free_segment(s);
         return fail_cuda(e, "segment allocation");
     }
-    cudaMemsetAsync(s.shadow, 0, (size_t)shadow_bytes(s.cap_rows, idx->d), idx->stream);
+    if (s.shadow) cudaMemsetAsync(s.shadow, 0, (size_t)shadow_bytes(s.cap_rows, idx->d), idx->stream);
     cudaMemsetAsync(s.stats, 0, sizeof(OperandStats), idx->stream);
     *out = s;
     return HAC_OK;
@@ -198,6 +221,39 @@ int writable_segment(hac_index* idx, int64_t want_rows, Segment** out) {
     s.base = (uint32_t)idx->ntotal;
     idx->segs.push_back(s);
     *out = &idx->segs.back();
+    return HAC_OK;
+}
+
+// rows [seg->f16_rows, end) of the segment -> f16 image (+ the norms of the f16 screen margin); seg->shadow exists
+void convert_f16_rows(hac_index* idx, Segment* seg, int64_t end, cudaStream_t s) {
+    const int d = idx->d;
+    const int64_t r0 = seg->f16_rows, m = end - r0;
+    if (m <= 0) return;
+    const float* src = seg->rows + (size_t)r0 * d;
+    launch_absmax(src, m * d, idx->add_scratch, s);
+    launch_pick_scale(seg->stats, idx->add_scratch, /*keep_scale=*/r0 > 0 ? 1 : 0, s);
+    const int64_t n_pad = std::min(round_up(end, kRowAlign), seg->cap_rows) - r0;
+    launch_convert_rows(src, m, n_pad, d, seg->shadow, r0, seg->stats, nullptr, nullptr, idx->drop_bits_x,
+                        idx->center_valid ? idx->center : nullptr, s);
+    seg->f16_rows = end;
+}
+
+// the f16 screen is about to run: allocate / complete the f16 image of every segment (no-op when it is up to date)
+int ensure_f16_image(hac_index* idx, cudaStream_t s) {
+    bool touched = false;
+    for (auto& seg : idx->segs) {
+        if (seg.shadow != nullptr && seg.f16_rows == seg.n_rows) continue;
+        if (seg.shadow == nullptr) {
+            cudaError_t e = cudaMalloc(&seg.shadow, (size_t)shadow_bytes(seg.cap_rows, idx->d));
+            if (e != cudaSuccess) return fail_cuda(e, "f16 image allocation");
+            cudaMemsetAsync(seg.shadow, 0, (size_t)shadow_bytes(seg.cap_rows, idx->d), s);
+            seg.f16_rows = 0;
+        }
+        convert_f16_rows(idx, &seg, seg.n_rows, s);
+        merge_stats_kernel<<<1, 1, 0, s>>>(idx->corpus_stats, seg.stats);
+        touched = true;
+    }
+    if (touched) CU(cudaGetLastError());
     return HAC_OK;
 }
 
@@ -251,12 +307,11 @@ int add_rows(hac_index* idx, int64_t n, const float* src, RowSource kind, cudaSt
             idx->center_valid = true;
         }
         const float* center = idx->center_valid ? idx->center : nullptr;
-        launch_absmax(dst, m * d, idx->add_scratch, s);
-        launch_pick_scale(seg->stats, idx->add_scratch, /*keep_scale=*/seg->n_rows > 0 ? 1 : 0, s);
         const int64_t end = seg->n_rows + m;
-        const int64_t n_pad = std::min(round_up(end, kRowAlign), seg->cap_rows) - seg->n_rows;
-        launch_convert_rows(dst, m, n_pad, d, seg->shadow, seg->n_rows, seg->stats, nullptr, nullptr, idx->drop_bits_x,
-                            center, s);
+        if (seg->shadow != nullptr && seg->f16_rows == seg->n_rows) {
+            // the f16 image exists and is complete: keep it so (otherwise it is (re)built on first use, ensure_f16_image)
+            convert_f16_rows(idx, seg, end, s);
+        }
         if (seg->shadow8 != nullptr) {
             // whole tiles are rebuilt from the fp32 rows (an append into a partly filled tile changes its scale)
             launch_convert_tiles_i8(seg->rows, end, d, seg->n_rows / kTileRows,
@@ -285,8 +340,11 @@ void free_workspace(Workspace& w) {
                     w.cb.score, w.cb.row, w.cb.exact, w.cb.count, w.cb.sorted, w.cb.overflow, w.D, w.I, w.q_shift};
     for (void* p : ptrs)
         if (p) cudaFree(p);
-    if (w.pairs) cudaFree(w.pairs);
-    if (w.pair_hist) cudaFree(w.pair_hist);
+    for (auto& l : w.lg) {
+        if (l.score) cudaFree(l.score);
+        if (l.row) cudaFree(l.row);
+        if (l.count) cudaFree(l.count);
+    }
     if (w.host_pinned) cudaFreeHost(w.host_pinned);
     w = Workspace{};
 }
@@ -349,6 +407,28 @@ int ensure_workspace(hac_index* idx, int nq_pad, uint32_t cap, int64_t out_elems
     return HAC_OK;
 }
 
+// log shortlists of the int8 path: [2][nq_pad][log_cap] (screen score, row) + [2][nq_pad] counters
+int ensure_logs(hac_index* idx, int nq_pad, uint32_t log_cap) {
+    Workspace& w = idx->ws;
+    if (nq_pad <= w.log_nq_pad && log_cap <= w.log_cap) return HAC_OK;
+    const int np = std::max(nq_pad, w.log_nq_pad);
+    const uint32_t lc = std::max(log_cap, w.log_cap);
+    for (auto& l : w.lg) {
+        if (l.score) cudaFree(l.score);
+        if (l.row) cudaFree(l.row);
+        if (l.count) cudaFree(l.count);
+        l = CandBuf{};
+    }
+    w.log_nq_pad = 0; w.log_cap = 0;
+    for (auto& l : w.lg) {
+        CU(cudaMalloc(&l.score, (size_t)np * lc * sizeof(float)));
+        CU(cudaMalloc(&l.row, (size_t)np * lc * sizeof(uint32_t)));
+        CU(cudaMalloc(&l.count, (size_t)np * sizeof(uint32_t)));
+    }
+    w.log_nq_pad = np; w.log_cap = lc;
+    return HAC_OK;
+}
+
 struct HostReadback {
     uint32_t overflow;
     uint32_t pad;
@@ -358,145 +438,222 @@ struct HostReadback {
     float screen_err_max;
 };
 
-// int8 screen path.  Per chunk: int8 tensor-core scan with integer thresholds -> exact fp32 rescore of the
-// rows it emitted -> refresh on exact scores (tau = k-th best exact score so far, everything below dropped).
-// A row is emitted when its upper bound  a8 + m8(q, tile)  reaches tau, so only ONE margin separates the
-// screen from the exact threshold, and after the last chunk the shortlist IS the exact top-k.
-// Returns 1 when the shortlist overflowed (caller falls back to the f16 path), 0 on success, < 0 on error.
+// int8 screen path.  The corpus is cut in chunks; per chunk: int8 tensor-core scan with integer thresholds, its
+// survivors appended to a log shortlist -> exact fp32 rescore of the log, survivors of THAT (exact score >= the k-th
+// best exact score so far) moved to the main shortlist -> refresh (tau = k-th best exact score, everything below
+// dropped, emission threshold raised).  A row is emitted when its upper bound  a8 + m8(q, tile)  reaches tau, so only
+// ONE margin separates the screen from the exact threshold, and after the last chunk the shortlist IS the exact top-k.
+//
+// Schedule.  Thresholds must exist before a chunk may be large, so the first chunks (the prelude) are small and
+// synchronous: scan i waits for the worker (rescore + refresh) of chunk i-1.  Once `min_rows` rows have been seen the
+// search is pipelined: the scans run back to back on the handle's high-priority stream, the worker of chunk i runs on
+// the low-priority side stream beside the scan of chunk i+1, and scan i only waits for the worker of chunk i-2 (which
+// also frees the log buffer it writes, lg[i & 1]).  A stale threshold is a valid lower bound on the final one - the
+// overlap changes how many rows are emitted, never the result.
+struct ChunkPlan {
+    int seg;
+    int64_t r0, r1;
+    int dist;          // the scan waits for the worker of chunk (index - dist)
+};
+
+void plan_chunks_i8(const hac_index* idx, int nq, int nq_pad, int k, uint32_t log_cap, std::vector<ChunkPlan>& out,
+                    int* n_sync) {
+    const bool few = nq <= 4 && k <= 128;
+    const int n_qtiles = nq_pad / kTileRows;
+    const int cg = (idx->i8_cta_group == 2 && n_qtiles % 2 == 0) ? 2 : 1;
+    // one "round" of the tile-major scan: every CTA group takes one 256-row tile
+    const int64_t quantum = kRowAlign * std::max(1, idx->sm_count / cg);
+    // synchronous chunks: the first is emitted unfiltered and must fit the log; later ones grow with the rows seen so
+    // far - a chunk is expected to emit about growth * k * exp(m8 * z / sigma) rows per query
+    const int64_t first = few ? log_cap / 2
+                              : std::min<int64_t>(log_cap / 2, std::max<int64_t>(512, round_up(2 * (int64_t)k, kRowAlign)));
+    double sync_growth, pipe_growth = idx->i8_pipe_growth;
+    int64_t min_rows;
+    const bool pipeline = idx->i8_pipeline && idx->i8_pipe_dist >= 2;
+    if (pipeline) {
+        sync_growth = idx->i8_chunk_growth > 0.0 ? idx->i8_chunk_growth : (few ? 4.0 : (k <= 128 ? 2.0 : 1.0));
+        // about 75 us of scan per pipelined chunk: 4 rounds at 2560 queries (a unit of 256 queries x 256 rows takes
+        // ~2 us), more rows for smaller batches, whose scan is bound by HBM (~9M rows per ms)
+        min_rows = idx->i8_pipe_min_rows > 0 ? idx->i8_pipe_min_rows
+                                             : std::min<int64_t>(1 << 20, std::max<int64_t>(75776, 75776ll * 2560 / nq_pad));
+        min_rows = round_up(min_rows, quantum);
+    } else {
+        // no overlap: every chunk boundary costs a full scan ramp-down + rescore + refresh, and fresher thresholds
+        // emit fewer rows (measured at 25.7M x 2514, k=100: growth 2.0 -> 26.4M pairs, 53.5 ms; 1.0 -> 21.9M, 48.8 ms;
+        // 0.6 -> 19.9M, 47.2 ms; 0.35 -> 18.5M, 46.9 ms); small batches keep few chunks (each costs ~40 us)
+        sync_growth = idx->i8_chunk_growth > 0.0 ? idx->i8_chunk_growth
+                      : few ? 4.0
+                      : (nq >= 512 && k <= 128 && idx->ntotal >= (8ll << 20)) ? 0.6
+                      : (nq >= 512 && k <= 128 && idx->ntotal >= (1ll << 20)) ? 1.0
+                      : (k <= 128 ? 2.0 : 1.0);
+        min_rows = INT64_MAX;
+    }
+    for (int attempt = 0; attempt < 8; ++attempt) {
+        out.clear();
+        *n_sync = 0;
+        int64_t rows_done = 0;
+        for (size_t si = 0; si < idx->segs.size(); ++si) {
+            const Segment& seg = idx->segs[si];
+            int64_t r = 0;
+            while (r < seg.n_rows) {
+                const bool piped = pipeline && rows_done >= min_rows;
+                int64_t size;
+                if (piped) {
+                    size = std::max<int64_t>(min_rows, (int64_t)(pipe_growth * (double)rows_done));
+                    size = size / quantum * quantum;
+                    if (seg.n_rows - (r + size) < min_rows / 2) size = seg.n_rows - r;     // no runt at the segment end
+                } else {
+                    size = rows_done == 0 ? first : (int64_t)(sync_growth * (double)rows_done);
+                    if (pipeline) size = std::min(size, min_rows);
+                    size = std::max<int64_t>(kRowAlign, size / kRowAlign * kRowAlign);
+                }
+                const int64_t r1 = std::min(seg.n_rows, r + size);
+                out.push_back(ChunkPlan{(int)si, r, r1, piped ? idx->i8_pipe_dist : 1});
+                if (!piped) ++*n_sync;
+                rows_done += r1 - r;
+                r = r1;
+            }
+        }
+        if ((int)out.size() <= kMaxChunks) return;
+        pipe_growth *= 1.5;                  // too many chunks for the event pool: coarser schedule
+        sync_growth *= 1.5;
+    }
+}
+
+// Returns 1 when a shortlist overflowed (caller falls back to the f16 path), 0 on success, < 0 on error.
 int search_batch_i8(hac_index* idx, int nq, int nq_pad, const float* q_dev, int k, float* D_dev, int64_t* I_dev,
                     cudaStream_t s, const SegTable& segs) {
     const int d = idx->d;
     hac_stats& st = idx->stats;
-    // a handful of queries: rescoring is cheap and every chunk costs ~40 us of launch / refresh latency, so the
-    // shortlist is doubled and the chunks grow twice as fast (7 instead of 11 chunks over 25.7M rows)
+    // a handful of queries: rescoring is cheap and every synchronous chunk costs ~40 us of launch / refresh latency,
+    // so the log is doubled and the prelude grows twice as fast
     const bool few = nq <= 4 && k <= 128;
-    const uint32_t cap = few ? 2 * cap_for_k(k, 0) : cap_for_k(k, 0);
+    const uint32_t cap = cap_for_k(k, 0);
+    const uint32_t log_cap = few ? 2 * cap : cap;
     int rc = ensure_workspace(idx, nq_pad, cap, 0);
+    if (rc == HAC_OK) rc = ensure_logs(idx, nq_pad, log_cap);
     if (rc != HAC_OK) return rc;
     Workspace& w = idx->ws;
     CandBuf cb = w.cb;
     cb.cap = cap;
-    HostReadback* hr = static_cast<HostReadback*>(w.host_pinned);
-    int launches = 0, n_chunks = 0, n_ev = 2;
-    {   // scratch of the row-ordered rescore
-        const int64_t need_pairs = (int64_t)nq_pad * cap;
-        int64_t max_rows = 0;
-        for (const auto& sg : idx->segs) max_rows = std::max(max_rows, sg.n_rows);
-        const int64_t need_buckets = (max_rows >> 11) + 2;
-        if (need_pairs > w.pairs_cap) {
-            if (w.pairs) cudaFree(w.pairs);
-            w.pairs = nullptr; w.pairs_cap = 0;
-            CU(cudaMalloc(&w.pairs, need_pairs * sizeof(uint2)));
-            w.pairs_cap = need_pairs;
-        }
-        if (need_buckets > w.pair_buckets) {
-            if (w.pair_hist) cudaFree(w.pair_hist);
-            w.pair_hist = nullptr; w.pair_buckets = 0;
-            CU(cudaMalloc(&w.pair_hist, (2 * need_buckets + 1) * sizeof(uint32_t)));
-            w.pair_buckets = need_buckets;
-        }
+    CandBuf lg[2];
+    for (int i = 0; i < 2; ++i) {
+        lg[i] = w.lg[i];
+        lg[i].cap = log_cap;
+        lg[i].exact = nullptr;
+        lg[i].sorted = nullptr;
+        lg[i].overflow = cb.overflow;
+        lg[i].emitted = cb.emitted;
     }
+    HostReadback* hr = static_cast<HostReadback*>(w.host_pinned);
+    std::vector<ChunkPlan> plan;
+    int n_sync = 0;
+    plan_chunks_i8(idx, nq, nq_pad, k, log_cap, plan, &n_sync);
+    if ((int)plan.size() > kMaxChunks) return fail(HAC_E_STATE, "int8 search: chunk plan exceeds the event pool");
     const float* center = idx->center_valid ? idx->center : nullptr;
     // threshold exchange with the other shards: on when the caller armed an epoch for this search
     ThrExchange ex = idx->exchange;
     const bool use_ex = ex.n_peers > 0 && idx->exchange_epoch > 0 && nq <= idx->exchange_capacity && idx->cur_batch < 16;
     ex.tag = (uint32_t)(((uint64_t)idx->exchange_epoch << 4) | (uint64_t)idx->cur_batch);
-    cudaEventRecord(idx->ev[0], s);
-    launch_init_search(cb, w.tau, w.thr, nq, nq_pad, s);
-    launch_convert_queries_i8(q_dev, nq, nq_pad, d, w.q_shadow8, w.q_consts, s);
+    // A: scans (and everything before the first one); B: workers and the final select.  The caller's stream is
+    // ordered before A at the start and after A at the end.
+    cudaStream_t A = idx->stream, B = idx->side;
+    if (s != A) {
+        CU(cudaEventRecord(idx->ev_in, s));
+        CU(cudaStreamWaitEvent(A, idx->ev_in, 0));
+    }
+    int launches = 0;
+    cudaEventRecord(idx->ev[0], A);
+    launch_init_search(cb, w.tau, w.thr, nq, nq_pad, A);
+    cudaMemsetAsync(lg[0].count, 0, (size_t)nq_pad * sizeof(uint32_t), A);
+    cudaMemsetAsync(lg[1].count, 0, (size_t)nq_pad * sizeof(uint32_t), A);
+    launch_convert_queries_i8(q_dev, nq, nq_pad, d, w.q_shadow8, w.q_consts, A);
     if (center != nullptr) {
-        launch_query_shift(q_dev, nq, nq_pad, d, center, w.q_shift, s);
+        launch_query_shift(q_dev, nq, nq_pad, d, center, w.q_shift, A);
         ++launches;
     }
-    launch_margins(nullptr, nullptr, nullptr, nullptr, d, w.margin, w.scalars + 1, nq, s);   // refresh margin = 0 (exact scores)
-    launch_margins_i8(w.q_consts, idx->corpus_stats, d, w.q_norm /*scratch*/, w.scalars + 1, nq, s);   // statistics
-    cudaMemsetAsync(w.scalars + 2, 0, sizeof(float), s);
-    cudaMemsetAsync(w.counters + 1, 0, sizeof(unsigned long long), s);
+    launch_margins(nullptr, nullptr, nullptr, nullptr, d, w.margin, w.scalars + 1, nq, A);   // refresh margin = 0 (exact scores)
+    launch_margins_i8(w.q_consts, idx->corpus_stats, d, w.q_norm /*scratch*/, w.scalars + 1, nq, A);   // statistics
+    cudaMemsetAsync(w.scalars + 2, 0, sizeof(float), A);
+    cudaMemsetAsync(w.counters + 1, 0, sizeof(unsigned long long), A);
     launches += 4;
-    // the first chunk is emitted unfiltered and rescored exactly, so it is kept small; later chunks grow with the
-    // rows seen so far: a chunk is expected to emit about growth * k * exp(m8 * z / sigma) rows per query
-    // large batches: rescoring the emitted pairs is a fifth of the search, and fresher thresholds emit fewer of them
-    // (measured at 25.7M x 2514, k=100: growth 2.0 -> 26.4M pairs, 53.5 ms; 1.0 -> 21.9M, 48.8 ms; 0.6 -> 19.9M,
-    // 47.2 ms; 0.35 -> 18.5M, 46.9 ms); smaller batches keep few chunks (each costs ~40 us of latency)
-    // and small shards (8-GPU slices) gain less from pruning than the extra chunks cost
-    const double growth = idx->i8_chunk_growth > 0.0 ? idx->i8_chunk_growth
-                          : few ? 4.0
-                          : (nq >= 512 && k <= 128 && idx->ntotal >= (8ll << 20)) ? 0.6
-                          : (nq >= 512 && k <= 128 && idx->ntotal >= (1ll << 20)) ? 1.0
-                          : (k <= 128 ? 2.0 : 1.0);
-    const int64_t first = few ? cap / 2 : std::min<int64_t>(cap / 2, std::max<int64_t>(512, round_up(2 * (int64_t)k, kRowAlign)));
-    int64_t rows_done = 0;
-    for (size_t si = 0; si < idx->segs.size(); ++si) {
-        const Segment& seg = idx->segs[si];
-        int64_t r = 0;
-        while (r < seg.n_rows) {
-            int64_t size = rows_done == 0 ? first : (int64_t)(growth * (double)rows_done);
-            size = std::max<int64_t>(kRowAlign, size / kRowAlign * kRowAlign);
-            const int64_t r1 = std::min(seg.n_rows, r + size);
-            const bool timed = n_ev + 2 <= kMaxEvents;
-            if (timed) cudaEventRecord(idx->ev[n_ev], s);
-            MmaScanArgs a;
-            a.q_shadow = w.q_shadow8;
-            a.x_shadow = seg.shadow8;
-            a.q_stats = nullptr;
-            a.x_stats = nullptr;
-            a.q_shift = center != nullptr ? w.q_shift : nullptr;
-            a.center_norm = center != nullptr ? center + d : nullptr;
-            a.x_tiles = seg.tiles8;
-            a.q_consts = w.q_consts;
-            a.thr = w.thr;
-            a.d = d;
-            a.tile_major = idx->scan_tile_major < 0 ? 1 : idx->scan_tile_major;
-            a.n_qtiles = nq_pad / kTileRows;
-            a.ct0 = r / kRowAlign;
-            a.ct1 = (r1 + kRowAlign - 1) / kRowAlign;
-            a.seg_rows = std::min(seg.n_rows, r1);
-            a.row_id_base = seg.base;
-            a.cb = cb;
-            CU(launch_scan_mma_i8(a, idx->sm_count, idx->i8_cta_group, s));
-            if (timed) {
-                cudaEventRecord(idx->ev[n_ev + 1], s);
-                n_ev += 2;
-            }
-            // row-ordered rescoring pays off when a chunk emits millions of pairs; small batches go straight to the
-            // per-query kernel (its CTAs split each shortlist), three launches less per chunk
-            bool by_row = idx->i8_rescore_by_row && r1 - r >= 65536 && nq >= 256;
-            if (by_row)
-                by_row = launch_rescore_new_by_row(cb, q_dev, d, segs, nq, seg.base + (uint32_t)r, seg.base + (uint32_t)r1,
-                                                   w.pair_hist, w.pair_hist + w.pair_buckets,
-                                                   w.pair_hist + 2 * w.pair_buckets, w.pairs, idx->sm_count,
-                                                   w.scalars + 2, w.counters + 1, s);
-            if (!by_row) launch_rescore_new(cb, q_dev, d, segs, nq, w.scalars + 2, w.counters + 1, s);
-            launch_refresh(cb, k, w.margin, w.tau, w.thr, nq, s, use_ex ? &ex : nullptr);
-            launches += by_row ? 6 : 3;
-            ++n_chunks;
-            rows_done += r1 - r;
-            r = r1;
+    const int n_chunks = (int)plan.size();
+    int waited = -1;                       // A has already been ordered after the workers of chunks <= waited
+    for (int i = 0; i < n_chunks; ++i) {
+        const ChunkPlan& ch = plan[i];
+        const Segment& seg = idx->segs[ch.seg];
+        const int dep = i - ch.dist;
+        if (dep > waited) {
+            CU(cudaStreamWaitEvent(A, idx->wdone[dep], 0));
+            waited = dep;
         }
+        cudaEvent_t ev_start = idx->ev[2 + 2 * i], ev_stop = idx->ev[3 + 2 * i];
+        cudaEventRecord(ev_start, A);
+        MmaScanArgs a;
+        a.q_shadow = w.q_shadow8;
+        a.x_shadow = seg.shadow8;
+        a.q_stats = nullptr;
+        a.x_stats = nullptr;
+        a.q_shift = center != nullptr ? w.q_shift : nullptr;
+        a.center_norm = center != nullptr ? center + d : nullptr;
+        a.x_tiles = seg.tiles8;
+        a.q_consts = w.q_consts;
+        a.thr = w.thr;
+        a.d = d;
+        a.tile_major = idx->scan_tile_major < 0 ? 1 : idx->scan_tile_major;
+        // resident corpus tile (ring of b_slots 16 KiB slots); the pipelined schedule keeps 34 KB of shared memory
+        // free for the co-resident worker CTAs (rescore 3 KB, refresh 17 KB), i.e. at most 6 slots
+        const int want_b = (n_sync < n_chunks) ? std::min(idx->i8_b_slots, 6) : idx->i8_b_slots;
+        a.b_slots = (a.tile_major && d / kBlockK8 <= want_b) ? want_b : 0;
+        a.n_qtiles = nq_pad / kTileRows;
+        a.ct0 = ch.r0 / kRowAlign;
+        a.ct1 = (ch.r1 + kRowAlign - 1) / kRowAlign;
+        a.seg_rows = std::min(seg.n_rows, ch.r1);
+        a.row_id_base = seg.base;
+        a.cb = lg[i & 1];
+        CU(launch_scan_mma_i8(a, idx->sm_count, idx->i8_cta_group, A));
+        CU(cudaEventRecord(ev_stop, A));
+        // worker of the chunk, on the side stream
+        CU(cudaStreamWaitEvent(B, ev_stop, 0));
+        if (!launch_rescore_log(lg[i & 1], cb, q_dev, d, segs, nq, w.tau, w.scalars + 2, w.counters + 1, B))
+            return fail(HAC_E_INVALID, "int8 search: unsupported dimension");
+        launch_refresh(cb, k, w.margin, w.tau, w.thr, nq, B, use_ex ? &ex : nullptr, lg[i & 1].count, /*small_cta=*/true);
+        CU(cudaEventRecord(idx->wdone[i], B));
+        launches += 3;
     }
-    launch_final_select(cb, k, nq, idx->id_table, idx->id_base, D_dev, I_dev, /*use_score=*/true, s);
+    launch_final_select(cb, k, nq, idx->id_table, idx->id_base, D_dev, I_dev, /*use_score=*/true, B);
     ++launches;
-    cudaEventRecord(idx->ev[1], s);
+    CU(cudaEventRecord(idx->ev_join, B));
+    CU(cudaStreamWaitEvent(A, idx->ev_join, 0));
+    cudaEventRecord(idx->ev[1], A);
     CU(cudaGetLastError());
-    CU(cudaMemcpyAsync(&hr->overflow, cb.overflow, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
-    CU(cudaMemcpyAsync(&hr->emitted, w.counters, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
-    CU(cudaMemcpyAsync(&hr->margin_max, w.scalars + 1, 2 * sizeof(float), cudaMemcpyDeviceToHost, s));
-    CU(cudaStreamSynchronize(s));
+    CU(cudaMemcpyAsync(&hr->overflow, cb.overflow, sizeof(uint32_t), cudaMemcpyDeviceToHost, A));
+    CU(cudaMemcpyAsync(&hr->emitted, w.counters, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, A));
+    CU(cudaMemcpyAsync(&hr->margin_max, w.scalars + 1, 2 * sizeof(float), cudaMemcpyDeviceToHost, A));
+    if (s != A) {
+        CU(cudaEventRecord(idx->ev_out, A));
+        CU(cudaStreamWaitEvent(s, idx->ev_out, 0));
+    }
+    CU(cudaStreamSynchronize(A));
     st.n_chunks = n_chunks;
+    st.n_sync_chunks = n_sync;
+    st.pipelined = n_sync < n_chunks ? 1 : 0;
     st.kernel_launches = launches;
     st.candidates_emitted = (int64_t)hr->emitted;
     st.candidates_rescored = (int64_t)hr->rescored;
     st.margin_max = hr->margin_max;
     st.screen_err_max = hr->screen_err_max;
-    float ms = 0.f, scan_ms = 0.f;
+    float ms = 0.f, scan_ms = 0.f, tail_ms = 0.f;
     cudaEventElapsedTime(&ms, idx->ev[0], idx->ev[1]);
-    for (int i = 2; i + 1 < n_ev; i += 2) {
+    for (int i = 0; i < n_chunks; ++i) {
         float t = 0.f;
-        cudaEventElapsedTime(&t, idx->ev[i], idx->ev[i + 1]);
+        cudaEventElapsedTime(&t, idx->ev[2 + 2 * i], idx->ev[3 + 2 * i]);
         scan_ms += t;
     }
+    if (n_chunks > 0) cudaEventElapsedTime(&tail_ms, idx->ev[3 + 2 * (n_chunks - 1)], idx->ev[1]);
     st.total_ms = ms;
     st.scan_ms = scan_ms;
+    st.tail_ms = tail_ms;
     return hr->overflow ? 1 : 0;
 }
 
@@ -522,6 +679,10 @@ int search_batch(hac_index* idx, int nq, const float* q_dev, int k, float* D_dev
     if (path == HAC_PATH_GEMV && nq > 4) return fail(HAC_E_INVALID, "GEMV path takes at most 4 queries per batch");
     if (!idx->events_ready) {
         for (auto& e : idx->ev) CU(cudaEventCreate(&e));
+        for (auto& e : idx->wdone) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&idx->ev_in, cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&idx->ev_out, cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&idx->ev_join, cudaEventDisableTiming));
         idx->events_ready = true;
     }
     if ((path == HAC_PATH_MMA || path == HAC_PATH_I8) && !idx->mma_configured) {
@@ -531,6 +692,9 @@ int search_batch(hac_index* idx, int nq, const float* q_dev, int k, float* D_dev
     hac_stats& st = idx->stats;
     st.path = path;
     st.retries = 0;
+    st.n_sync_chunks = 0;
+    st.pipelined = 0;
+    st.tail_ms = 0.f;
 
     SegTable segs;
     segs.n = (int)idx->segs.size();
@@ -545,6 +709,10 @@ int search_batch(hac_index* idx, int nq, const float* q_dev, int k, float* D_dev
         path = HAC_PATH_MMA;            // shortlist overflow: redo with the f16 screen (and its careful mode)
         st.path = path;
         st.retries = 1;
+    }
+    if (path == HAC_PATH_MMA) {
+        const int rcf = ensure_f16_image(idx, s);        // lazy f16 image: built on the first search that needs it
+        if (rcf != HAC_OK) return rcf;
     }
     const int retries_before = st.retries;
     // level 0: fast mode - the whole search is enqueued without a host round trip; the overflow flag is
@@ -685,6 +853,7 @@ int search_batch(hac_index* idx, int nq, const float* q_dev, int k, float* D_dev
         CU(cudaMemcpyAsync(&hr->margin_max, w.scalars + 1, 2 * sizeof(float), cudaMemcpyDeviceToHost, s));
         CU(cudaStreamSynchronize(s));
         st.n_chunks = n_chunks;
+        st.n_sync_chunks = n_chunks;
         st.kernel_launches = launches;
         st.candidates_emitted = (int64_t)hr->emitted;
         st.candidates_rescored = (int64_t)hr->rescored;
@@ -725,7 +894,9 @@ int search_common(hac_index* idx, int64_t nq, const float* q, bool q_on_host, in
     // the producer of q and the consumer of D / I - and with the caller's caching allocator.
     cudaStream_t s = (q_on_host && out_on_host) ? idx->stream : user_stream;
     idx->stats.ntotal = idx->ntotal;
-    const int64_t max_batch = (path == HAC_PATH_GEMV) ? 4 : kMaxQueryBatch;
+    // batches are sized by the path AUTO will resolve to: a "default_path" of GEMV takes 4 queries at a time
+    const bool auto_gemv = path == HAC_PATH_AUTO && idx->default_path == HAC_PATH_GEMV;
+    const int64_t max_batch = (path == HAC_PATH_GEMV || auto_gemv) ? 4 : kMaxQueryBatch;
     if (idx->ntotal == 0) {
         // faiss: empty index -> every slot unfilled
         if (out_on_host) {
@@ -736,7 +907,7 @@ int search_common(hac_index* idx, int64_t nq, const float* q, bool q_on_host, in
         }
         return HAC_OK;
     }
-    float total_ms = 0.f, scan_ms = 0.f;
+    float total_ms = 0.f, scan_ms = 0.f, tail_ms = 0.f;
     int64_t emitted = 0, rescored = 0;
     int launches = 0, retries = 0;
     float margin_max = 0.f, err_max = 0.f;
@@ -765,7 +936,9 @@ int search_common(hac_index* idx, int64_t nq, const float* q, bool q_on_host, in
         launches += idx->stats.kernel_launches; retries += idx->stats.retries;
         margin_max = std::max(margin_max, idx->stats.margin_max);
         err_max = std::max(err_max, idx->stats.screen_err_max);
+        tail_ms += idx->stats.tail_ms;
     }
+    idx->stats.tail_ms = tail_ms;
     idx->stats.total_ms = total_ms; idx->stats.scan_ms = scan_ms;
     idx->stats.candidates_emitted = emitted; idx->stats.candidates_rescored = rescored;
     idx->stats.kernel_launches = launches; idx->stats.retries = retries;
@@ -800,7 +973,12 @@ int hac_create(int d, int device, hac_index** out) {
     // opt-in to the int8 image without touching the caller's code (the reference builds its index through faiss names)
     if (const char* b8 = getenv("HAC_BUILD_I8")) idx->build_i8 = atoi(b8) != 0;
     if (d % kBlockK8 != 0) idx->build_i8 = false;
-    cudaError_t e = cudaStreamCreateWithFlags(&idx->stream, cudaStreamNonBlocking);
+    int prio_least = 0, prio_greatest = 0;
+    cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest);
+    cudaError_t e = cudaStreamCreateWithPriority(&idx->stream, cudaStreamNonBlocking, prio_greatest);
+    if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&idx->side, cudaStreamNonBlocking, prio_least);
+    if (const char* v = getenv("HAC_LAZY_F16")) idx->lazy_f16 = atoi(v) != 0;
+    if (const char* v = getenv("HAC_I8_PIPELINE")) idx->i8_pipeline = atoi(v) != 0;
     if (e == cudaSuccess) e = cudaMalloc(&idx->corpus_stats, sizeof(OperandStats));
     if (e == cudaSuccess) e = cudaMalloc(&idx->add_scratch, 4 * sizeof(float));
     if (e == cudaSuccess) e = cudaMalloc(&idx->center, (size_t)(d + 1) * sizeof(float));
@@ -825,9 +1003,15 @@ int hac_destroy(hac_index* idx) {
     if (idx->add_scratch) cudaFree(idx->add_scratch);
     if (idx->center) cudaFree(idx->center);
     if (idx->center_accum) cudaFree(idx->center_accum);
-    if (idx->events_ready)
+    if (idx->events_ready) {
         for (auto& e : idx->ev) cudaEventDestroy(e);
+        for (auto& e : idx->wdone) cudaEventDestroy(e);
+        cudaEventDestroy(idx->ev_in);
+        cudaEventDestroy(idx->ev_out);
+        cudaEventDestroy(idx->ev_join);
+    }
     if (idx->stream) cudaStreamDestroy(idx->stream);
+    if (idx->side) cudaStreamDestroy(idx->side);
     delete idx;
     return HAC_OK;
 }
@@ -895,6 +1079,7 @@ int hac_reset(hac_index* idx) {
     }
     for (auto& s : idx->segs) {
         s.n_rows = 0;
+        s.f16_rows = 0;
         s.base = 0;
         s.closed = false;
         CU(cudaMemsetAsync(s.stats, 0, sizeof(OperandStats), idx->stream));
@@ -1068,7 +1253,32 @@ int hac_set_option(hac_index* idx, const char* name, int64_t value) {
         idx->center_valid = false;
         return HAC_OK;
     }
-    if (strcmp(name, "i8_rescore_by_row") == 0) { idx->i8_rescore_by_row = value != 0; return HAC_OK; }
+    if (strcmp(name, "i8_pipeline") == 0) { idx->i8_pipeline = value != 0; return HAC_OK; }
+    if (strcmp(name, "i8_b_slots") == 0) {
+        if (value != 0 && (value < 6 || value > 8)) return fail(HAC_E_INVALID, "i8_b_slots must be 0 or in [6, 8]");
+        idx->i8_b_slots = (int)value;
+        return HAC_OK;
+    }
+    if (strcmp(name, "i8_pipe_dist") == 0) {
+        if (value != 1 && value != 2) return fail(HAC_E_INVALID, "i8_pipe_dist must be 1 or 2");
+        idx->i8_pipe_dist = (int)value;
+        return HAC_OK;
+    }
+    if (strcmp(name, "i8_pipe_growth_x1000") == 0) {
+        if (value < 10 || value > 4000) return fail(HAC_E_INVALID, "i8_pipe_growth_x1000 must be in [10, 4000]");
+        idx->i8_pipe_growth = (double)value / 1000.0;
+        return HAC_OK;
+    }
+    if (strcmp(name, "i8_pipe_min_rows") == 0) {
+        if (value != 0 && (value < 4096 || value > (1ll << 26))) return fail(HAC_E_INVALID, "i8_pipe_min_rows must be 0 or in [4096, 2^26]");
+        idx->i8_pipe_min_rows = value;
+        return HAC_OK;
+    }
+    if (strcmp(name, "lazy_f16") == 0) {
+        if (idx->ntotal != 0 || !idx->segs.empty()) return fail(HAC_E_STATE, "lazy_f16 must be set on an empty index");
+        idx->lazy_f16 = value < 0 ? -1 : (value != 0);
+        return HAC_OK;
+    }
     if (strcmp(name, "exchange_epoch") == 0) {
         if (value < 0 || value > 0x0FFFFFFF) return fail(HAC_E_INVALID, "exchange_epoch out of range");
         idx->exchange_epoch = value;
@@ -1109,13 +1319,15 @@ int hac_get_stats(const hac_index* idx, hac_stats* out) {
     if (idx == nullptr || out == nullptr) return fail(HAC_E_INVALID, "get_stats: null argument");
     *out = idx->stats;
     out->ntotal = idx->ntotal;
-    int64_t b32 = 0, bsh = 0;
+    int64_t b32 = 0, bsh = 0, b8 = 0;
     for (const auto& s : idx->segs) {
         b32 += s.cap_rows * (int64_t)idx->d * 4;
-        bsh += shadow_bytes(s.cap_rows, idx->d) + (s.shadow8 ? shadow8_bytes(s.cap_rows, idx->d) : 0);
+        if (s.shadow) bsh += shadow_bytes(s.cap_rows, idx->d);
+        if (s.shadow8) b8 += shadow8_bytes(s.cap_rows, idx->d) + shadow_tiles(s.cap_rows) * (int64_t)sizeof(TileQ8);
     }
     out->bytes_fp32 = b32;
     out->bytes_shadow = bsh;
+    out->bytes_i8 = b8;
     return HAC_OK;
 }
 

@@ -95,8 +95,10 @@ void launch_margins(const float* q_norm, const float* q_err, const OperandStats*
                     int d, float* margin, float* margin_max, int nq, cudaStream_t s);
 // per query: sort the shortlist, raise tau to the k-th best screen score, drop entries below tau - 2m
 // ex: optional threshold exchange (exact-score shortlists only, i.e. the int8 path); nullptr = none
+// clear_count: optional [nq] counters zeroed by the kernel (the log shortlist the preceding rescore consumed)
+// small_cta: 256 threads per query whatever the batch size (co-resident with a running scan kernel)
 void launch_refresh(CandBuf cb, int k, const float* margin, float* tau, float* thr, int nq, cudaStream_t s,
-                    const ThrExchange* ex = nullptr);
+                    const ThrExchange* ex = nullptr, uint32_t* clear_count = nullptr, bool small_cta = false);
 // exact fp32 scores of every shortlisted pair
 void launch_rescore(CandBuf cb, const float* q, int d, SegTable segs, int nq, float* screen_err_max,
                     unsigned long long* rescored, cudaStream_t s);
@@ -104,11 +106,12 @@ void launch_rescore(CandBuf cb, const float* q, int d, SegTable segs, int nq, fl
 // replaced by the exact one, so the refresh that follows works on exact scores (int8 path)
 void launch_rescore_new(CandBuf cb, const float* q, int d, SegTable segs, int nq, float* screen_err_max,
                         unsigned long long* rescored, cudaStream_t s);
-// same, but the (query, row) pairs are first bucketed by row and rescored in row order (page locality, one HBM
-// fetch per distinct row); scratch: hist/cursor [buckets of 2048 rows + 1], total [1], pairs [max pairs]
-bool launch_rescore_new_by_row(CandBuf cb, const float* q, int d, SegTable segs, int nq, uint32_t row_lo,
-                               uint32_t row_hi, uint32_t* hist, uint32_t* cursor, uint32_t* total, uint2* pairs,
-                               int sm_count, float* screen_err_max, unsigned long long* rescored, cudaStream_t s);
+// pipelined int8 search: the scan of chunk i appends its survivors to a LOG shortlist `lg`; this kernel rescores every
+// log entry exactly and appends those that can still reach the top-k (exact score >= tau[q], the k-th best exact score
+// so far) to the main shortlist `cb`.  Small register / shared-memory footprint so that its CTAs are co-resident with
+// the persistent scan kernel of the NEXT chunk (side stream).  d must be a multiple of 128.
+bool launch_rescore_log(CandBuf lg, CandBuf cb, const float* q, int d, SegTable segs, int nq, const float* tau,
+                        float* screen_err_max, unsigned long long* rescored, cudaStream_t s);
 // final top-k by (exact score desc, id asc) with id translation
 // use_score: the `score` array already holds exact scores (int8 path) - rank by it instead of `exact`
 void launch_final_select(CandBuf cb, int k, int nq, const int64_t* id_table, int64_t id_base, float* D,
@@ -136,6 +139,7 @@ struct MmaScanArgs {
     int d;
     int n_qtiles;
     int tile_major;         // 1: every CTA walks whole corpus tiles (all query tiles back to back); 0: units striped
+    int b_slots = 0;        // int8 CTA pairs: > 0 = keep the corpus tile resident in a ring of this many 16 KiB slots (7-8)
     int64_t ct0, ct1;       // 256-row tiles of the segment
     int64_t seg_rows;       // valid rows of the segment
     uint32_t row_id_base;

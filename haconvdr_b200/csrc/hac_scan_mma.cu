@@ -16,6 +16,12 @@
 //            the MMAs; the peer forwards "my half has landed" to the leader through a remote
 //            mbarrier arrive; tcgen05.commit multicasts slot-free / accumulator-ready to both CTAs.
 //   Defaults: int8 -> kCG = 2 (single-tile batches run kCG = 1), f16 -> kCG = 1 (power-bound either way).
+//   kBRes (int8 CTA pairs only): the corpus tile stays RESIDENT in shared memory while the pair walks all query groups
+//            of that tile (the tile-major order runs them back to back).  Shared memory is cut into 14 slots of
+//            16 KiB: a ring of 6 for the query K blocks (streamed, one unit deep) and a ring of 7-8 for the corpus K
+//            blocks - 6 in use, the spare ones take the next tile's first blocks, the others are refilled as the last
+//            query group's MMAs retire.  Operand bytes moved from L2 into shared memory per unit drop from 2 x 192 KiB
+//            to 192 + 19 KiB at 10 query groups; the scan is power-bound and that traffic is its largest overhead.
 // Warp roles (320 threads, persistent): warp 0 = copy producer, warp 1 = MMA issuer (leader) or
 // forwarder (peer) and owner of the TMEM allocation, warps 2..9 = epilogue (TMEM lane quarter =
 // warp % 4, one query per thread; warps 2..5 drain columns 0..127 of a tile, warps 6..9 columns 128..255).
@@ -36,7 +42,9 @@ constexpr int kTileM = 128;                                // queries per CTA ti
 constexpr int kTileN = 256;                                // corpus rows per tile (TMEM columns)
 constexpr int kThreads = 320;                              // producer warp, MMA warp, 8 epilogue warps
 constexpr int kStash = 8;                                  // per-thread survivors kept until the TMEM buffer is released
-constexpr int kMaxStages = 6;
+constexpr int kMaxStages = 14;                             // barrier slots: stages, or A ring + B ring (kBRes)
+constexpr int kASlots = 6;                                 // kBRes: ring of query K blocks (one unit deep)
+constexpr int kMaxBSlots = 8;                              // kBRes: ring of corpus K blocks (6 resident + spares)
 
 template <int kCG>
 struct Cfg {
@@ -44,8 +52,9 @@ struct Cfg {
     static constexpr int kABytes = kPieceBytes;                              // 128 queries x 64 k
     static constexpr int kBBytes = kCG == 1 ? 2 * kPieceBytes : kPieceBytes; // 256 or 128 rows x 64 k
     static constexpr int kStageBytes = kABytes + kBBytes;
-    static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+    static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 512 /*barriers*/;
 };
+constexpr int bres_smem_bytes(int b_slots) { return (kASlots + b_slots) * kPieceBytes + 1024 + 512; }
 
 struct Barriers {
     uint64_t full[kMaxStages];       // this CTA's operand bytes of the stage have landed
@@ -131,12 +140,15 @@ struct UnitSchedule {
     }
 };
 
-template <int kCG, bool kI8>
+template <int kCG, bool kI8, bool kBRes>
 __global__ void __launch_bounds__(kThreads, 1) scan_mma_kernel(const MmaScanArgs a) {
+    static_assert(!kBRes || (kCG == 2 && kI8), "the resident-corpus-tile variant exists for int8 CTA pairs only");
     using C = Cfg<kCG>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    Barriers* bars = reinterpret_cast<Barriers*>(smem + C::kStages * C::kStageBytes);
+    const int b_slots = kBRes ? a.b_slots : 0;              // kBRes: slots [0, 6) = A ring, [6, 6 + b_slots) = B ring
+    Barriers* bars = reinterpret_cast<Barriers*>(smem + (kBRes ? (kASlots + b_slots) * kPieceBytes : C::kStages * C::kStageBytes));
+    const int n_bar_slots = kBRes ? kASlots + b_slots : C::kStages;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int kb_count = a.d / (kI8 ? kBlockK8 : kBlockK);
@@ -148,7 +160,7 @@ __global__ void __launch_bounds__(kThreads, 1) scan_mma_kernel(const MmaScanArgs
 
     if constexpr (kCG == 2) cluster_sync_all();          // both CTAs resident before any cross-CTA traffic
     if (threadIdx.x == 0) {
-        for (int i = 0; i < C::kStages; ++i) {
+        for (int i = 0; i < n_bar_slots; ++i) {
             mbar_init(&bars->full[i], 1);
             mbar_init(&bars->peer_full[i], 1);
             mbar_init(&bars->empty[i], 1);
@@ -168,6 +180,37 @@ __global__ void __launch_bounds__(kThreads, 1) scan_mma_kernel(const MmaScanArgs
     if (warp == 0) {
         // ---------------- producer: shadow pieces -> shared memory ----------------
         if (elect_one()) {
+            if constexpr (kBRes) {
+                // A ring: one 16 KiB query K block per slot, streamed for every unit.  B ring: the 6 K blocks of this
+                // CTA's half of the corpus tile, loaded once per corpus tile; a slot is refilled when the MMAs of the
+                // tile's LAST query group that read it have retired (b "empty" barrier = slot kASlots + s).
+                uint32_t a_slot = 0, a_phase = 0, b_slot = 0, b_phase = 0;
+                int64_t prev_ct = -1;
+                for (int64_t i = 0; i < sched.n_mine; ++i) {
+                    int64_t ct_rel;
+                    int qg;
+                    sched.get(i, ct_rel, qg);
+                    const int64_t ct = a.ct0 + ct_rel;
+                    const bool new_tile = ct != prev_ct;
+                    prev_ct = ct;
+                    const int qt = qg * 2 + (int)cta_rank;
+                    const uint8_t* srcA = a.q_shadow + (size_t)qt * kb_count * kPieceBytes;
+                    const uint8_t* srcB = a.x_shadow + (size_t)(2 * ct + cta_rank) * kb_count * kPieceBytes;
+                    for (int kb = 0; kb < kb_count; ++kb) {
+                        if (new_tile) {
+                            uint64_t* full = &bars->full[kASlots + b_slot];
+                            wait_or_trap(&bars->empty[kASlots + b_slot], b_phase ^ 1);
+                            mbar_arrive_expect_tx(full, kPieceBytes);
+                            bulk_g2s(smem + (kASlots + b_slot) * kPieceBytes, srcB + (size_t)kb * kPieceBytes, kPieceBytes, full);
+                            if (++b_slot == (uint32_t)b_slots) { b_slot = 0; b_phase ^= 1; }
+                        }
+                        wait_or_trap(&bars->empty[a_slot], a_phase ^ 1);
+                        mbar_arrive_expect_tx(&bars->full[a_slot], kPieceBytes);
+                        bulk_g2s(smem + a_slot * kPieceBytes, srcA + (size_t)kb * kPieceBytes, kPieceBytes, &bars->full[a_slot]);
+                        if (++a_slot == kASlots) { a_slot = 0; a_phase ^= 1; }
+                    }
+                }
+            } else {
             uint32_t stage = 0, phase = 0;
             for (int64_t i = 0; i < sched.n_mine; ++i) {
                 int64_t ct_rel;
@@ -191,12 +234,51 @@ __global__ void __launch_bounds__(kThreads, 1) scan_mma_kernel(const MmaScanArgs
                     if (++stage == C::kStages) { stage = 0; phase ^= 1; }
                 }
             }
+            }
         }
     } else if (warp == 1) {
         if (leader) {
             // ---------------- MMA issuer ----------------
             if (elect_one()) {
                 constexpr uint32_t idesc = kI8 ? umma_idesc_i8(kTileM * kCG, kTileN) : umma_idesc_f16(kTileM * kCG, kTileN);
+                if constexpr (kBRes) {
+                    uint32_t a_slot = 0, a_phase = 0, b_slot = 0, b_phase = 0, it = 0;
+                    uint32_t cur_b[8];                       // B-ring slot of K block kb of the resident corpus tile (d <= 1024)
+                    int64_t prev_ct = -1;
+                    for (int64_t i = 0; i < sched.n_mine; ++i, ++it) {
+                        int64_t ct_rel, ct_next = -1;
+                        int qg, qg_next;
+                        sched.get(i, ct_rel, qg);
+                        if (i + 1 < sched.n_mine) sched.get(i + 1, ct_next, qg_next);
+                        const bool new_tile = ct_rel != prev_ct;
+                        const bool last_of_tile = ct_next != ct_rel;     // the tile's slots are released behind this unit
+                        prev_ct = ct_rel;
+                        const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
+                        wait_or_trap(&bars->tmem_empty[acc], acc_phase ^ 1);
+                        tc_fence_after();
+                        const uint32_t tmem_d = tmem_base + acc * kTileN;
+                        for (int kb = 0; kb < kb_count; ++kb) {
+                            if (new_tile) {
+                                cur_b[kb] = b_slot;
+                                wait_or_trap(&bars->full[kASlots + b_slot], b_phase);
+                                wait_or_trap(&bars->peer_full[kASlots + b_slot], b_phase);
+                                if (++b_slot == (uint32_t)b_slots) { b_slot = 0; b_phase ^= 1; }
+                            }
+                            wait_or_trap(&bars->full[a_slot], a_phase);
+                            wait_or_trap(&bars->peer_full[a_slot], a_phase);
+                            tc_fence_after();
+                            const uint64_t descA = umma_desc_k128(smem_u32(smem + a_slot * kPieceBytes));
+                            const uint64_t descB = umma_desc_k128(smem_u32(smem + (kASlots + cur_b[kb]) * kPieceBytes));
+#pragma unroll
+                            for (int k = 0; k < 4; ++k)
+                                umma_i8<2>(tmem_d, descA + 2 * k, descB + 2 * k, idesc, (kb | k) != 0);
+                            umma_commit_2cta(&bars->empty[a_slot], 0b11);
+                            if (last_of_tile) umma_commit_2cta(&bars->empty[kASlots + cur_b[kb]], 0b11);
+                            if (kb == kb_count - 1) umma_commit_2cta(&bars->tmem_full[acc], 0b11);
+                            if (++a_slot == kASlots) { a_slot = 0; a_phase ^= 1; }
+                        }
+                    }
+                } else {
                 uint32_t stage = 0, phase = 0, it = 0;
                 for (int64_t i = 0; i < sched.n_mine; ++i, ++it) {
                     const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
@@ -228,10 +310,32 @@ __global__ void __launch_bounds__(kThreads, 1) scan_mma_kernel(const MmaScanArgs
                         if (++stage == C::kStages) { stage = 0; phase ^= 1; }
                     }
                 }
+                }
             }
         } else {
             // ---------------- peer forwarder: my half of the stage has landed ----------------
             if (elect_one()) {
+                if constexpr (kBRes) {
+                    uint32_t a_slot = 0, a_phase = 0, b_slot = 0, b_phase = 0;
+                    int64_t prev_ct = -1;
+                    for (int64_t i = 0; i < sched.n_mine; ++i) {
+                        int64_t ct_rel;
+                        int qg;
+                        sched.get(i, ct_rel, qg);
+                        const bool new_tile = ct_rel != prev_ct;
+                        prev_ct = ct_rel;
+                        for (int kb = 0; kb < kb_count; ++kb) {
+                            if (new_tile) {
+                                wait_or_trap(&bars->full[kASlots + b_slot], b_phase);
+                                mbar_arrive_cluster(&bars->peer_full[kASlots + b_slot], 0);
+                                if (++b_slot == (uint32_t)b_slots) { b_slot = 0; b_phase ^= 1; }
+                            }
+                            wait_or_trap(&bars->full[a_slot], a_phase);
+                            mbar_arrive_cluster(&bars->peer_full[a_slot], 0);
+                            if (++a_slot == kASlots) { a_slot = 0; a_phase ^= 1; }
+                        }
+                    }
+                } else {
                 uint32_t stage = 0, phase = 0;
                 for (int64_t i = 0; i < sched.n_mine; ++i) {
                     for (int kb = 0; kb < kb_count; ++kb) {
@@ -239,6 +343,7 @@ __global__ void __launch_bounds__(kThreads, 1) scan_mma_kernel(const MmaScanArgs
                         mbar_arrive_cluster(&bars->peer_full[stage], 0);
                         if (++stage == C::kStages) { stage = 0; phase ^= 1; }
                     }
+                }
                 }
             }
         }
@@ -293,7 +398,9 @@ __global__ void __launch_bounds__(kThreads, 1) scan_mma_kernel(const MmaScanArgs
             sched.get(i, ct_rel, qg);
             const int64_t ct = a.ct0 + ct_rel;
             const int q = (qg * kCG + (int)cta_rank) * kTileM + quarter * 32 + lane;
-            c.thr = a.thr[q];
+            // the thresholds rise WHILE this launch runs (the previous chunks' rescore / refresh work on a side
+            // stream): read them past the non-coherent L1; a stale value is a valid (lower) threshold
+            c.thr = __ldcg(a.thr + q);
             c.shift = a.q_shift != nullptr ? a.q_shift[q] : 0.f;
             if constexpr (kI8) {
                 c.qc = a.q_consts[q];
@@ -441,14 +548,17 @@ __global__ void __launch_bounds__(kThreads, 1) scan_mma_kernel(const MmaScanArgs
 }  // namespace
 
 cudaError_t scan_mma_configure() {
-    cudaError_t e = cudaFuncSetAttribute(scan_mma_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(scan_mma_kernel<1, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          Cfg<1>::kSmemBytes);
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(scan_mma_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<1>::kSmemBytes);
+    e = cudaFuncSetAttribute(scan_mma_kernel<1, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<1>::kSmemBytes);
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(scan_mma_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<2>::kSmemBytes);
+    e = cudaFuncSetAttribute(scan_mma_kernel<2, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<2>::kSmemBytes);
     if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(scan_mma_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    e = cudaFuncSetAttribute(scan_mma_kernel<2, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             bres_smem_bytes(kMaxBSlots));
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(scan_mma_kernel<2, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 Cfg<2>::kSmemBytes);
 }
 
@@ -470,7 +580,15 @@ cudaError_t launch_pairs(const MmaScanArgs& a, int sm_count, cudaStream_t s) {
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, scan_mma_kernel<2, kI8>, a);
+    if constexpr (kI8) {
+        // resident corpus tile: needs the tile's K blocks (d / 128) to fit the B ring
+        if (a.b_slots > 0) {
+            if (a.b_slots > kMaxBSlots || a.b_slots < a.d / kBlockK8) return cudaErrorInvalidValue;
+            cfg.dynamicSmemBytes = bres_smem_bytes(a.b_slots);
+            return cudaLaunchKernelEx(&cfg, scan_mma_kernel<2, true, true>, a);
+        }
+    }
+    return cudaLaunchKernelEx(&cfg, scan_mma_kernel<2, kI8, false>, a);
 }
 }  // namespace
 
@@ -480,7 +598,7 @@ cudaError_t launch_scan_mma_i8(const MmaScanArgs& a, int sm_count, int cta_group
     if (a.x_tiles == nullptr || a.q_consts == nullptr || a.d % kBlockK8 != 0) return cudaErrorInvalidValue;
     if (cta_group == 2 && (a.n_qtiles % 2) == 0) return launch_pairs<true>(a, sm_count, s);
     const int grid = (int)(n_units < sm_count ? n_units : sm_count);
-    scan_mma_kernel<1, true><<<grid, kThreads, Cfg<1>::kSmemBytes, s>>>(a);
+    scan_mma_kernel<1, true, false><<<grid, kThreads, Cfg<1>::kSmemBytes, s>>>(a);
     return cudaGetLastError();
 }
 
@@ -490,7 +608,7 @@ cudaError_t launch_scan_mma(const MmaScanArgs& a, int sm_count, int cta_group, c
     if (cta_group == 2 && (a.n_qtiles % 2) == 0) return launch_pairs<false>(a, sm_count, s);
     const int64_t n_units = n_ctiles * a.n_qtiles;
     const int grid = (int)(n_units < sm_count ? n_units : sm_count);
-    scan_mma_kernel<1, false><<<grid, kThreads, Cfg<1>::kSmemBytes, s>>>(a);
+    scan_mma_kernel<1, false, false><<<grid, kThreads, Cfg<1>::kSmemBytes, s>>>(a);
     return cudaGetLastError();
 }
 

@@ -125,7 +125,8 @@ constexpr int kRefreshMaxThreads = 1024;   // 256 per query for large batches, 1
 __global__ void __launch_bounds__(kRefreshMaxThreads) refresh_kernel(CandBuf cb, int k,
                                                                   const float* __restrict__ margin,
                                                                   float* __restrict__ tau,
-                                                                  float* __restrict__ thr, const ThrExchange ex) {
+                                                                  float* __restrict__ thr, const ThrExchange ex,
+                                                                  uint32_t* __restrict__ clear_count) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     uint32_t* keys = reinterpret_cast<uint32_t*>(smem_raw);          // [cap]
     __shared__ uint32_t hist[256];
@@ -143,7 +144,10 @@ __global__ void __launch_bounds__(kRefreshMaxThreads) refresh_kernel(CandBuf cb,
         asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(peer_word) : "l"(ex.peers[tid] + q) : "memory");
     else if (tid == ex.n_peers && ex.n_peers > 0)
         asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(peer_word) : "l"(ex.mine + q) : "memory");
-    if (tid == 0) { s_peer_key = 0xFFFFFFFFu; s_peer_have = 0u; s_own_key = 0u; }
+    if (tid == 0) {
+        s_peer_key = 0xFFFFFFFFu; s_peer_have = 0u; s_own_key = 0u;
+        if (clear_count != nullptr) clear_count[q] = 0u;     // the log the preceding rescore consumed is free again
+    }
     const uint32_t raw = cb.count[q];
     const int cnt = (int)min(raw, cb.cap);
     if (raw > cb.cap && tid == 0) *cb.overflow = 1u;
@@ -269,12 +273,13 @@ __global__ void __launch_bounds__(kRefreshMaxThreads) refresh_kernel(CandBuf cb,
 }
 
 void launch_refresh(CandBuf cb, int k, const float* margin, float* tau, float* thr, int nq, cudaStream_t s,
-                    const ThrExchange* ex) {
+                    const ThrExchange* ex, uint32_t* clear_count, bool small_cta) {
     const size_t smem = (size_t)cb.cap * sizeof(uint32_t);
     // the attribute is per device (several devices per process are possible), so it is set per launch
     if (smem > 40 * 1024) cudaFuncSetAttribute(refresh_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     ThrExchange none{};
-    refresh_kernel<<<nq, nq <= 64 ? kRefreshMaxThreads : 256, smem, s>>>(cb, k, margin, tau, thr, ex ? *ex : none);
+    const int threads = (nq <= 64 && !small_cta) ? kRefreshMaxThreads : 256;
+    refresh_kernel<<<nq, threads, smem, s>>>(cb, k, margin, tau, thr, ex ? *ex : none, clear_count);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -420,6 +425,119 @@ void launch_rescore(CandBuf cb, const float* q, int d, SegTable segs, int nq, fl
 void launch_rescore_new(CandBuf cb, const float* q, int d, SegTable segs, int nq, float* screen_err_max,
                         unsigned long long* rescored, cudaStream_t s) {
     launch_rescore_any<true>(cb, q, d, segs, nq, screen_err_max, rescored, s);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Pipelined int8 search, worker side.  The scan of a chunk appends its survivors (screen score, row) to a log shortlist;
+// this kernel computes the exact fp32 score of every log entry (same per-lane FMA order as everywhere else) and moves
+// the entries that can still reach the top-k - exact score >= tau[q], the k-th best exact score found so far - into the
+// main shortlist.  It runs on a side stream WHILE the scan kernel of the next chunk occupies every SM, so its footprint
+// is what fits beside that kernel (168 regs x 320 threads, 198 KB of shared memory per SM): 128 threads, <= 80
+// registers (the query slice sits in 3 KB of shared memory instead of registers), two rows per warp in flight.
+template <int VPL>
+__global__ void __launch_bounds__(128, 6) rescore_log_kernel(CandBuf lg, CandBuf cb, const float* __restrict__ qmat,
+                                                             SegTable segs, const float* __restrict__ tau,
+                                                             float* __restrict__ screen_err_max,
+                                                             unsigned long long* __restrict__ rescored) {
+    constexpr int d = VPL * 128;
+    __shared__ float4 qs[VPL * 32];
+    const int q = blockIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
+    const uint32_t raw = lg.count[q];
+    const int cnt = (int)min(raw, lg.cap);
+    if (cnt == 0) return;                                   // uniform per block
+    if (raw > lg.cap && threadIdx.x == 0) *cb.overflow = 1u;
+    for (int i = threadIdx.x; i < VPL * 32; i += blockDim.x)
+        qs[i] = __ldg(reinterpret_cast<const float4*>(qmat + (size_t)q * d) + i);
+    __syncthreads();
+    const float tau_q = tau[q];
+    const uint32_t* rows = lg.row + (size_t)q * lg.cap;
+    const float* old = lg.score + (size_t)q * lg.cap;
+    float worst = 0.f;
+    const int step = 2 * n_warps * (int)gridDim.y;
+    int slot = 2 * (warp + n_warps * (int)blockIdx.y);
+    uint32_t ra = 0, rb = 0;
+    float old_a = 0.f, old_b = 0.f;
+    auto fetch_meta = [&](int sl) {
+        if (sl < cnt) {
+            const bool hb = sl + 1 < cnt;
+            ra = rows[sl];
+            rb = hb ? rows[sl + 1] : ra;
+            if (lane == 0) {
+                old_a = old[sl];
+                old_b = hb ? old[sl + 1] : 0.f;
+            }
+        }
+    };
+    auto keep = [&](float score, uint32_t row) {
+        if (score >= tau_q) {
+            const uint32_t pos = atomicAdd(cb.count + q, 1u);
+            if (pos < cb.cap) {
+                cb.score[(size_t)q * cb.cap + pos] = score;
+                cb.row[(size_t)q * cb.cap + pos] = row;
+            } else {
+                *cb.overflow = 1u;
+            }
+        }
+    };
+    fetch_meta(slot);
+    for (; slot < cnt; slot += step) {
+        const bool has_b = slot + 1 < cnt;
+        const uint32_t row_a = ra, row_b = rb;
+        const float4* pa = reinterpret_cast<const float4*>(seg_row_ptr(segs, row_a, d));
+        const float4* pb = reinterpret_cast<const float4*>(seg_row_ptr(segs, row_b, d));
+        const float cur_a = old_a, cur_b = old_b;
+        float4 xa[VPL], xb[VPL];
+#pragma unroll
+        for (int i = 0; i < VPL; ++i) {
+            xa[i] = __ldg(pa + i * 32 + lane);
+            xb[i] = __ldg(pb + i * 32 + lane);
+        }
+        fetch_meta(slot + step);
+        float a = 0.f, b = 0.f;
+#pragma unroll
+        for (int i = 0; i < VPL; ++i) {
+            const float4 qv = qs[i * 32 + lane];
+            a = lane_fma4(a, qv, xa[i]);
+            b = lane_fma4(b, qv, xb[i]);
+        }
+        a = warp_sum(a);
+        b = warp_sum(b);
+        if (lane == 0) {
+            worst = fmaxf(worst, fabsf(a - cur_a));
+            keep(a, row_a);
+            if (has_b) {
+                worst = fmaxf(worst, fabsf(b - cur_b));
+                keep(b, row_b);
+            }
+        }
+    }
+    if (lane == 0) {
+        if (worst > 0.f) atomicMax(reinterpret_cast<int*>(screen_err_max), __float_as_int(worst));
+        if (warp == 0 && blockIdx.y == 0) atomicAdd(rescored, (unsigned long long)cnt);
+    }
+}
+
+bool launch_rescore_log(CandBuf lg, CandBuf cb, const float* q, int d, SegTable segs, int nq, const float* tau,
+                        float* screen_err_max, unsigned long long* rescored, cudaStream_t s) {
+    // large batches: one CTA per query (a chunk's log holds a few hundred entries per query); a handful of queries:
+    // the log is split over many CTAs so that its rows are fetched in one or two latencies
+    const int per_query = (int)std::min<int64_t>(std::max(1, 1184 / std::max(nq, 1)), ((int64_t)lg.cap + 7) / 8);
+    const dim3 grid((unsigned)nq, (unsigned)std::max(1, per_query));
+#define HAC_RESCORE_LOG(V) rescore_log_kernel<V><<<grid, 128, 0, s>>>(lg, cb, q, segs, tau, screen_err_max, rescored)
+    switch (d) {
+        case 128: HAC_RESCORE_LOG(1); break;
+        case 256: HAC_RESCORE_LOG(2); break;
+        case 384: HAC_RESCORE_LOG(3); break;
+        case 512: HAC_RESCORE_LOG(4); break;
+        case 640: HAC_RESCORE_LOG(5); break;
+        case 768: HAC_RESCORE_LOG(6); break;
+        case 896: HAC_RESCORE_LOG(7); break;
+        case 1024: HAC_RESCORE_LOG(8); break;
+        default: return false;
+    }
+#undef HAC_RESCORE_LOG
+    return true;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -735,148 +853,6 @@ void launch_reciprocal_rank(const int64_t* pids, int64_t nq, int k, const int64_
     if (nq <= 0) return;
     const size_t smem = (size_t)k * (sizeof(int64_t) + 1);
     reciprocal_rank_kernel<<<(unsigned)nq, kRrThreads, smem, s>>>(pids, k, rel_ptr, rel_pids, rr_out, rank_out);
-}
-
-}  // namespace hac
-
-// ---------------------------------------------------------------------------------------------
-// int8 path, stage 2 in row order.  The rows a chunk emitted are spread over tens of GB; rescoring them query by
-// query touches a new 2 MB page with almost every row and runs at ~1.6 TB/s (ncu: all warps stalled on
-// long-scoreboard, DRAM 20 % busy).  Here the (query, row) pairs of the chunk are first bucketed by row
-// (counting sort over 2048-row buckets), then rescored in that order: neighbouring warps read neighbouring
-// rows (same pages), and a row emitted by several queries is fetched from HBM once and re-read from L2.
-namespace hac {
-
-constexpr int kPairBucketShift = 11;
-
-__global__ void pairs_hist_kernel(CandBuf cb, int nq, uint32_t row_lo, uint32_t* __restrict__ hist) {
-    const int q = blockIdx.x;
-    const uint32_t cnt = min(cb.count[q], cb.cap), first = min(cb.sorted[q], cnt);
-    const uint32_t* rows = cb.row + (size_t)q * cb.cap;
-    for (uint32_t i = first + threadIdx.x; i < cnt; i += blockDim.x)
-        atomicAdd(hist + ((rows[i] - row_lo) >> kPairBucketShift), 1u);
-}
-
-// exclusive scan of the bucket histogram (one block); cursor <- offsets, total <- number of pairs
-__global__ void __launch_bounds__(1024) pairs_scan_kernel(const uint32_t* __restrict__ hist, int n_buckets,
-                                                          uint32_t* __restrict__ cursor, uint32_t* __restrict__ total) {
-    __shared__ uint32_t warp_sums[32];
-    __shared__ uint32_t carry;
-    if (threadIdx.x == 0) carry = 0u;
-    __syncthreads();
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int base = 0; base < n_buckets; base += 1024) {
-        const int i = base + threadIdx.x;
-        const uint32_t v = i < n_buckets ? hist[i] : 0u;
-        uint32_t incl = v;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= o) incl += t;
-        }
-        if (lane == 31) warp_sums[warp] = incl;
-        __syncthreads();
-        if (warp == 0) {
-            uint32_t w = warp_sums[lane], wi = w;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const uint32_t t = __shfl_up_sync(0xffffffffu, wi, o);
-                if (lane >= o) wi += t;
-            }
-            warp_sums[lane] = wi - w;            // exclusive prefix of the warp sums
-        }
-        __syncthreads();
-        const uint32_t excl = carry + warp_sums[warp] + incl - v;
-        if (i < n_buckets) cursor[i] = excl;
-        __syncthreads();
-        if (threadIdx.x == 1023) carry = excl + v;
-        __syncthreads();
-    }
-    if (threadIdx.x == 0) *total = carry;
-}
-
-__global__ void pairs_scatter_kernel(CandBuf cb, int nq, uint32_t row_lo, uint32_t* __restrict__ cursor,
-                                     uint2* __restrict__ pairs) {
-    const int q = blockIdx.x;
-    const uint32_t cnt = min(cb.count[q], cb.cap), first = min(cb.sorted[q], cnt);
-    const uint32_t* rows = cb.row + (size_t)q * cb.cap;
-    for (uint32_t i = first + threadIdx.x; i < cnt; i += blockDim.x) {
-        const uint32_t row = rows[i];
-        const uint32_t pos = atomicAdd(cursor + ((row - row_lo) >> kPairBucketShift), 1u);
-        pairs[pos] = make_uint2(row, (uint32_t)q * cb.cap + i);      // (row, flat slot in the shortlist arrays)
-    }
-}
-
-template <int VPL>
-__global__ void __launch_bounds__(256) rescore_pairs_kernel(CandBuf cb, const uint2* __restrict__ pairs,
-                                                            const uint32_t* __restrict__ total,
-                                                            const float* __restrict__ qmat, SegTable segs,
-                                                            float* __restrict__ screen_err_max,
-                                                            unsigned long long* __restrict__ rescored) {
-    constexpr int d = VPL * 128;
-    const int lane = threadIdx.x & 31;
-    const uint32_t gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
-    const uint32_t n = *total;
-    float worst = 0.f;
-    // consecutive warps take consecutive (row-ordered) pairs; the next pair and its screen score are fetched while the
-    // current row is in flight (one exposed global-memory latency per iteration instead of two)
-    uint2 pr = make_uint2(0u, 0u);
-    float old = 0.f;
-    auto fetch_meta = [&](uint32_t p) {
-        if (p < n) {
-            pr = pairs[p];
-            if (lane == 0) old = cb.score[pr.y];
-        }
-    };
-    fetch_meta(gw);
-    for (uint32_t p = gw; p < n; p += n_warps) {
-        const uint2 cur = pr;
-        const float cur_old = old;
-        const uint32_t q = cur.y / cb.cap;
-        const float4* xrow = reinterpret_cast<const float4*>(seg_row_ptr(segs, cur.x, d));
-        const float4* qrow = reinterpret_cast<const float4*>(qmat + (size_t)q * d);
-        float4 xv[VPL], qv[VPL];
-#pragma unroll
-        for (int i = 0; i < VPL; ++i) {
-            xv[i] = __ldg(xrow + i * 32 + lane);
-            qv[i] = __ldg(qrow + i * 32 + lane);
-        }
-        fetch_meta(p + n_warps);
-        float a = 0.f;
-#pragma unroll
-        for (int i = 0; i < VPL; ++i) a = lane_fma4(a, qv[i], xv[i]);
-        a = warp_sum(a);
-        if (lane == 0) {
-            worst = fmaxf(worst, fabsf(a - cur_old));
-            cb.exact[cur.y] = a;
-            cb.score[cur.y] = a;
-        }
-    }
-    if (lane == 0) {
-        if (worst > 0.f) atomicMax(reinterpret_cast<int*>(screen_err_max), __float_as_int(worst));
-        if (gw == 0) atomicAdd(rescored, (unsigned long long)n);
-    }
-}
-
-// rescore the entries appended since the last refresh, in row order; rows of the chunk lie in [row_lo, row_hi)
-bool launch_rescore_new_by_row(CandBuf cb, const float* q, int d, SegTable segs, int nq, uint32_t row_lo, uint32_t row_hi,
-                               uint32_t* hist, uint32_t* cursor, uint32_t* total, uint2* pairs, int sm_count,
-                               float* screen_err_max, unsigned long long* rescored, cudaStream_t s) {
-    const int n_buckets = (int)(((row_hi - row_lo) >> kPairBucketShift) + 1);
-    cudaMemsetAsync(hist, 0, (size_t)n_buckets * sizeof(uint32_t), s);
-    pairs_hist_kernel<<<nq, 256, 0, s>>>(cb, nq, row_lo, hist);
-    pairs_scan_kernel<<<1, 1024, 0, s>>>(hist, n_buckets, cursor, total);
-    pairs_scatter_kernel<<<nq, 256, 0, s>>>(cb, nq, row_lo, cursor, pairs);
-    const int grid = sm_count * 6;
-    switch (d) {
-        case 128: rescore_pairs_kernel<1><<<grid, 256, 0, s>>>(cb, pairs, total, q, segs, screen_err_max, rescored); break;
-        case 256: rescore_pairs_kernel<2><<<grid, 256, 0, s>>>(cb, pairs, total, q, segs, screen_err_max, rescored); break;
-        case 512: rescore_pairs_kernel<4><<<grid, 256, 0, s>>>(cb, pairs, total, q, segs, screen_err_max, rescored); break;
-        case 768: rescore_pairs_kernel<6><<<grid, 256, 0, s>>>(cb, pairs, total, q, segs, screen_err_max, rescored); break;
-        case 1024: rescore_pairs_kernel<8><<<grid, 256, 0, s>>>(cb, pairs, total, q, segs, screen_err_max, rescored); break;
-        default: return false;
-    }
-    return true;
 }
 
 }  // namespace hac

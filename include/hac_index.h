@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define HAC_ABI_VERSION 1
+#define HAC_ABI_VERSION 2
 
 #define HAC_OK 0
 #define HAC_E_INVALID (-1)   /* bad argument (dimension mismatch, k out of range, null pointer) */
@@ -62,7 +62,12 @@ typedef struct hac_stats {
     float   total_ms;             /* device time of the whole last search (CUDA events) */
     int64_t ntotal;
     int64_t bytes_fp32;           /* HBM held by the fp32 rows */
-    int64_t bytes_shadow;         /* HBM held by the f16 tiled shadow */
+    int64_t bytes_shadow;         /* HBM held by the f16 tiled image (0 until a search needs it, see "lazy_f16") */
+    int64_t bytes_i8;             /* HBM held by the int8 tiled image and its per-tile constants */
+    int32_t n_sync_chunks;        /* chunks of the last search whose scan waited for the previous chunk's thresholds */
+    int32_t pipelined;            /* 1 = the last search overlapped rescoring with the scans (int8 screen) */
+    float   tail_ms;              /* device time between the end of the last scan and the end of the last search */
+    float   reserved0;
 } hac_stats;
 
 /* ---- lifetime ------------------------------------------------------------------------------

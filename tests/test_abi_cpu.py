@@ -20,7 +20,7 @@ def test_library_exports_every_declared_symbol():
     declared = set(re.findall(r"\b(hac_[a-z_]+)\s*\(", hdr))
     assert declared == set(_lib.SIGNATURES)
     L = _lib.lib()                                  # binds all of them (AttributeError otherwise)
-    assert L.hac_abi_version() == 1
+    assert L.hac_abi_version() == _lib.HAC_ABI_VERSION
     assert isinstance(_lib.last_error(), str)
 
 

@@ -8,11 +8,9 @@ import numpy as np
 import pytest
 
 from oracle.compare import assert_parity
+from fullscale_util import DIM, N_QUERIES, N_ROWS, arbiter_topk, queries_over_all_tiles
 
 pytestmark = pytest.mark.gpu
-
-N_ROWS = 25_700_592
-DIM = 768
 
 
 @pytest.fixture(scope="module")
@@ -50,35 +48,59 @@ def test_planted_rows_rank_first_with_exact_score(big_index):
     assert 110 < float(np.median(D[n_planted:, 99])) < 140
 
 
-def test_full_corpus_rescoring_with_torch_agrees(big_index):
-    """Independent exact path: regenerate the corpus in slabs, fp32 matmul (TF32 off) + topk."""
+def test_headline_batch_all_query_tiles_against_fp64_arbiter(big_index):
+    """The shape bench.py times: 2514 queries (20 query tiles -> the CTA-pair int8 scan, tile-major, pipelined chunks)
+    over 25.7M rows.  260 queries spread over ALL 20 tiles are compared - ids, ORDER and scores, tolerance groups per
+    SURVEY 8d - with an fp64 re-scoring of the regenerated corpus; the rest through idempotence and planted rows."""
     import torch
+    import haconvdr_b200 as hb
     from haconvdr_b200.index import synth_rows_device
     idx, q, n_planted = big_index
-    torch.backends.cuda.matmul.allow_tf32 = False
+    q_all = synth_rows_device(N_QUERIES, DIM, seed=4242)
+    assert torch.equal(q_all[:40], q)
+    D, I = idx.search(q_all, 100)
+    st = idx.stats()
+    assert st["path"] == hb.HAC_PATH_I8 and st["retries"] == 0, st
+    assert st["screen_err_max"] <= st["margin_max"], st
+    assert st["bytes_shadow"] == 0, "the f16 image must not exist before a search needs it"
+    sel = queries_over_all_tiles()
+    assert len(sel) >= 256 and len(set((sel // 128).tolist())) == 20
+    sel_t = torch.from_numpy(sel).cuda()
+    ref_D, ref_I, scores_of = arbiter_topk(q_all[sel_t], N_ROWS - n_planted, 100, planted=3.0 * q[:n_planted])
+    got_D, got_I = D[sel_t].cpu().numpy(), I[sel_t].cpu().numpy()
+    rep = assert_parity(ref_D, ref_I, got_D, got_I, rtol=1e-5, ref_scores_of=scores_of)
+    assert rep.recall == 1.0 and rep.n_queries == len(sel)
+    Dn, In = D.cpu().numpy(), I.cpu().numpy()
+    assert np.all(np.diff(Dn, axis=1) <= 0) and In.min() >= 0 and In.max() < N_ROWS
+    for i in range(n_planted):
+        assert In[i, 0] == N_ROWS - n_planted + i
+    # the pipelined schedule, the streamed-operand CTA-pair scan and the single-CTA scan return bitwise the same
+    # 2514 x 100 result as the default (chunk-synchronous schedule, resident corpus tile)
+    assert st["pipelined"] == 0
+    idx.set_option("i8_pipeline", 1)
+    idx.set_option("i8_b_slots", 6)
+    D2, I2 = idx.search(q_all, 100)
+    assert idx.stats()["pipelined"] == 1
+    idx.set_option("i8_pipeline", 0)
+    assert torch.equal(I2, I) and torch.equal(D2, D)
+    for opt, val, back in (("i8_b_slots", 0, 8), ("i8_b_slots", 7, 8), ("i8_cta_group", 1, 2)):
+        idx.set_option(opt, val)
+        D3, I3 = idx.search(q_all, 100)
+        idx.set_option(opt, back)
+        assert torch.equal(I3, I) and torch.equal(D3, D), (opt, val)
+    # small batches of the same queries (single-tile scan, HBM-bound) agree with the rows of the big batch
+    for nq in (1, 4, 32):
+        Ds, Is = idx.search(q_all[:nq], 100)
+        assert torch.equal(Is, I[:nq]) and torch.equal(Ds, D[:nq]), nq
+
+
+def test_full_corpus_rescoring_with_torch_agrees(big_index):
+    """Independent exact path: regenerate the corpus in slabs, fp64 matmul + topk (fullscale_util.arbiter_topk)."""
+    idx, q, n_planted = big_index
     sel = q[n_planted:n_planted + 8]
-    k = 100
-    best_s = torch.full((sel.shape[0], k), -float("inf"), device="cuda")
-    best_i = torch.full((sel.shape[0], k), -1, dtype=torch.int64, device="cuda")
-    slab = 2_000_000
-    n_syn = N_ROWS - n_planted
-    sel64 = sel.double()
-    slabs = [(r0, min(slab, n_syn - r0)) for r0 in range(0, n_syn, slab)] + [(n_syn, n_planted)]
-    for r0, n in slabs:
-        # the last slab is the planted rows (3 * q_i), which also score high against other queries
-        x = synth_rows_device(n, DIM, seed=42, row0=r0) if r0 < n_syn else 3.0 * q[:n_planted]
-        s = (sel64 @ x.double().T)                       # fp64 arbiter on the device
-        s, i = torch.topk(s, min(k, n), dim=1)
-        cat_s = torch.cat([best_s.double(), s], 1)
-        cat_i = torch.cat([best_i, i + r0], 1)
-        top = torch.topk(cat_s, k, dim=1)
-        best_s, best_i = top.values, torch.gather(cat_i, 1, top.indices)
-        del x, s
-    D, I = idx.search(sel, k)
-    ref_D, ref_I = best_s.cpu().numpy(), best_i.cpu().numpy()
-    order = np.lexsort((ref_I, -ref_D), axis=1)          # (score desc, id asc)
-    ref_D, ref_I = np.take_along_axis(ref_D, order, 1), np.take_along_axis(ref_I, order, 1)
-    rep = assert_parity(ref_D, ref_I, D.cpu().numpy(), I.cpu().numpy(), rtol=1e-5)
+    ref_D, ref_I, scores_of = arbiter_topk(sel, N_ROWS - n_planted, 100, planted=3.0 * q[:n_planted])
+    D, I = idx.search(sel, 100)
+    rep = assert_parity(ref_D, ref_I, D.cpu().numpy(), I.cpu().numpy(), rtol=1e-5, ref_scores_of=scores_of)
     assert rep.recall == 1.0
 
 

@@ -1,4 +1,6 @@
-"""GPU (-m gpu), needs >= 2 devices (skipped otherwise): the real multi-GPU paths.
+"""GPU (-m gpu): the multi-shard paths.  The first tests run on ONE device (two shards = two handles on cuda:0, the
+"peer" pointers are same-device buffers), so the exchange / peer-merge logic is exercised on a single-GPU box too;
+the rest needs >= 2 devices (skipped otherwise): the real multi-GPU paths.
   * torchrun, one process per GPU, NCCL all-gather of Q x k candidates + device merge
     (haconvdr_b200.sharded.ShardedFlatIPIndex) against the fp64 arbiter;
   * the in-process faiss IndexShards stand-in (faiss_compat.index_cpu_to_gpu_multiple, n_gpu = 2)."""
@@ -119,5 +121,113 @@ def test_in_process_index_shards_two_devices():
     D64, I64 = brute_force_fp64(q, x, 100)
     x64 = x.astype(np.float64)
     assert_parity(D64, I64, D, I, rtol=1e-5, ref_scores_of=lambda qi, ids: x64[ids] @ q[qi].astype(np.float64))
+    index.reset()
+    assert index.ntotal == 0
+
+
+# ---- one device, two shards: threshold exchange + peer-pointer merge through the C ABI -----------------------------
+def _two_shards(x, split):
+    import haconvdr_b200 as hb
+    a, b = hb.FlatIPIndex(768, 0), hb.FlatIPIndex(768, 0)
+    a.add(x[:split])
+    b.add(x[split:])
+    b.set_id_base(split)
+    return a, b
+
+
+@pytest.mark.parametrize("nq,n,k,concurrent", [(150, 60000, 100, True), (150, 60000, 100, False), (3, 40000, 10, True),
+                                               (300, 90001, 1, True), (40, 30000, 128, False)])
+def test_threshold_exchange_and_peer_merge_two_shards_one_device(nq, n, k, concurrent):
+    """hac_set_threshold_exchange + hac_merge_topk_peers_device with same-device "peer" pointers: two shards search
+    (concurrently from two host threads on two streams, or one after the other), publish their ceil(k/2)-th best
+    scores to each other, return only their share of the global top-k, and the peer-pointer merge of the two lists
+    equals the brute-force result of the whole corpus.  Same protocol as one process per GPU over NVLink."""
+    import threading
+    import torch
+    from haconvdr_b200.index import merge_topk_peers_device
+    from oracle.compare import assert_parity
+    from oracle.flat_ip import brute_force_fp64
+    rng = np.random.default_rng(nq + n + k)
+    x = rng.standard_normal((n, 768), dtype=np.float32)
+    q = rng.standard_normal((nq, 768), dtype=np.float32)
+    split = n // 2 + 17
+    shards = _two_shards(x, split)
+    dev = torch.device("cuda", 0)
+    cap = 4096
+    words = [torch.zeros(cap, dtype=torch.int64, device=dev) for _ in range(2)]
+    for r, sh in enumerate(shards):
+        sh.set_threshold_exchange(words[r].data_ptr(), [words[1 - r].data_ptr()], cap)
+    qd = torch.from_numpy(q).to(dev)
+    D64, I64 = brute_force_fp64(q, x, k)
+    x64 = x.astype(np.float64)
+    scores_of = lambda qi, ids: x64[ids] @ q[qi].astype(np.float64)   # noqa: E731
+
+    def run(epoch):
+        outs = [(torch.empty((nq, k), dtype=torch.float32, device=dev), torch.empty((nq, k), dtype=torch.int64, device=dev))
+                for _ in range(2)]
+        errs = []
+
+        def one(r):
+            try:
+                torch.cuda.set_device(0)
+                with torch.cuda.stream(torch.cuda.Stream(dev)):
+                    shards[r].set_option("exchange_epoch", epoch)
+                    shards[r].search(qd, k, out=outs[r])
+                    shards[r].set_option("exchange_epoch", 0)
+            except Exception as e:   # noqa: BLE001
+                errs.append(e)
+        if concurrent:
+            ts = [threading.Thread(target=one, args=(r,)) for r in range(2)]
+            [t.start() for t in ts]
+            [t.join() for t in ts]
+        else:
+            one(0)
+            one(1)
+        assert not errs, errs
+        torch.cuda.synchronize()
+        stats = [sh.stats() for sh in shards]
+        D, I = merge_topk_peers_device([o[0].data_ptr() for o in outs], [o[1].data_ptr() for o in outs], nq, k, k, dev)
+        return D.cpu().numpy(), I.cpu().numpy(), stats, outs
+
+    D0, I0, st_off, _ = run(0)                                   # exchange off: every shard returns its own full top-k
+    assert_parity(D64, I64, D0, I0, rtol=1e-5, ref_scores_of=scores_of)
+    for epoch in (1, 2, 7):
+        D1, I1, st_on, outs = run(epoch)
+        assert np.array_equal(I1, I0) and np.array_equal(D1, D0), epoch
+        for st in st_on:
+            assert st["retries"] == 0 and st["screen_err_max"] <= st["margin_max"], st
+    if not concurrent:
+        # shard 1 searched after shard 0 had published its final bounds: it keeps only rows that can reach the global
+        # top-k, so it returns fillers where its own k-th best would have been
+        assert int((outs[1][1] < 0).sum().item()) > 0
+        assert st_on[1]["candidates_rescored"] <= st_off[1]["candidates_rescored"]
+    # a stale epoch is ignored (tags differ): results unchanged
+    D2, I2, _, _ = run(3)
+    assert np.array_equal(I2, I0) and np.array_equal(D2, D0)
+    for sh in shards:
+        sh.set_threshold_exchange(0, [], 0)
+        sh.close()
+
+
+def test_in_process_index_shards_on_one_device():
+    """faiss_compat.ShardedInProcessIndex (what `index_cpu_to_gpu_multiple` returns for n_gpu > 1) with both shards
+    placed on cuda:0: add / search / reset against the brute-force oracle."""
+    from haconvdr_b200 import faiss_compat as faiss
+    from oracle.compare import assert_parity
+    from oracle.flat_ip import brute_force_fp64
+    index = faiss.ShardedInProcessIndex(768, [0, 0])
+    rng = np.random.default_rng(6)
+    x = rng.standard_normal((33001, 768), dtype=np.float32)
+    q = rng.standard_normal((90, 768), dtype=np.float32)
+    index.add(x[:12000])
+    index.add(x[12000:])
+    assert index.ntotal == 33001
+    x64 = x.astype(np.float64)
+    for k in (100, 1):
+        D, I = index.search(q, k)
+        D64, I64 = brute_force_fp64(q, x, k)
+        assert_parity(D64, I64, D, I, rtol=1e-5, ref_scores_of=lambda qi, ids: x64[ids] @ q[qi].astype(np.float64))
+    D2, I2 = index.search(q, 1)
+    assert np.array_equal(I2, I) and np.array_equal(D2, D)
     index.reset()
     assert index.ntotal == 0

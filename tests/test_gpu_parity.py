@@ -546,8 +546,11 @@ def test_auto_path_policy(nq, k):
     D, I = idx.search(q, k)
     st = idx.stats()
     assert st["path"] == (hb.HAC_PATH_I8 if k <= 128 else hb.HAC_PATH_MMA) and st["retries"] == 0, st
-    assert st["bytes_shadow"] >= 90000 * 768 * 3               # f16 + int8 images
+    assert st["bytes_i8"] >= 90000 * 768                       # the int8 image is built on add ...
+    if k <= 128:
+        assert st["bytes_shadow"] == 0                         # ... the f16 image only when a search needs it
     Dm, Im = idx.search(q, k, path=hb.HAC_PATH_MMA)
+    assert idx.stats()["bytes_shadow"] >= 90000 * 768 * 2
     assert np.array_equal(I, Im) and np.array_equal(D, Dm)
     _check(q, x, k, D, I, also_fp32_oracle=False)
     idx.set_option("i8_auto_max_k", 0)
@@ -558,7 +561,8 @@ def test_auto_path_policy(nq, k):
     idx2.set_option("build_i8", 0)
     idx2.add(x[:20000])
     D2, I2 = idx2.search(q, min(k, 128), path=hb.HAC_PATH_I8)
-    assert idx2.stats()["path"] == hb.HAC_PATH_MMA and idx2.stats()["bytes_shadow"] < 20224 * 768 * 3
+    assert idx2.stats()["path"] == hb.HAC_PATH_MMA and idx2.stats()["bytes_i8"] == 0
+    assert 20000 * 768 * 2 <= idx2.stats()["bytes_shadow"] < 20224 * 768 * 3
     _check(q, x[:20000], min(k, 128), D2, I2, also_fp32_oracle=False)
 
 
@@ -650,12 +654,108 @@ def test_int8_screen_cta_pairs_and_unit_schedules(nq, n, k):
     Dm, Im = idx.search(q, k, path=hb.HAC_PATH_MMA)
     for cg in (1, 2):
         for tile_major in (0, 1):
-            idx.set_option("i8_cta_group", cg)
-            idx.set_option("scan_tile_major", tile_major)
-            D8, I8 = idx.search(q, k, path=hb.HAC_PATH_I8)
-            st = idx.stats()
-            assert st["path"] == hb.HAC_PATH_I8 and st["retries"] == 0, (cg, tile_major, st)
-            assert np.array_equal(I8, Im) and np.array_equal(D8, Dm), (cg, tile_major)
+            # b_slots: the CTA-pair scan keeps the corpus tile resident across its query groups (ring of 7 / 8 slots)
+            for b_slots in ((0, 7, 8) if (cg == 2 and tile_major == 1) else (8,)):
+                idx.set_option("i8_cta_group", cg)
+                idx.set_option("scan_tile_major", tile_major)
+                idx.set_option("i8_b_slots", b_slots)
+                D8, I8 = idx.search(q, k, path=hb.HAC_PATH_I8)
+                st = idx.stats()
+                assert st["path"] == hb.HAC_PATH_I8 and st["retries"] == 0, (cg, tile_major, b_slots, st)
+                assert np.array_equal(I8, Im) and np.array_equal(D8, Dm), (cg, tile_major, b_slots)
             Df, If = idx.search(q, k, path=hb.HAC_PATH_MMA)          # the f16 scan under the same schedule
             assert np.array_equal(If, Im) and np.array_equal(Df, Dm), (cg, tile_major)
     _check(q, x, k, Dm, Im, also_fp32_oracle=False)
+
+
+@pytest.mark.parametrize("nq,n,k", [(1, 200003, 100), (4, 150000, 10), (130, 120001, 100), (300, 260000, 100),
+                                    (520, 90000, 1), (64, 70000, 1000)])
+def test_int8_pipelined_search_equals_the_synchronous_one(nq, n, k):
+    """The pipelined int8 search (scans back to back, rescore + refresh of chunk i on a side stream beside the scan of
+    chunk i+1, stale thresholds) returns bitwise what the chunk-synchronous schedule and the f16 screen return; with
+    `i8_pipe_min_rows` lowered the overlap engages on a corpus the oracle can still brute-force."""
+    hb = _engine()
+    rng = np.random.default_rng(nq * 7 + k)
+    x = rng.standard_normal((n, 768), dtype=np.float32)
+    q = rng.standard_normal((nq, 768), dtype=np.float32)
+    idx = hb.FlatIPIndex(768)
+    idx.add(x[: n // 2 + 11])
+    idx.add(x[n // 2 + 11:])
+    idx.set_option("i8_pipeline", 0)
+    D0, I0 = idx.search(q, k, path=hb.HAC_PATH_I8)
+    st0 = idx.stats()
+    assert st0["path"] == hb.HAC_PATH_I8 and st0["retries"] == 0 and st0["pipelined"] == 0, st0
+    _check(q, x, k, D0, I0, also_fp32_oracle=False)
+    idx.set_option("i8_pipeline", 1)
+    for min_rows, growth, dist in ((4096, 125, 2), (8192, 500, 2), (4096, 125, 1), (0, 125, 2)):
+        idx.set_option("i8_pipe_min_rows", min_rows)
+        idx.set_option("i8_pipe_growth_x1000", growth)
+        idx.set_option("i8_pipe_dist", dist)
+        for _ in range(2):
+            D1, I1 = idx.search(q, k, path=hb.HAC_PATH_I8)
+            st = idx.stats()
+            assert st["path"] == hb.HAC_PATH_I8 and st["retries"] == 0, (min_rows, growth, dist, st)
+            assert st["screen_err_max"] <= st["margin_max"], st
+            assert np.array_equal(I1, I0) and np.array_equal(D1, D0), (min_rows, growth, dist)
+        if min_rows and dist == 2 and n >= 100000:
+            assert st["pipelined"] == 1 and st["n_sync_chunks"] < st["n_chunks"], st
+    Dm, Im = idx.search(q, k, path=hb.HAC_PATH_MMA)
+    assert np.array_equal(Im, I0) and np.array_equal(Dm, D0)
+    # the device-tensor API on a caller stream goes through the same two internal streams
+    import torch
+    side = torch.cuda.Stream()
+    with torch.cuda.stream(side):
+        qd = torch.from_numpy(q).cuda()
+        Dd, Id = idx.search(qd, k, path=hb.HAC_PATH_I8)
+        Dd, Id = Dd.cpu().numpy(), Id.cpu().numpy()
+    assert np.array_equal(Id, I0) and np.array_equal(Dd, D0)
+
+
+def test_f16_image_is_built_lazily_and_kept_up_to_date():
+    """With the int8 image present the f16 image (2 bytes per element of HBM) does not exist until a search needs the
+    f16 screen; once built, later adds keep it complete; `lazy_f16 = 0` builds it on add as before."""
+    hb = _engine()
+    rng = np.random.default_rng(404)
+    x = rng.standard_normal((70000, 768), dtype=np.float32)
+    q = rng.standard_normal((140, 768), dtype=np.float32)
+    idx = hb.FlatIPIndex(768)
+    idx.add(x[:30000])
+    D8, I8 = idx.search(q, 100)
+    assert idx.stats()["path"] == hb.HAC_PATH_I8 and idx.stats()["bytes_shadow"] == 0
+    Dm, Im = idx.search(q, 100, path=hb.HAC_PATH_MMA)          # builds the image
+    assert idx.stats()["bytes_shadow"] >= 30000 * 768 * 2
+    assert np.array_equal(Im, I8) and np.array_equal(Dm, D8)
+    idx.add(x[30000:30001])                                    # appended into the existing segment / a new one
+    idx.add(x[30001:])
+    D8, I8 = idx.search(q, 100)
+    Dm, Im = idx.search(q, 100, path=hb.HAC_PATH_MMA)
+    assert np.array_equal(Im, I8) and np.array_equal(Dm, D8)
+    _check(q, x, 100, Dm, Im, also_fp32_oracle=False)
+    Dk, Ik = idx.search(q[:40], 300)                           # AUTO with k > 128: the f16 screen
+    assert idx.stats()["path"] == hb.HAC_PATH_MMA
+    _check(q[:40], x, 300, Dk, Ik, also_fp32_oracle=False)
+    idx.reset()
+    idx.add(x[:5000])
+    Dm, Im = idx.search(q, 10, path=hb.HAC_PATH_MMA)
+    _check(q, x[:5000], 10, Dm, Im, also_fp32_oracle=False)
+    eager = hb.FlatIPIndex(768)
+    eager.set_option("lazy_f16", 0)
+    eager.add(x[:9000])
+    assert eager.stats()["bytes_shadow"] >= 9000 * 768 * 2
+    De, Ie = eager.search(q, 10, path=hb.HAC_PATH_MMA)
+    _check(q, x[:9000], 10, De, Ie, also_fp32_oracle=False)
+
+
+def test_default_path_gemv_batches_by_four():
+    """`default_path = GEMV` must split an AUTO search into batches of 4 (it used to fail for nq > 4)."""
+    hb = _engine()
+    rng = np.random.default_rng(9)
+    x = rng.standard_normal((6000, 768), dtype=np.float32)
+    q = rng.standard_normal((11, 768), dtype=np.float32)
+    idx = hb.FlatIPIndex(768)
+    idx.add(x)
+    idx.set_option("default_path", hb.HAC_PATH_GEMV)
+    idx.set_option("i8_auto_max_k", 0)
+    D, I = idx.search(q, 10)
+    assert idx.stats()["path"] == hb.HAC_PATH_GEMV
+    _check(q, x, 10, D, I, also_fp32_oracle=False)

@@ -25,6 +25,21 @@ def test_restated_loop_matches_reference_golden(name):
     np.testing.assert_allclose(D, g["D"], rtol=1e-6, atol=0)
 
 
+@pytest.mark.parametrize("name", GOLDEN_MERGE_CASES)
+def test_cost_faithful_python_loop_matches_reference_golden(name):
+    """oracle/ref_loop.py (tuples + deepcopy + two-pointer merges: what bench.py --impl reference times when the
+    reference module is not mounted) returns exactly what the reference's own function returned."""
+    from oracle.ref_loop import search_blocks_python
+    g = load_golden(name)
+    with tempfile.TemporaryDirectory() as d:
+        write_blocks(d, g["blocks"], g["id_start"])
+        nb = int(g.get("block_num", len(g["blocks"]) + 3))
+        D, I = search_blocks_python(nb, d, FlatIP(g["q"].shape[1]), g["q"], g["k"])
+    assert D.dtype == np.float64 and I.dtype == np.int64
+    assert D.shape == g["D"].shape and np.array_equal(I, g["I"])
+    np.testing.assert_allclose(D, g["D"], rtol=1e-6, atol=0)
+
+
 def test_integer_known_answers_are_exact():
     g = load_golden("kat_int_d768_1block")
     x, q = g["blocks"][0], g["q"]
