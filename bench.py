@@ -64,7 +64,7 @@ def parse_args():
     ap.add_argument("--parity-queries", type=int, default=64)
     ap.add_argument("--exchange", default="auto", choices=["auto", "p2p", "nccl"])
     ap.add_argument("--ref-blocks", type=int, default=2, help="--impl reference: on-disk blocks per step")
-    ap.add_argument("--ref-block-rows", type=int, default=400_000, help="--impl reference: rows per on-disk block")
+    ap.add_argument("--ref-block-rows", type=int, default=1_000_000, help="--impl reference: rows per on-disk block")
     args = ap.parse_args()
     args.config = args.config or args.workload or "topiocqa"
     cfg = CONFIGS[args.config]

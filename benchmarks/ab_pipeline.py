@@ -1,7 +1,8 @@
 #!/usr/bin/env python
 """Round-2 A/B on one GPU (full TopiOCQA-scale corpus by default): the pipelined int8 search (scans back to back,
-rescore + refresh on a side stream beside the next scan) against the chunk-synchronous schedule of round 1, for the
-headline batch and for the small turn batches, alternating in one process.
+rescore + refresh on a side stream beside the next scan) against the chunk-synchronous schedule of round 1, and the
+resident-corpus-tile CTA-pair scan (i8_b_slots) against the streamed-operand one, for the headline batch and for the
+small turn batches, alternating in one process.
 
 One JSON line per (batch, variant).  Usage: python benchmarks/ab_pipeline.py [--rows N] [--reps R] [--only big,small]
 """
@@ -16,14 +17,14 @@ def med(xs):
 
 VARIANTS = [
     # name, options
-    ("sync", {"i8_pipeline": 0}),
-    ("pipe", {"i8_pipeline": 1}),
-    ("pipe_g250", {"i8_pipeline": 1, "i8_pipe_growth_x1000": 250}),
-    ("pipe_g60", {"i8_pipeline": 1, "i8_pipe_growth_x1000": 60}),
-    ("pipe_min2x", {"i8_pipeline": 1, "i8_pipe_min_rows": 151552}),
-    ("pipe_dist1", {"i8_pipeline": 1, "i8_pipe_dist": 1}),
+    ("sync_b0", {"i8_pipeline": 0, "i8_b_slots": 0}),
+    ("sync_b8", {"i8_pipeline": 0, "i8_b_slots": 8}),
+    ("sync_b7", {"i8_pipeline": 0, "i8_b_slots": 7}),
+    ("pipe_b0", {"i8_pipeline": 1, "i8_b_slots": 0}),
+    ("pipe_b6", {"i8_pipeline": 1, "i8_b_slots": 6}),
 ]
-DEFAULTS = {"i8_pipeline": 1, "i8_pipe_growth_x1000": 125, "i8_pipe_min_rows": 0, "i8_pipe_dist": 2}
+DEFAULTS = {"i8_pipeline": 0, "i8_pipe_growth_x1000": 125, "i8_pipe_min_rows": 0, "i8_pipe_dist": 2, "i8_b_slots": 0,
+            "i8_chunk_growth_x100": 0}
 
 
 def main():

@@ -11,17 +11,21 @@ def main():
     ap.add_argument("--rows", type=int, default=25_700_592)
     ap.add_argument("--queries", type=int, default=1)
     ap.add_argument("--cta-group", type=int, default=1)
+    ap.add_argument("--b-slots", type=int, default=-1, help="i8_b_slots (resident corpus tile ring); -1 = engine default")
+    ap.add_argument("--k", type=int, default=100)
     args = ap.parse_args()
     from haconvdr_b200 import FlatIPIndex, HAC_PATH_I8
     from haconvdr_b200.index import synth_rows_device
     idx = FlatIPIndex(768, 0)
     idx.set_option("build_i8", 1)
     idx.set_option("i8_cta_group", args.cta_group)
+    if args.b_slots >= 0:
+        idx.set_option("i8_b_slots", args.b_slots)
     idx.reserve(args.rows)
     idx.add_synthetic(args.rows, seed=42)
     q = synth_rows_device(args.queries, 768, seed=4242)
     for _ in range(2):
-        D, I = idx.search(q, 100, path=HAC_PATH_I8)
+        D, I = idx.search(q, args.k, path=HAC_PATH_I8)
     st = idx.stats()
     print(json.dumps({"rows": args.rows, "queries": args.queries, "total_ms": st["total_ms"], "scan_ms": st["scan_ms"],
                       "chunks": st["n_chunks"], "launches": st["kernel_launches"], "path": st["path"]}))

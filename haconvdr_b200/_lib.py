@@ -18,6 +18,7 @@ HAC_PATH_AUTO, HAC_PATH_GEMV, HAC_PATH_MMA, HAC_PATH_I8 = 0, 1, 2, 3
 HAC_MAX_K = 1024
 
 HAC_ABI_VERSION = 2
+HAC_EXCHANGE_WORDS_PER_QUERY = 16
 
 c_i64 = ctypes.c_int64
 c_f32p = ctypes.POINTER(ctypes.c_float)
@@ -61,9 +62,12 @@ SIGNATURES = {
                                              ctypes.c_int, _VP, _VP, _VP]),
     "hac_merge_topk_peers_device": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, c_i64, ctypes.c_int,
                                                    ctypes.POINTER(_VP), ctypes.POINTER(_VP), ctypes.c_int, _VP, _VP, _VP]),
+    "hac_enable_peer_access": (ctypes.c_int, [ctypes.c_int, ctypes.c_int]),
     "hac_gather_ids_device": (ctypes.c_int, [ctypes.c_int, _VP, c_i64, _VP, c_i64, _VP, _VP]),
     "hac_set_threshold_exchange": (ctypes.c_int, [_VP, _VP, ctypes.POINTER(_VP), ctypes.c_int, c_i64]),
     "hac_reciprocal_rank_device": (ctypes.c_int, [ctypes.c_int, _VP, c_i64, ctypes.c_int, _VP, _VP, _VP, _VP, _VP]),
+    "hac_save_shard": (ctypes.c_int, [_VP, ctypes.c_char_p]),
+    "hac_load_shard": (ctypes.c_int, [_VP, ctypes.c_char_p]),
     "hac_pinned_alloc": (ctypes.c_int, [ctypes.c_size_t, ctypes.POINTER(_VP)]),
     "hac_pinned_free": (ctypes.c_int, [_VP]),
     "hac_set_option": (ctypes.c_int, [_VP, ctypes.c_char_p, c_i64]),

@@ -4,6 +4,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <unistd.h>
 
 #include <algorithm>
 #include <string>
@@ -134,7 +135,7 @@ struct hac_index {
     // bound, so nothing but the number of emitted rows depends on the overlap.
     // int8 CTA-pair scan: ring slots (16 KiB) that keep the corpus tile resident across its query groups (0 = off: both
     // operands streamed per unit).  8 leaves no room for a co-resident worker CTA; the pipelined search uses 7.
-    int i8_b_slots = 8;
+    int i8_b_slots = 0;                     // measured: 54.1 ms of scan with the tile resident (7 or 8 slots) vs 34.8 ms streamed
     bool i8_pipeline = false;               // measured on one GPU: 47.1 ms pipelined vs 46.2 ms synchronous (the scan is power-bound: co-running rescores slow it by what they save)
     int i8_pipe_dist = 2;                   // 1 = every scan waits for the previous chunk's worker (no overlap)
     double i8_pipe_growth = 0.125;          // pipelined chunks: max(i8_pipe_min_rows, growth * rows seen so far)
@@ -471,7 +472,9 @@ void plan_chunks_i8(const hac_index* idx, int nq, int nq_pad, int k, uint32_t lo
     int64_t min_rows;
     const bool pipeline = idx->i8_pipeline && idx->i8_pipe_dist >= 2;
     if (pipeline) {
-        sync_growth = idx->i8_chunk_growth > 0.0 ? idx->i8_chunk_growth : (few ? 4.0 : (k <= 128 ? 2.0 : 1.0));
+        // prelude: large batches pay ~1 us per emitted row per query and ~40 us per synchronous chunk: growth 0.6
+        sync_growth = idx->i8_chunk_growth > 0.0 ? idx->i8_chunk_growth
+                      : few ? 4.0 : (nq >= 512 && k <= 128) ? 0.6 : (k <= 128 ? 2.0 : 1.0);
         // about 75 us of scan per pipelined chunk: 4 rounds at 2560 queries (a unit of 256 queries x 256 rows takes
         // ~2 us), more rows for smaller batches, whose scan is bound by HBM (~9M rows per ms)
         min_rows = idx->i8_pipe_min_rows > 0 ? idx->i8_pipe_min_rows
@@ -553,8 +556,23 @@ int search_batch_i8(hac_index* idx, int nq, int nq_pad, const float* q_dev, int 
     const float* center = idx->center_valid ? idx->center : nullptr;
     // threshold exchange with the other shards: on when the caller armed an epoch for this search
     ThrExchange ex = idx->exchange;
-    const bool use_ex = ex.n_peers > 0 && idx->exchange_epoch > 0 && nq <= idx->exchange_capacity && idx->cur_batch < 16;
+    const bool use_ex = ex.n_peers > 0 && idx->exchange_epoch > 0 && (int64_t)nq * kExWords <= idx->exchange_capacity &&
+                        idx->cur_batch < 16;
     ex.tag = (uint32_t)(((uint64_t)idx->exchange_epoch << 4) | (uint64_t)idx->cur_batch);
+    if (use_ex) {
+        // ranks at which every shard publishes its best scores: dense around a shard's fair share ks = ceil(k / G)
+        // (where the global k-th best cuts an evenly mixed shard), sparser up to k (skewed shards)
+        const int G = ex.n_peers + 1, ks = (k + G - 1) / G;
+        const double mult[] = {0.3, 0.5, 0.7, 0.85, 1.0, 1.2, 1.5, 2.0, 3.0, 5.0};
+        std::vector<int> r;
+        for (double m : mult) r.push_back(std::min(k, std::max(1, (int)(m * ks + 0.5))));
+        r.push_back(std::min(k, std::max(1, k / 2)));
+        r.push_back(k);
+        std::sort(r.begin(), r.end());
+        r.erase(std::unique(r.begin(), r.end()), r.end());
+        ex.n_ranks = (int)std::min<size_t>(r.size(), kExRanks);
+        for (int i = 0; i < ex.n_ranks; ++i) ex.ranks[i] = r[r.size() - ex.n_ranks + i];   // keep the largest (k is last)
+    }
     // A: scans (and everything before the first one); B: workers and the final select.  The caller's stream is
     // ordered before A at the start and after A at the end.
     cudaStream_t A = idx->stream, B = idx->side;
@@ -1168,6 +1186,24 @@ int hac_merge_topk_peers_device(int device, int n_lists, int64_t nq, int k, cons
     return HAC_OK;
 }
 
+int hac_enable_peer_access(int device, int peer) {
+    int n_dev = 0;
+    CU(cudaGetDeviceCount(&n_dev));
+    if (device < 0 || device >= n_dev || peer < 0 || peer >= n_dev) return fail(HAC_E_INVALID, "enable_peer_access: no such device");
+    if (device == peer) return HAC_OK;
+    int can = 0;
+    CU(cudaDeviceCanAccessPeer(&can, device, peer));
+    if (!can) return fail(HAC_E_STATE, "enable_peer_access: the devices are not peer-capable");
+    DeviceGuard guard(device);
+    cudaError_t e = cudaDeviceEnablePeerAccess(peer, 0);
+    if (e == cudaErrorPeerAccessAlreadyEnabled) {
+        cudaGetLastError();
+        return HAC_OK;
+    }
+    if (e != cudaSuccess) return fail_cuda(e, "cudaDeviceEnablePeerAccess");
+    return HAC_OK;
+}
+
 int hac_gather_ids_device(int device, const int64_t* table_dev, int64_t table_n, const int64_t* ids_dev, int64_t n,
                           int64_t* out_dev, void* stream) {
     if (!table_dev || !ids_dev || !out_dev || n < 0) return fail(HAC_E_INVALID, "gather: bad argument");
@@ -1203,6 +1239,203 @@ int hac_reciprocal_rank_device(int device, const int64_t* pids_dev, int64_t nq, 
     launch_reciprocal_rank(pids_dev, nq, k, rel_ptr_dev, rel_pids_dev, rr_out_dev, rank_out_dev,
                            static_cast<cudaStream_t>(stream));
     CU(cudaGetLastError());
+    return HAC_OK;
+}
+
+// ---- shard files --------------------------------------------------------------------------------------------------
+namespace {
+constexpr uint64_t kShardAlign = 4096;
+constexpr size_t kShardChunk = 64ull << 20;
+struct ShardSection {
+    uint64_t offset, bytes;
+};
+struct ShardHeader {
+    char magic[8];
+    uint32_t version, d;
+    uint64_t n_rows, cap_rows;
+    uint32_t flags, pad;
+    ShardSection center, rows, i8, tiles;
+    OperandStats stats;
+};
+static_assert(sizeof(ShardHeader) <= kShardAlign, "shard header must fit its page");
+uint64_t shard_pad(uint64_t v) { return (v + kShardAlign - 1) / kShardAlign * kShardAlign; }
+
+struct FileCloser {
+    FILE* f;
+    ~FileCloser() { if (f) fclose(f); }
+};
+struct PinnedPair {
+    void* p[2] = {nullptr, nullptr};
+    cudaEvent_t ev[2] = {nullptr, nullptr};
+    ~PinnedPair() {
+        for (int i = 0; i < 2; ++i) {
+            if (ev[i]) cudaEventDestroy(ev[i]);
+            if (p[i]) cudaFreeHost(p[i]);
+        }
+    }
+};
+
+// device memory -> file at `offset`, staged through one pinned buffer
+int write_section(FILE* f, uint64_t offset, const void* dev, uint64_t bytes, void* pinned, cudaStream_t s) {
+    if (fseeko(f, (off_t)offset, SEEK_SET) != 0) return fail(HAC_E_STATE, "save_shard: seek failed");
+    for (uint64_t o = 0; o < bytes; o += kShardChunk) {
+        const size_t n = (size_t)std::min<uint64_t>(kShardChunk, bytes - o);
+        CU(cudaMemcpyAsync(pinned, static_cast<const uint8_t*>(dev) + o, n, cudaMemcpyDeviceToHost, s));
+        CU(cudaStreamSynchronize(s));
+        if (fwrite(pinned, 1, n, f) != n) return fail(HAC_E_STATE, "save_shard: short write (disk full?)");
+    }
+    return HAC_OK;
+}
+// file section -> device memory: the read of chunk i+1 overlaps the DMA of chunk i
+int read_section(FILE* f, uint64_t offset, void* dev, uint64_t bytes, PinnedPair& pp, cudaStream_t s) {
+    if (fseeko(f, (off_t)offset, SEEK_SET) != 0) return fail(HAC_E_STATE, "load_shard: seek failed");
+    int b = 0;
+    for (uint64_t o = 0; o < bytes; o += kShardChunk, b ^= 1) {
+        const size_t n = (size_t)std::min<uint64_t>(kShardChunk, bytes - o);
+        CU(cudaEventSynchronize(pp.ev[b]));                      // the DMA that last used this buffer has finished
+        if (fread(pp.p[b], 1, n, f) != n) return fail(HAC_E_STATE, "load_shard: short read (truncated file)");
+        CU(cudaMemcpyAsync(static_cast<uint8_t*>(dev) + o, pp.p[b], n, cudaMemcpyHostToDevice, s));
+        CU(cudaEventRecord(pp.ev[b], s));
+    }
+    return HAC_OK;
+}
+}  // namespace
+
+int hac_save_shard(hac_index* idx, const char* path) {
+    if (idx == nullptr || path == nullptr) return fail(HAC_E_INVALID, "save_shard: null argument");
+    if (idx->ntotal == 0) return fail(HAC_E_STATE, "save_shard: the index is empty");
+    DeviceGuard guard(idx->device);
+    cudaStream_t s = idx->stream;
+    CU(cudaStreamSynchronize(s));
+    const int d = idx->d;
+    std::vector<const Segment*> segs;
+    for (const auto& sg : idx->segs)
+        if (sg.n_rows > 0) segs.push_back(&sg);
+    const bool with_i8 = segs.size() == 1 && segs[0]->shadow8 != nullptr;
+    ShardHeader h{};
+    memcpy(h.magic, "HACSHD01", 8);
+    h.version = 1;
+    h.d = (uint32_t)d;
+    h.n_rows = (uint64_t)idx->ntotal;
+    h.cap_rows = (uint64_t)round_up(idx->ntotal, kRowAlign);
+    h.flags = (with_i8 ? 1u : 0u) | (idx->center_valid ? 2u : 0u);
+    uint64_t at = kShardAlign;
+    h.center = {at, idx->center_valid ? (uint64_t)(d + 1) * sizeof(float) : 0};
+    at = shard_pad(at + h.center.bytes);
+    h.rows = {at, h.n_rows * (uint64_t)d * sizeof(float)};
+    at = shard_pad(at + h.rows.bytes);
+    h.i8 = {at, with_i8 ? (uint64_t)shadow8_bytes((int64_t)h.cap_rows, d) : 0};
+    at = shard_pad(at + h.i8.bytes);
+    h.tiles = {at, with_i8 ? (uint64_t)shadow_tiles((int64_t)h.cap_rows) * sizeof(TileQ8) : 0};
+    const uint64_t total = shard_pad(at + h.tiles.bytes);
+    CU(cudaMemcpy(&h.stats, idx->corpus_stats, sizeof(OperandStats), cudaMemcpyDeviceToHost));
+    const std::string tmp = std::string(path) + ".tmp";
+    void* pinned = nullptr;
+    CU(cudaMallocHost(&pinned, kShardChunk));
+    int rc = HAC_OK;
+    {
+        FileCloser fc{fopen(tmp.c_str(), "wb")};
+        if (fc.f == nullptr) {
+            cudaFreeHost(pinned);
+            return fail(HAC_E_STATE, std::string("save_shard: cannot create ") + tmp);
+        }
+        std::vector<uint8_t> page(kShardAlign, 0);
+        memcpy(page.data(), &h, sizeof h);
+        if (fwrite(page.data(), 1, page.size(), fc.f) != page.size()) rc = fail(HAC_E_STATE, "save_shard: short write");
+        if (rc == HAC_OK && h.center.bytes) rc = write_section(fc.f, h.center.offset, idx->center, h.center.bytes, pinned, s);
+        uint64_t row_at = h.rows.offset;
+        for (size_t i = 0; rc == HAC_OK && i < segs.size(); ++i) {
+            const uint64_t nb = (uint64_t)segs[i]->n_rows * d * sizeof(float);
+            rc = write_section(fc.f, row_at, segs[i]->rows, nb, pinned, s);
+            row_at += nb;
+        }
+        if (rc == HAC_OK && with_i8) rc = write_section(fc.f, h.i8.offset, segs[0]->shadow8, h.i8.bytes, pinned, s);
+        if (rc == HAC_OK && with_i8) rc = write_section(fc.f, h.tiles.offset, segs[0]->tiles8, h.tiles.bytes, pinned, s);
+        if (rc == HAC_OK && (fflush(fc.f) != 0 || ftruncate(fileno(fc.f), (off_t)total) != 0))
+            rc = fail(HAC_E_STATE, "save_shard: could not finish the file");
+    }
+    cudaFreeHost(pinned);
+    if (rc != HAC_OK) {
+        remove(tmp.c_str());
+        return rc;
+    }
+    if (rename(tmp.c_str(), path) != 0) return fail(HAC_E_STATE, std::string("save_shard: cannot rename to ") + path);
+    return HAC_OK;
+}
+
+int hac_load_shard(hac_index* idx, const char* path) {
+    if (idx == nullptr || path == nullptr) return fail(HAC_E_INVALID, "load_shard: null argument");
+    if (idx->ntotal != 0) return fail(HAC_E_STATE, "load_shard: the index must be empty (reset it first)");
+    DeviceGuard guard(idx->device);
+    cudaStream_t s = idx->stream;
+    FileCloser fc{fopen(path, "rb")};
+    if (fc.f == nullptr) return fail(HAC_E_INVALID, std::string("load_shard: cannot open ") + path);
+    ShardHeader h{};
+    if (fread(&h, 1, sizeof h, fc.f) != sizeof h || memcmp(h.magic, "HACSHD01", 8) != 0 || h.version != 1)
+        return fail(HAC_E_INVALID, std::string("load_shard: not a version-1 shard file: ") + path);
+    if ((int)h.d != idx->d) return fail(HAC_E_INVALID, "load_shard: dimension of the file differs from the index");
+    if (h.n_rows == 0 || h.n_rows > 0xFFFFFF00ull || h.cap_rows != (uint64_t)round_up((int64_t)h.n_rows, kRowAlign) ||
+        h.rows.bytes != h.n_rows * (uint64_t)h.d * sizeof(float))
+        return fail(HAC_E_INVALID, "load_shard: corrupt header");
+    if (fseeko(fc.f, 0, SEEK_END) != 0 || (uint64_t)ftello(fc.f) < h.rows.offset + h.rows.bytes ||
+        (uint64_t)ftello(fc.f) < h.tiles.offset + h.tiles.bytes)
+        return fail(HAC_E_INVALID, "load_shard: truncated file");
+    const int d = idx->d;
+    const bool file_i8 = (h.flags & 1u) != 0;
+    if (file_i8 && (h.i8.bytes != (uint64_t)shadow8_bytes((int64_t)h.cap_rows, d) ||
+                    h.tiles.bytes != (uint64_t)shadow_tiles((int64_t)h.cap_rows) * sizeof(TileQ8)))
+        return fail(HAC_E_INVALID, "load_shard: int8 sections do not match the row count");
+    // one segment of exactly the file's capacity (an existing larger empty one is kept)
+    for (auto& sg : idx->segs) free_segment(sg);
+    idx->segs.clear();
+    Segment seg;
+    int rc = alloc_segment(idx, (int64_t)h.cap_rows, &seg);
+    if (rc != HAC_OK) return rc;
+    seg.base = 0;
+    idx->segs.push_back(seg);
+    Segment& sg = idx->segs.back();
+    PinnedPair pp;
+    for (int i = 0; i < 2; ++i) {
+        CU(cudaMallocHost(&pp.p[i], kShardChunk));
+        CU(cudaEventCreateWithFlags(&pp.ev[i], cudaEventDisableTiming));
+    }
+    idx->center_valid = false;
+    if ((h.flags & 2u) && idx->center_enabled) {
+        if (h.center.bytes != (uint64_t)(d + 1) * sizeof(float)) return fail(HAC_E_INVALID, "load_shard: corrupt centre section");
+        rc = read_section(fc.f, h.center.offset, idx->center, h.center.bytes, pp, s);
+        if (rc != HAC_OK) return rc;
+        idx->center_valid = true;
+    } else if (h.flags & 2u) {
+        return fail(HAC_E_STATE, "load_shard: the file holds a centred image but center_screen is off on this index");
+    }
+    rc = read_section(fc.f, h.rows.offset, sg.rows, h.rows.bytes, pp, s);
+    if (rc != HAC_OK) return rc;
+    sg.n_rows = (int64_t)h.n_rows;
+    sg.f16_rows = 0;
+    const float* center = idx->center_valid ? idx->center : nullptr;
+    if (sg.shadow8 != nullptr) {
+        if (file_i8) {
+            rc = read_section(fc.f, h.i8.offset, sg.shadow8, h.i8.bytes, pp, s);
+            if (rc == HAC_OK) rc = read_section(fc.f, h.tiles.offset, sg.tiles8, h.tiles.bytes, pp, s);
+            if (rc != HAC_OK) return rc;
+            CU(cudaMemcpyAsync(sg.stats, &h.stats, sizeof(OperandStats), cudaMemcpyHostToDevice, s));
+            // the f16 statistics of the file belong to an image this index has not built: the lazy build recomputes them
+            CU(cudaMemcpyAsync(idx->corpus_stats, &h.stats, sizeof(OperandStats), cudaMemcpyHostToDevice, s));
+        } else {
+            // written from a multi-segment shard: the image is rebuilt from the rows (one conversion pass)
+            launch_convert_tiles_i8(sg.rows, sg.n_rows, d, 0, (int64_t)h.cap_rows / kTileRows, sg.shadow8, sg.tiles8, sg.stats,
+                                    center, s);
+            merge_stats_kernel<<<1, 1, 0, s>>>(idx->corpus_stats, sg.stats);
+        }
+    }
+    if (sg.shadow != nullptr) {                                  // eager f16 image requested ("lazy_f16" = 0)
+        sg.f16_rows = 0;
+        convert_f16_rows(idx, &sg, sg.n_rows, s);
+        merge_stats_kernel<<<1, 1, 0, s>>>(idx->corpus_stats, sg.stats);
+    }
+    CU(cudaGetLastError());
+    idx->ntotal = (int64_t)h.n_rows;
+    CU(cudaStreamSynchronize(s));
     return HAC_OK;
 }
 

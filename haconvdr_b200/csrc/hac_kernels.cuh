@@ -44,16 +44,21 @@ struct CandBuf {
     uint32_t cap;
 };
 
-// Cross-shard threshold exchange (one process per GPU, corpus sharded): every shard publishes, per query, its
-// ceil(k/G)-th best exact score so far into a buffer its peers can read over NVLink; the minimum over all shards is a
-// lower bound on the GLOBAL k-th best (refresh_kernel), to which every shard raises its threshold.  Entries are
-// (tag << 32 | float bits); a reader ignores entries whose tag is not the current search's, so no barrier or reset is
-// needed between searches.
+// Cross-shard threshold exchange (one process per GPU, corpus sharded): every shard publishes, per query, its best
+// exact scores so far at n_ranks fixed ranks into a buffer its peers can read over NVLink.  A word (shard, rank c, L)
+// claims "this shard holds >= c rows scoring >= L"; the largest T at which the claims of all shards add up to k rows
+// is a lower bound on the GLOBAL k-th best (refresh_kernel), to which every shard raises its threshold.  Words are
+// (tag << 32 | float bits), kExWords per query; a reader ignores words whose tag is not the current search's, so no
+// barrier or reset is needed between searches.
+constexpr int kExWords = 16;      // = HAC_EXCHANGE_WORDS_PER_QUERY
+constexpr int kExRanks = 12;      // published ranks per query (<= kExWords)
 struct ThrExchange {
-    unsigned long long* mine;                          // [capacity] this shard's published bounds (peer-readable)
+    unsigned long long* mine;                          // [capacity] this shard's published claims (peer-readable)
     const unsigned long long* peers[kMaxPeerLists];    // the other shards' buffers (peer-mapped device pointers)
     int n_peers;                                       // 0 = no exchange
     uint32_t tag;
+    int n_ranks;
+    int ranks[kExRanks];                               // ascending, 1-based, last = k
 };
 
 struct SegTable {

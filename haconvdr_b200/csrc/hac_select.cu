@@ -133,19 +133,23 @@ __global__ void __launch_bounds__(kRefreshMaxThreads) refresh_kernel(CandBuf cb,
     __shared__ uint32_t s_prefix, s_want;
     __shared__ uint32_t warp_cnt[kRefreshMaxThreads / 32];
     __shared__ uint32_t s_base;
-    __shared__ uint32_t s_peer_key, s_peer_have, s_own_key;
+    __shared__ uint32_t s_top_n, s_best_key;
+    __shared__ uint32_t top[1024];                                  // exchange: keys of this shard's best entries, sorted
+    __shared__ uint32_t claim[kMaxPeerLists * kExRanks];            // exchange: claim[shard * n_ranks + j] = key or 0
     const int q = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int n_threads = blockDim.x;
-    // peers' published bounds (and this shard's own previous one): the loads cross NVLink (~2 us), so they are issued
-    // first and consumed last
-    unsigned long long peer_word = 0ull;
-    if (tid < ex.n_peers)
-        asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(peer_word) : "l"(ex.peers[tid] + q) : "memory");
-    else if (tid == ex.n_peers && ex.n_peers > 0)
-        asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(peer_word) : "l"(ex.mine + q) : "memory");
+    // exchange: thread t < (n_peers + 1) * n_ranks owns the word (shard t / n_ranks, rank slot t % n_ranks); shard n_peers
+    // is this shard itself.  The loads cross NVLink (~2 us), so they are issued first and consumed last.
+    const int n_claims = ex.n_peers > 0 ? (ex.n_peers + 1) * ex.n_ranks : 0;
+    unsigned long long word = 0ull;
+    if (tid < n_claims) {
+        const int sh = tid / ex.n_ranks, j = tid - sh * ex.n_ranks;
+        const unsigned long long* src = (sh < ex.n_peers ? ex.peers[sh] : ex.mine) + (size_t)q * kExWords + j;
+        asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(word) : "l"(src) : "memory");
+    }
     if (tid == 0) {
-        s_peer_key = 0xFFFFFFFFu; s_peer_have = 0u; s_own_key = 0u;
+        s_top_n = 0u; s_best_key = 0u;
         if (clear_count != nullptr) clear_count[q] = 0u;     // the log the preceding rescore consumed is free again
     }
     const uint32_t raw = cb.count[q];
@@ -200,33 +204,64 @@ __global__ void __launch_bounds__(kRefreshMaxThreads) refresh_kernel(CandBuf cb,
         return s_prefix;
     };
     float tau_new = tau[q];
-    if (cnt >= k) tau_new = fmaxf(tau_new, key_float(select_kth((uint32_t)k)));
+    uint32_t kth_key = 0u;                       // key of this shard's k-th best entry (0: fewer than k entries)
+    if (cnt >= k) {
+        kth_key = select_kth((uint32_t)k);
+        tau_new = fmaxf(tau_new, key_float(kth_key));
+    }
     if (ex.n_peers > 0) {
-        // Share rule: if each of the G shards holds at least ks = ceil(k / G) rows scoring >= L_r, then at least k rows
-        // score >= min_r L_r globally.  This shard publishes L = its ks-th best exact score so far; once every peer has
-        // published for this search, min over all shards is a lower bound on the global k-th best - for evenly mixed
-        // shards about the global k-th best itself, where a shard's own k-th best only knows 1/G of the rows.
-        const int ks = (k + ex.n_peers) / (ex.n_peers + 1);
-        float L = -INFINITY;
-        if (cnt >= ks) L = key_float(select_kth((uint32_t)ks));
+        // Claims.  Shard r publishes L_r(c) = its c-th best exact score so far for a few fixed ranks c (ex.ranks, the
+        // same on every shard): "shard r holds >= c rows scoring >= L_r(c)".  For any T, the shards together hold at
+        // least  sum_r max{ c : L_r(c) >= T }  rows scoring >= T; the largest T for which that sum reaches k is a lower
+        // bound on the global k-th best - about the global k-th best itself when the ranks resolve each shard's share,
+        // where a shard's own k-th best only knows 1/G of the rows.  Claims only strengthen during a search and a
+        // missing or stale word is simply no claim, so no ordering between the shards is needed.
         __syncthreads();
-        if ((uint32_t)(peer_word >> 32) == ex.tag) {
-            if (tid < ex.n_peers) {
-                atomicMin(&s_peer_key, float_key(__uint_as_float((uint32_t)peer_word)));
-                atomicAdd(&s_peer_have, 1u);
-            } else if (tid == ex.n_peers) {
-                s_own_key = float_key(__uint_as_float((uint32_t)peer_word));   // what this shard published before
+        for (int i = tid; i < cnt; i += n_threads) {
+            const uint32_t key = keys[i];
+            if (key >= kth_key) {
+                const uint32_t pos = atomicAdd(&s_top_n, 1u);
+                if (pos < 1024u) top[pos] = key;
             }
         }
         __syncthreads();
-        if (s_own_key != 0u) L = fmaxf(L, key_float(s_own_key));        // an earlier claim stays true
-        if (L > -INFINITY) {
-            if (tid == 0) {
-                const unsigned long long w = ((unsigned long long)ex.tag << 32) | (unsigned long long)__float_as_uint(L);
-                asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(ex.mine + q), "l"(w) : "memory");
-            }
-            if (s_peer_have == (uint32_t)ex.n_peers) tau_new = fmaxf(tau_new, fminf(L, key_float(s_peer_key)));
+        const uint32_t m = s_top_n;                 // this shard's entries that can matter: its top-k (ties included)
+        const bool have_top = m <= 1024u;
+        if (have_top) {
+            const int P = next_pow2((int)max(m, 2u));
+            for (int i = (int)m + tid; i < P; i += n_threads) top[i] = 0u;
+            bitonic_sort_desc(top, P);              // (block-wide; starts and ends with a barrier)
         }
+        if (tid < n_claims) {
+            const int sh = tid / ex.n_ranks, j = tid - sh * ex.n_ranks;
+            uint32_t key = 0u;
+            if ((uint32_t)(word >> 32) == ex.tag) key = float_key(__uint_as_float((uint32_t)word));
+            if (sh == ex.n_peers && have_top && m >= (uint32_t)ex.ranks[j]) {
+                const uint32_t now = top[ex.ranks[j] - 1];
+                if (now > key) {                    // an earlier claim stays true; publish only a stronger one
+                    key = now;
+                    const unsigned long long w = ((unsigned long long)ex.tag << 32) |
+                                                 (unsigned long long)__float_as_uint(key_float(key));
+                    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(ex.mine + (size_t)q * kExWords + j), "l"(w)
+                                 : "memory");
+                }
+            }
+            claim[tid] = key;
+        }
+        __syncthreads();
+        if (tid < n_claims && claim[tid] != 0u) {
+            const uint32_t T = claim[tid];          // candidate threshold: does the sum of the claims reach k at T?
+            int total = 0;
+            for (int sh = 0; sh <= ex.n_peers; ++sh) {
+                int best = 0;
+                for (int j = 0; j < ex.n_ranks; ++j)
+                    if (claim[sh * ex.n_ranks + j] >= T) best = max(best, ex.ranks[j]);
+                total += best;
+            }
+            if (total >= k) atomicMax(&s_best_key, T);
+        }
+        __syncthreads();
+        if (s_best_key != 0u) tau_new = fmaxf(tau_new, key_float(s_best_key));
     }
     float thr_new = -INFINITY;
     if (tau_new > -INFINITY) {

@@ -100,57 +100,148 @@ class IndexFlatIP:
 
 
 class ShardedInProcessIndex:
-    """faiss IndexShards equivalent inside one process: rows of every ``add`` are split into
-    contiguous ranges, one per device; ``search`` runs on every device, gathers the G x Q x k
-    candidates on the first device (peer copies over NVLink) and merges them there."""
+    """faiss IndexShards equivalent inside one process (`index_cpu_to_gpu_multiple` with ``co.shard = True``,
+    `/root/reference/src/test_HAConvDR_topiocqa.py:55-66`): rows of every ``add`` are split into contiguous ranges,
+    one per device.  ``search`` is the same protocol as one process per GPU (``haconvdr_b200.sharded``):
+
+    * one persistent host thread and one CUDA stream per shard (the C-ABI calls release the GIL, so the devices run
+      concurrently); queries go up once per device from a reused page-locked buffer;
+    * the shards publish their best scores to each other WHILE they scan (``hac_set_threshold_exchange``: peer-mapped
+      device pointers, ``hac_enable_peer_access``), so every shard rescores only its share of the global top-k;
+    * results stay in per-device buffers; ONE merge kernel on the first device reads all of them in place over NVLink
+      (``hac_merge_topk_peers_device``) - no gather copies, no host round trip before the final D2H."""
 
     def __init__(self, d: int, devices):
+        import torch
+        from concurrent.futures import ThreadPoolExecutor
+        from . import _lib
         self.d = int(d)
         self.devices = [int(v) for v in devices]
         self.shards = [FlatIPIndex(self.d, dev) for dev in self.devices]
-        self._ids = [np.zeros(0, np.int64) for _ in self.devices]
+        self._rows = [[] for _ in self.devices]          # per shard: (global_start, n) of every add
         self.ntotal = 0
         self.is_trained = True
+        self.threshold_exchange = True
+        self._torch = torch
+        self._pool = ThreadPoolExecutor(len(self.devices), thread_name_prefix="hac-shard")
+        self._streams = [torch.cuda.Stream(device=dev) for dev in self.devices]
+        self._events = [torch.cuda.Event() for _ in self.devices]
+        self._peer_ok = True
+        for a in sorted(set(self.devices)):              # kernels on a read (merge) and write (exchange) memory of b
+            for b in sorted(set(self.devices)):
+                if a != b and _lib.lib().hac_enable_peer_access(a, b) != 0:
+                    self._peer_ok = False                # no peer access on this system: gather copies, no exchange
+        self._epoch = 0
+        self._words = None        # per shard: int64 CUDA tensor of exchange words, capacity in queries
+        self._words_cap = 0
+        self._res = None          # per shard: (D [cap] float32, I [cap] int64) result buffers
+        self._res_cap = 0
+        self._q_pinned = None
+        self._out_pinned = None
+
+    def _set_ids(self, g):
+        rows = self._rows[g]
+        if len(rows) == 1:
+            self.shards[g].set_id_base(rows[0][0])
+        else:                                            # several adds: ids are no longer base + local row
+            self.shards[g].set_id_table(np.concatenate([np.arange(s, s + n, dtype=np.int64) for s, n in rows]))
 
     def add(self, x):
         x = np.ascontiguousarray(x, dtype=np.float32)
         assert x.ndim == 2 and x.shape[1] == self.d, "add: expected [n, %d] float32" % self.d
         n, G = x.shape[0], len(self.shards)
         bounds = [(g * n) // G for g in range(G + 1)]
-        for g, sh in enumerate(self.shards):
+
+        def one(g):
             lo, hi = bounds[g], bounds[g + 1]
             if hi > lo:
-                sh.add(x[lo:hi])
-                self._ids[g] = np.concatenate([self._ids[g], np.arange(self.ntotal + lo, self.ntotal + hi)])
-                sh.set_id_table(self._ids[g])
+                self.shards[g].add(x[lo:hi])
+                self._rows[g].append((self.ntotal + lo, hi - lo))
+                self._set_ids(g)
+        list(self._pool.map(one, range(G)))              # the shards copy and convert their rows concurrently
         self.ntotal += n
 
     def reset(self):
         for g, sh in enumerate(self.shards):
             sh.reset()
-            self._ids[g] = np.zeros(0, np.int64)
+            self._rows[g] = []
         self.ntotal = 0
 
+    def _ensure_buffers(self, nq, k):
+        torch = self._torch
+        from ._lib import HAC_EXCHANGE_WORDS_PER_QUERY as WPQ
+        if nq * k > self._res_cap:
+            cap = 1 << 16
+            while cap < nq * k:
+                cap *= 2
+            self._res = [(torch.empty(cap, dtype=torch.float32, device="cuda:%d" % dev),
+                          torch.empty(cap, dtype=torch.int64, device="cuda:%d" % dev)) for dev in self.devices]
+            self._res_cap = cap
+        if self.threshold_exchange and self._peer_ok and nq > self._words_cap:
+            cap = 4096
+            while cap < nq:
+                cap *= 2
+            self._words = [torch.zeros(cap * WPQ, dtype=torch.int64, device="cuda:%d" % dev) for dev in self.devices]
+            for dev in set(self.devices):
+                torch.cuda.synchronize(dev)
+            for g, sh in enumerate(self.shards):
+                sh.set_threshold_exchange(self._words[g].data_ptr(),
+                                          [w.data_ptr() for h, w in enumerate(self._words) if h != g], cap * WPQ)
+            self._words_cap = cap
+
     def search(self, q, k):
-        import torch
-        from concurrent.futures import ThreadPoolExecutor
+        torch = self._torch
+        from .index import merge_topk_peers_device
         q = np.ascontiguousarray(q, dtype=np.float32)
         assert q.ndim == 2 and q.shape[1] == self.d, "search: expected [nq, %d] float32" % self.d
-        dev0 = torch.device("cuda", self.devices[0])
-        q_host = torch.from_numpy(q).pin_memory()
+        nq, k, G = q.shape[0], int(k), len(self.shards)
+        if self._q_pinned is None or self._q_pinned.shape[0] < nq:
+            self._q_pinned = torch.empty((max(nq, 256), self.d), dtype=torch.float32).pin_memory()
+        qp = self._q_pinned[:nq]
+        qp.copy_(torch.from_numpy(q))
+        self._ensure_buffers(nq, k)
+        self._epoch = self._epoch % 0x0FFFFFFF + 1
+        armed = self.threshold_exchange and self._peer_ok and self._words is not None and G > 1
+        outs = [(D[:nq * k].view(nq, k), I[:nq * k].view(nq, k)) for D, I in self._res]
 
-        def one(dev, sh):                      # one host thread per shard, as faiss IndexShards does;
-            with torch.cuda.device(dev):       # the C-ABI call releases the GIL, so the devices run concurrently
-                qd = q_host.to(torch.device("cuda", dev), non_blocking=True)
-                return sh.search(qd, k)
+        def one(g):
+            dev, sh = self.devices[g], self.shards[g]
+            with torch.cuda.device(dev), torch.cuda.stream(self._streams[g]):
+                qd = qp.to(torch.device("cuda", dev), non_blocking=True)
+                sh.set_option("exchange_epoch", self._epoch if armed else 0)
+                try:
+                    sh.search(qd, k, out=outs[g])
+                finally:
+                    sh.set_option("exchange_epoch", 0)
+                self._events[g].record(self._streams[g])
+        list(self._pool.map(one, range(G)))              # re-raises the first shard failure after all have finished
+        dev0 = self.devices[0]
+        with torch.cuda.device(dev0), torch.cuda.stream(self._streams[0]):
+            for ev in self._events[1:]:
+                self._streams[0].wait_event(ev)
+            if self._peer_ok:
+                Dm, Im = merge_topk_peers_device([o[0].data_ptr() for o in outs], [o[1].data_ptr() for o in outs],
+                                                 nq, k, k, torch.device("cuda", dev0))
+            else:
+                Dm, Im = merge_topk_device(torch.stack([o[0].to("cuda:%d" % dev0) for o in outs]),
+                                           torch.stack([o[1].to("cuda:%d" % dev0) for o in outs]), k)
+            if self._out_pinned is None or self._out_pinned[0].numel() < nq * k:
+                n = max(nq * k, 1 << 16)
+                self._out_pinned = (torch.empty(n, dtype=torch.float32).pin_memory(),
+                                    torch.empty(n, dtype=torch.int64).pin_memory())
+            Dh, Ih = self._out_pinned[0][:nq * k].view(nq, k), self._out_pinned[1][:nq * k].view(nq, k)
+            Dh.copy_(Dm, non_blocking=True)
+            Ih.copy_(Im, non_blocking=True)
+            self._streams[0].synchronize()
+        return Dh.numpy().copy(), Ih.numpy().copy()
 
-        with ThreadPoolExecutor(len(self.shards)) as pool:
-            parts = list(pool.map(one, self.devices, self.shards))
-        D = torch.stack([p[0].to(dev0) for p in parts])
-        I = torch.stack([p[1].to(dev0) for p in parts])
-        with torch.cuda.device(dev0):
-            Dm, Im = merge_topk_device(D, I, k)
-        return Dm.cpu().numpy(), Im.cpu().numpy()
+    def stats(self):
+        return [sh.stats() for sh in self.shards]
+
+    def close(self):
+        self._pool.shutdown(wait=True)
+        for sh in self.shards:
+            sh.close()
 
 
 def index_cpu_to_gpu_multiple(vres, vdev, cpu_index, co=None):

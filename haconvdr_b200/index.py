@@ -83,6 +83,14 @@ class FlatIPIndex:
     def reset(self):
         check(self._lib.hac_reset(self._h), "hac_reset")
 
+    # -- shard files (engine-native corpus format: fp32 rows + int8 image + tile constants + centre) -----------
+    def save_shard(self, path: str):
+        check(self._lib.hac_save_shard(self._h, str(path).encode()), "hac_save_shard")
+
+    def load_shard(self, path: str):
+        """Fill this (empty) index from a shard file by plain DMA - no conversion, no statistics pass."""
+        check(self._lib.hac_load_shard(self._h, str(path).encode()), "hac_load_shard")
+
     # -- id translation (replaces passage_embedding2id[I], reference :110) ---------------------------
     def set_id_base(self, base: int):
         check(self._lib.hac_set_id_base(self._h, int(base)), "hac_set_id_base")

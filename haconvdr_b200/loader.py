@@ -245,13 +245,36 @@ def load_block_array(path: str) -> np.ndarray:
         return pickle.load(h)
 
 
+def _native_is_current(nat: str, emb_path: str, embid_path: str) -> bool:
+    """A native file is used only if it cannot be stale: not older than the pickles it was converted from (when
+    they are still there), and with the row count of the current embedding pickle."""
+    try:
+        hdr = read_native_header(nat)
+    except (ValueError, OSError):
+        return False
+    have = [p for p in (emb_path, embid_path) if os.path.isfile(p)]
+    if any(os.path.getmtime(p) > os.path.getmtime(nat) for p in have):
+        return False
+    if os.path.isfile(emb_path):
+        try:
+            if parse_ndarray_pickle_header(emb_path).shape[0] != hdr.n_rows:
+                return False
+        except ValueError:
+            pass                      # an exotic pickle: the mtime check above is all there is
+    return True
+
+
 def find_block(block_dir: str, block_id: int):
-    """(embedding file, loader of its id array) of a block, preferring the native file; None when the block
-    is missing (the reference stops at the first missing block, `:94-95`)."""
+    """(embedding file, loader of its id array) of a block, preferring the native file when it is current (a native
+    file left over from an earlier encoder run must not override regenerated pickles); None when the block is
+    missing (the reference stops at the first missing block, `:94-95`)."""
     nat = native_block_path(block_dir, block_id)
-    if os.path.isfile(nat):
-        return nat, (lambda: load_native_embid(nat))
     emb_path, embid_path = block_paths(block_dir, block_id)
+    if os.path.isfile(nat):
+        if _native_is_current(nat, emb_path, embid_path):
+            return nat, (lambda: load_native_embid(nat))
+        import warnings
+        warnings.warn("%s is stale or unreadable (older than the block pickles, or another row count): ignored" % nat)
     if os.path.isfile(emb_path) and os.path.isfile(embid_path):
         return emb_path, (lambda: load_embid(embid_path))
     return None
@@ -322,6 +345,7 @@ def stream_block_into(index, emb_path: str, chunk_bytes: int = 64 << 20, buffers
     filled = [threading.Semaphore(0) for _ in bufs]
     freed = [threading.Semaphore(1) for _ in bufs]
     err = []
+    stop = threading.Event()
 
     n_readers = max(1, min(8, (os.cpu_count() or 2) // 2))
 
@@ -351,6 +375,8 @@ def stream_block_into(index, emb_path: str, chunk_bytes: int = 64 << 20, buffers
                     for i, (r0, nr) in enumerate(chunks):
                         b = i % len(bufs)
                         freed[b].acquire()
+                        if stop.is_set():                      # the consumer failed: nothing left to read for
+                            return
                         # O_DIRECT wants whole pages: the tail chunk reads into the file's zero padding
                         want = _pad(nr * row_bytes) if use_direct else nr * row_bytes
                         mv = memoryview(bufs[b].view).cast("B")[:want]
@@ -379,7 +405,10 @@ def stream_block_into(index, emb_path: str, chunk_bytes: int = 64 << 20, buffers
             _lib.check(L.hac_add(index._h, nr, bufs[b].ptr), "hac_add")   # returns after the copy completed
             freed[b].release()
     finally:
-        t.join(timeout=5)
+        stop.set()                         # on a consumer-side error the reader is parked on `freed`: wake it up
+        for sem in freed:
+            sem.release()
+        t.join()
         if own:
             for b in bufs:
                 b.free()

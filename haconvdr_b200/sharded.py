@@ -53,7 +53,7 @@ class ShardedFlatIPIndex:
         self._pinned_q = None      # page-locked staging for host queries
         self._pinned_out = None    # page-locked staging for host results
         self.exchange = exchange   # "auto" | "p2p" | "nccl"
-        self._symm = None          # (handle, buffer, nq, k) of the symmetric result buffer
+        self._symm = None          # (handle, buffer, slot_bytes) of the symmetric result buffer (2 slots)
         self._thr = None           # (handle, buffer, capacity) of the symmetric threshold-exchange buffer
         self._epoch = 0            # search counter, identical on all ranks (tags the exchanged thresholds)
         self.threshold_exchange = True   # p2p path: shards share their k-th-best bounds while they scan
@@ -123,26 +123,32 @@ class ShardedFlatIPIndex:
         if prof:
             ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
             ev[0].record()
+        nq_, k_ = int(q.shape[0]), int(k)
         use_p2p = (self.world_size > 1 and self._on_gpu() and self.exchange in ("auto", "p2p")
-                   and self._ensure_symm(int(q.shape[0]), int(k)))
+                   and self._ensure_symm(nq_ * k_ * 12 + 16))
+        err = None                                                 # a failure of THIS rank's local search
         if use_p2p:
             from .index import merge_topk_peers_device
-            hdl, buf, nq, _ = self._symm
+            hdl, buf, slot_bytes = self._symm
+            nq = nq_
             slot = self._step & 1
             self._step += 1
-            d_bytes, i_bytes = nq * k * 4, nq * k * 8
-            slot_bytes = (d_bytes + i_bytes + 255) // 256 * 256
+            d_bytes, i_bytes = (nq * k * 4 + 15) // 16 * 16, nq * k * 8      # ids start 16-byte aligned
             off = slot * slot_bytes
-            D_loc = buf[off:off + d_bytes].view(torch.float32).view(nq, k)
+            D_loc = buf[off:off + nq * k * 4].view(torch.float32).view(nq, k)
             I_loc = buf[off + d_bytes:off + d_bytes + i_bytes].view(torch.int64).view(nq, k)
-            # the shards publish their ceil(k/G)-th best scores to each other while they scan; the minimum bounds the
+            # the shards publish their best scores at a few ranks to each other while they scan; together they bound the
             # GLOBAL k-th best, so every shard emits / rescores ~1/G of the candidates it would alone; its list then
             # holds only its share of the global top-k (fillers behind), which is all the merge below needs
-            self._epoch += 1
+            self._epoch = self._epoch % 0x0FFFFFFF + 1             # 1 .. 2^28 - 1, identical on all ranks
             armed = self.threshold_exchange and self._ensure_thr(nq)
-            self.local.set_option("exchange_epoch", self._epoch if armed else 0)
             try:
+                self.local.set_option("exchange_epoch", self._epoch if armed else 0)
                 self.local.search(q, k, out=(D_loc, I_loc))      # results land in the symmetric buffer
+            except Exception as e:   # noqa: BLE001 - the peers are about to wait for this rank: keep the protocol going
+                err = e
+                D_loc.fill_(-3.4028234663852886e38)
+                I_loc.fill_(-1)
             finally:
                 if armed:
                     self.local.set_option("exchange_epoch", 0)
@@ -159,7 +165,14 @@ class ShardedFlatIPIndex:
                 self.last_phase_ms = {"local_search": ev[0].elapsed_time(ev[1]), "barrier": ev[1].elapsed_time(ev[2]),
                                       "p2p_merge": ev[2].elapsed_time(ev[3])}
         else:
-            D, I = self.local.search(q, k)
+            try:
+                D, I = self.local.search(q, k)
+            except Exception as e:   # noqa: BLE001
+                if self.world_size == 1:
+                    raise
+                err = e
+                D = torch.full((nq_, k_), -3.4028234663852886e38, dtype=torch.float32, device=self._gather_device())
+                I = torch.full((nq_, k_), -1, dtype=torch.int64, device=self._gather_device())
             if prof:
                 ev[1].record()
         if self.world_size > 1 and not use_p2p:
@@ -178,6 +191,13 @@ class ShardedFlatIPIndex:
                 torch.cuda.synchronize()
                 self.last_phase_ms = {"local_search": ev[0].elapsed_time(ev[1]), "all_gather": ev[1].elapsed_time(ev[2]),
                                       "merge": ev[2].elapsed_time(ev[3])}
+        if self.world_size > 1:
+            # every rank went through the same collectives whatever happened locally; now agree on the outcome, so
+            # that a failure on one rank (overflow, out of memory) raises on ALL ranks instead of hanging the others
+            if not self._agree(err is None):
+                if err is not None:
+                    raise err
+                raise RuntimeError("sharded search failed on another rank")
         if as_numpy and torch.is_tensor(D):
             if D.is_cuda:
                 if out_D is not None and out_I is not None:
@@ -201,55 +221,89 @@ class ShardedFlatIPIndex:
             return D.numpy(), I.numpy()
         return D, I
 
-    def _ensure_symm(self, nq: int, k: int) -> bool:
-        """Symmetric-memory result buffer (2 slots) for (nq, k); False if unavailable (-> NCCL path)."""
+    def _agree(self, ok: bool) -> bool:
+        """True iff `ok` on every rank (one tiny all-reduce; every rank must call it at the same point)."""
+        torch, dist = self._torch, self._dist
+        flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device=self._gather_device())
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)
+        return bool(flag.item())
+
+    def _gather_device(self):
+        return self._device() if self._on_gpu() else self._torch.device("cpu")
+
+    def _ensure_symm(self, need_bytes: int) -> bool:
+        """Symmetric-memory result buffer (2 slots), sized by capacity: it only ever grows, so a change of batch size
+        or k (online turns, the k sweep) reuses it.  False if unavailable on ANY rank (-> NCCL path on all ranks)."""
         if self._symm_failed:
             return False
-        if self._symm is not None and self._symm[2] == nq and self._symm[3] == k:
+        if self._symm is not None and self._symm[2] >= need_bytes:
             return True
         torch, dist = self._torch, self._dist
+        slot_bytes = 1 << 20
+        while slot_bytes < need_bytes:
+            slot_bytes *= 2
+        new, why = None, ""
         try:
             import torch.distributed._symmetric_memory as symm_mem
-            slot_bytes = (nq * k * 12 + 255) // 256 * 256
+            if self._symm is not None:
+                # peers may still be reading the old buffer (merge kernel of the previous search)
+                torch.cuda.synchronize(self._device())
+                dist.barrier(group=self.group)
             with torch.cuda.device(self._device()):
                 buf = symm_mem.empty((2 * slot_bytes,), dtype=torch.uint8, device=self._device())
                 hdl = symm_mem.rendezvous(buf, self.group if self.group is not None else dist.group.WORLD)
-            self._symm = (hdl, buf, nq, k)
-            self._step = 0
+            new = (hdl, buf, slot_bytes)
+        except Exception as e:          # noqa: BLE001 - decided together with the other ranks below
+            why = str(e)
+        if self._agree(new is not None):
+            self._symm = new            # `_step` keeps running: slot parity stays aligned across ranks
             return True
-        except Exception as e:          # no symmetric memory on this system: use the NCCL exchange
-            if self.exchange == "p2p":
-                raise
-            self._symm_failed = True
-            import warnings
-            warnings.warn("symmetric memory unavailable (%s); using the NCCL all-gather exchange" % (e,))
-            return False
+        if self.exchange == "p2p":
+            raise RuntimeError("symmetric memory unavailable on at least one rank (%s)" % (why or "peer failure"))
+        self._symm_failed = True
+        self._symm = None
+        import warnings
+        warnings.warn("symmetric memory unavailable (%s); using the NCCL all-gather exchange" % (why or "peer failure"))
+        return False
 
     def _ensure_thr(self, nq: int) -> bool:
-        """Symmetric-memory buffer of per-query threshold words, registered with the local engine."""
+        """Symmetric-memory buffer of per-query threshold words, registered with the local engine
+        (HAC_EXCHANGE_WORDS_PER_QUERY words per query).  Armed on all ranks or on none."""
+        from ._lib import HAC_EXCHANGE_WORDS_PER_QUERY as WPQ
+        if not self.threshold_exchange:
+            return False
         if self._thr is not None and self._thr[2] >= nq:
             return True
         torch, dist = self._torch, self._dist
+        new, why = None, ""
         try:
             import torch.distributed._symmetric_memory as symm_mem
-            cap = max(int(nq), 4096)
+            cap = 4096
+            while cap < nq:
+                cap *= 2
+            if self._thr is not None:
+                torch.cuda.synchronize(self._device())
+                dist.barrier(group=self.group)
             with torch.cuda.device(self._device()):
-                buf = symm_mem.empty((cap,), dtype=torch.int64, device=self._device())
+                buf = symm_mem.empty((cap * WPQ,), dtype=torch.int64, device=self._device())
                 buf.zero_()
                 hdl = symm_mem.rendezvous(buf, self.group if self.group is not None else dist.group.WORLD)
             torch.cuda.synchronize(self._device())
+            new = (hdl, buf, cap)
+        except Exception as e:          # noqa: BLE001 - decided together with the other ranks below
+            why = str(e)
+        if self._agree(new is not None):
+            hdl, buf, cap = new
             hdl.barrier(channel=1)                               # every rank's buffer is zeroed before anyone reads it
             ptrs = list(hdl.buffer_ptrs)
-            mine = ptrs[self.rank]
-            peers = [p for r, p in enumerate(ptrs) if r != self.rank]
-            self.local.set_threshold_exchange(mine, peers, cap)
-            self._thr = (hdl, buf, cap)
+            self.local.set_threshold_exchange(ptrs[self.rank], [p for r, p in enumerate(ptrs) if r != self.rank], cap * WPQ)
+            self._thr = new
             return True
-        except Exception as e:          # not available: every shard keeps its own thresholds (still exact)
-            import warnings
-            warnings.warn("threshold exchange unavailable (%s)" % (e,))
-            self.threshold_exchange = False
-            return False
+        import warnings
+        warnings.warn("threshold exchange unavailable (%s): every shard keeps its own thresholds (still exact)" % (
+            why or "peer failure"))
+        self.threshold_exchange = False        # not available: decided identically on every rank
+        return False
 
     def _on_gpu(self) -> bool:
         return hasattr(self.local, "device") and hasattr(self.local, "_h")

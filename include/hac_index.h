@@ -139,19 +139,28 @@ int hac_merge_topk_peers_device(int device, int n_lists, int64_t nq, int k, cons
 
 /* Cross-shard threshold exchange (one process per GPU, corpus sharded; optional).  A shard alone only knows the k-th
  * best score of its own 1/G of the rows, so it emits and rescores as many candidates as a whole-corpus search would.
- * With the exchange every shard publishes per query L_r = its ceil(k/G)-th best exact score so far into `mine_dev` and
- * reads what its peers published through `peers_dev` (HOST array of n_peers = G-1 <= 15 peer-mapped DEVICE pointers,
- * e.g. symmetric memory read over NVLink): at least k rows score >= min_r L_r globally, so that minimum is a lower
- * bound on the GLOBAL k-th best and every shard raises its threshold to it.  Buffers hold `capacity` u64 entries
- * (tag << 32 | float bits), zero-initialised by the caller.  The exchange is armed per search with
- * hac_set_option(idx, "exchange_epoch", e): e > 0 must be the same on all shards for the same search and different
- * from the previous searches' (stale entries are ignored by tag, no barrier or reset between searches), e = 0
+ * With the exchange every shard publishes, per query, its best exact scores so far at a few fixed ranks c_1 < c_2 < ...
+ * (around k/G, up to k) into `mine_dev` and reads what its peers published through `peers_dev` (HOST array of
+ * n_peers = G-1 <= 15 peer-mapped DEVICE pointers, e.g. symmetric memory read over NVLink).  A word (r, c_j, L) claims
+ * "shard r holds at least c_j rows scoring >= L"; any threshold T for which the claims add up to k rows is a lower
+ * bound on the GLOBAL k-th best, and every shard raises its threshold to the largest such T.  Buffers hold `capacity`
+ * u64 words (tag << 32 | float bits), HAC_EXCHANGE_WORDS_PER_QUERY per query, zero-initialised by the caller.  The
+ * exchange is armed per search with hac_set_option(idx, "exchange_epoch", e): e > 0 must be the same on all shards for
+ * the same search and different from the previous searches' (stale entries are ignored by tag, no barrier or reset
+ * between searches; claims only ever strengthen within a search, so any mix of old and new words is valid), e = 0
  * switches it off.  With it armed a shard's result holds only its candidates for the GLOBAL top-k (possibly fewer
  * than k, the rest filled with -FLT_MAX / -1): it is meant to be followed by hac_merge_topk_*.  Applies to the int8
  * screen (exact-score shortlists).  n_peers = 0 clears the buffers.
  * Replaces nothing in the reference: faiss IndexShards searches its shards independently. */
+#define HAC_EXCHANGE_WORDS_PER_QUERY 16
 int hac_set_threshold_exchange(hac_index* idx, uint64_t* mine_dev, const uint64_t* const* peers_dev, int n_peers,
                                int64_t capacity);
+
+/* Several shards inside ONE process (the faiss IndexShards form, src/test_HAConvDR_topiocqa.py:55-66 with n_gpu > 1):
+ * lets kernels running on `device` load and store memory of `peer` (cudaDeviceEnablePeerAccess; already enabled or
+ * device == peer is not an error), so that hac_merge_topk_peers_device and the threshold exchange can take plain
+ * device pointers of the other GPUs.  With one process per GPU the same is achieved with symmetric memory. */
+int hac_enable_peer_access(int device, int peer);
 
 /* offset -> pid gather on the device (src/test_HAConvDR_topiocqa.py:250): out[i] =
  * table[ids[i]] for ids >= 0, -1 otherwise.  table/ids/out are device pointers. */
@@ -166,6 +175,23 @@ int hac_gather_ids_device(int device, const int64_t* table_dev, int64_t table_n,
  * each query's relevant pids.  rr_out [nq] = 1/rank or 0, rank_out [nq] = 1-based rank or 0.  Device pointers. */
 int hac_reciprocal_rank_device(int device, const int64_t* pids_dev, int64_t nq, int k, const int64_t* rel_ptr_dev,
                                const int64_t* rel_pids_dev, float* rr_out_dev, int32_t* rank_out_dev, void* stream);
+
+/* ---- shard files (engine-native corpus format) -----------------------------------------------------
+ * What `gen_doc_embeddings.py:127-155` would write per shard instead of a dozen pickles: ONE 4 KiB-aligned file with
+ * the fp32 rows, the int8 tensor-core image of the same rows (tiled / swizzled exactly as it lies in HBM), its
+ * per-tile constants, the screen centre and the corpus statistics.
+ * hac_save_shard  writes the resident shard of `idx` (any number of segments; the int8 image is included when the
+ *                 shard is a single segment, else it is rebuilt on load).
+ * hac_load_shard  fills an EMPTY index from such a file by plain reads into page-locked staging + DMA: no pickle walk,
+ *                 no fp32 -> int8 conversion, no statistics pass.  d must match; id base / table are not part of the file.
+ * Layout (little endian; every section starts on a 4 KiB boundary):
+ *   header  4096 B: "HACSHD01", u32 version, u32 d, u64 n_rows, u64 cap_rows, u32 flags (1 = int8 image, 2 = centre),
+ *                   u32 pad, u64 offset / u64 bytes of the sections {centre, rows, int8 image, tile constants},
+ *                   8 x f32 corpus statistics
+ *   centre  (d + 1) f32;  rows  n_rows * d f32;  int8 image  ceil(cap_rows / 128) * (d / 128) * 16 KiB;
+ *   tile constants  ceil(cap_rows / 128) * 4 f32 */
+int hac_save_shard(hac_index* idx, const char* path);
+int hac_load_shard(hac_index* idx, const char* path);
 
 /* ---- pinned staging (loader) -----------------------------------------------------------------
  * Page-locked host buffers the block-pickle loader reads file payloads into, so that

@@ -82,6 +82,9 @@ def compare_topk(ref_D, ref_I, got_D, got_I, rtol: float = 1e-5, ref_scores_of=N
         rI, gI, rD, gD = ref_I[qi], got_I[qi], ref_D[qi], got_D[qi]
         valid = rI >= 0
         nv = int(valid.sum())
+        if nv > 1 and np.any(np.diff(gD[:nv]) > 0):
+            rep.failures.append("q%d: returned scores are not non-increasing" % qi)
+            continue
         if not np.array_equal(gI[nv:], rI[nv:]):
             rep.failures.append("q%d: filler slots differ" % qi)
             continue

@@ -47,17 +47,94 @@ def test_pickle_header_walker(proto, shape):
         assert hdr.shape == shape and hdr.dtype == np.dtype("<f4")
         raw = open(p, "rb").read()[hdr.payload_offset: hdr.payload_offset + hdr.payload_bytes]
         assert np.array_equal(np.frombuffer(raw, np.float32).reshape(shape), a)
-        # numpy 1.x module path, as written by the reference-era stack
-        raw1 = open(p, "rb").read().replace(b"numpy._core.multiarray", b"numpy.core.multiarray")
-        if raw1 != open(p, "rb").read():
-            # the FRAME length changes with the shorter module name; rewrite via pickletools-free patch
-            pass
+        # numpy 1.x module path ("numpy.core.multiarray"), as written by the reference-era stack (numpy 1.22): the
+        # same stream with the module string one byte shorter (length byte / FRAME length patched, so it still
+        # unpickles) must give the same header
+        raw = open(p, "rb").read()
+        if proto >= 4:
+            old_s, new_s = b"\x8c\x16numpy._core.multiarray", b"\x8c\x15numpy.core.multiarray"
+            assert old_s in raw
+            at = raw.index(old_s)
+            raw1 = raw.replace(old_s, new_s, 1)
+            assert raw1[2:3] == b"\x95"                          # FRAME: its length shrinks by the removed byte
+            flen = int.from_bytes(raw1[3:11], "little")
+            if at < 11 + flen:
+                raw1 = raw1[:3] + (flen - 1).to_bytes(8, "little") + raw1[11:]
+        else:
+            raw1 = raw.replace(b"cnumpy._core.multiarray\n", b"cnumpy.core.multiarray\n", 1)
+        assert raw1 != raw and b"numpy.core.multiarray" in raw1
+        p1 = os.path.join(d, "numpy1_era.pb")
+        with open(p1, "wb") as h:
+            h.write(raw1)
+        assert np.array_equal(pickle.load(open(p1, "rb")), a)      # a valid pickle (numpy keeps the old module path alive)
+        hdr1 = loader.parse_ndarray_pickle_header(p1)
+        assert hdr1.shape == shape and hdr1.dtype == hdr.dtype and hdr1.payload_bytes == hdr.payload_bytes
+        assert hdr1.payload_offset == hdr.payload_offset - 1
+        got = open(p1, "rb").read()[hdr1.payload_offset: hdr1.payload_offset + hdr1.payload_bytes]
+        assert np.array_equal(np.frombuffer(got, np.float32).reshape(shape), a)
     with tempfile.TemporaryDirectory() as d:
         p = os.path.join(d, "not_an_array.pb")
         with open(p, "wb") as h:
             pickle.dump({"a": 1}, h, protocol=4)
         with pytest.raises(ValueError):
             loader.parse_ndarray_pickle_header(p)
+
+
+def test_pickle_header_walker_binbytes8_payload_beyond_4gib():
+    """Every real block is 7.68 GB (`/root/reference/gen_doc_embeddings.py:87-88`, 2.5M x 768 fp32): its payload is
+    a BINBYTES8 item.  A sparse 4.3 GB file with the opcode stream of such a pickle (the header of a small ndarray
+    pickle with the shape and the payload item rewritten) must parse, and rows must be found where they are."""
+    n, d = 1_400_001, 768
+    small = np.zeros((2, d), np.float32)
+    raw = pickle.dumps(small, protocol=4)
+    shape_ops = b"K\x02M\x00\x03\x86"                           # (2, 768): BININT1 2, BININT2 768, TUPLE2
+    assert raw.count(shape_ops) == 1
+    big_shape = b"J" + int(n).to_bytes(4, "little", signed=True) + b"M\x00\x03\x86"
+    item = b"B" + (2 * d * 4).to_bytes(4, "little")              # BINBYTES u32 length
+    assert raw.count(item) == 1
+    head = raw[:raw.index(item)].replace(shape_ops, big_shape)
+    payload_bytes = n * d * 4
+    assert payload_bytes > 1 << 32
+    head += b"\x8e" + payload_bytes.to_bytes(8, "little")        # BINBYTES8 u64 length
+    row = np.arange(d, dtype=np.float32) + 0.5
+    with tempfile.TemporaryDirectory() as tmp:
+        p = os.path.join(tmp, "passage_emb_block_0.pb")
+        with open(p, "wb") as h:
+            h.write(head)
+            h.truncate(len(head) + payload_bytes + 64)           # sparse: only the touched pages exist
+        fd = os.open(p, os.O_RDWR)
+        try:
+            os.pwrite(fd, row.tobytes(), len(head) + (n - 1) * d * 4)     # the last row, beyond 4 GiB
+        finally:
+            os.close(fd)
+        hdr = loader.parse_ndarray_pickle_header(p)
+        assert hdr.shape == (n, d) and hdr.dtype == np.dtype("<f4")
+        assert hdr.payload_offset == len(head) and hdr.payload_bytes == payload_bytes
+        mm = np.memmap(p, dtype="<f4", mode="r", offset=hdr.payload_offset, shape=(n, d))
+        assert np.array_equal(mm[n - 1], row) and not mm[n - 2].any()
+        del mm
+        with open(p, "r+b") as h:                                 # a truncated block is refused, not half-loaded
+            h.truncate(len(head) + payload_bytes - 1)
+        with pytest.raises(ValueError):
+            loader.parse_ndarray_pickle_header(p)
+
+
+def test_stale_native_block_does_not_override_regenerated_pickles():
+    rng = np.random.default_rng(3)
+    a = rng.standard_normal((50, 64)).astype(np.float32)
+    with tempfile.TemporaryDirectory() as d:
+        write_blocks(d, [a])
+        nat = loader.convert_block_to_native(d, 0)
+        assert loader.find_block(d, 0)[0] == nat                  # current: preferred
+        write_blocks(d, [a[:40]])                                 # the encoder ran again: other row count, newer
+        t = os.path.getmtime(nat) + 10
+        os.utime(os.path.join(d, "passage_emb_block_0.pb"), (t, t))
+        with pytest.warns(UserWarning):
+            found = loader.find_block(d, 0)
+        assert found[0].endswith(".pb") and found[1]().shape == (40,)
+        os.remove(os.path.join(d, "passage_emb_block_0.pb"))      # pickles gone: the native file is all there is
+        os.remove(os.path.join(d, "passage_embid_block_0.pb"))
+        assert loader.find_block(d, 0)[0] == nat
 
 
 @pytest.mark.parametrize("name", GOLDEN_MERGE_CASES)

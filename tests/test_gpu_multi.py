@@ -153,7 +153,8 @@ def test_threshold_exchange_and_peer_merge_two_shards_one_device(nq, n, k, concu
     split = n // 2 + 17
     shards = _two_shards(x, split)
     dev = torch.device("cuda", 0)
-    cap = 4096
+    from haconvdr_b200._lib import HAC_EXCHANGE_WORDS_PER_QUERY
+    cap = 512 * HAC_EXCHANGE_WORDS_PER_QUERY          # u64 words: 16 per query
     words = [torch.zeros(cap, dtype=torch.int64, device=dev) for _ in range(2)]
     for r, sh in enumerate(shards):
         sh.set_threshold_exchange(words[r].data_ptr(), [words[1 - r].data_ptr()], cap)

@@ -759,3 +759,63 @@ def test_default_path_gemv_batches_by_four():
     D, I = idx.search(q, 10)
     assert idx.stats()["path"] == hb.HAC_PATH_GEMV
     _check(q, x, 10, D, I, also_fp32_oracle=False)
+
+
+def test_shard_file_round_trip_is_a_plain_dma_reload(tmp_path):
+    """hac_save_shard / hac_load_shard: one file per shard with the fp32 rows, the int8 image, its tile
+    constants and the centre.  A reloaded index answers bitwise like the one that was saved - on every scan path -
+    without running a conversion kernel; multi-segment shards are saved without the image and rebuilt on load."""
+    hb = _engine()
+    rng = np.random.default_rng(77)
+    mu = rng.standard_normal(768).astype(np.float32)
+    x = (0.5 * mu + rng.standard_normal((41003, 768))).astype(np.float32)       # a centre that is not zero
+    q = (0.5 * mu + rng.standard_normal((140, 768))).astype(np.float32)
+    src = hb.FlatIPIndex(768, reserve=41003)
+    src.add(x[:20000])
+    src.add(x[20000:])
+    D0, I0 = src.search(q, 100)
+    st0 = src.stats()
+    assert st0["path"] == hb.HAC_PATH_I8
+    path = str(tmp_path / "shard0.hacs")
+    src.save_shard(path)
+    import os
+    assert os.path.getsize(path) % 4096 == 0 and os.path.getsize(path) >= 41003 * 768 * 5
+    dst = hb.FlatIPIndex(768)
+    dst.load_shard(path)
+    assert dst.ntotal == 41003 and dst.stats()["bytes_shadow"] == 0 and dst.stats()["bytes_i8"] > 0
+    D1, I1 = dst.search(q, 100)
+    st1 = dst.stats()
+    assert st1["path"] == hb.HAC_PATH_I8 and st1["retries"] == 0
+    assert np.array_equal(I1, I0) and np.array_equal(D1, D0)
+    assert st1["candidates_emitted"] == st0["candidates_emitted"]              # the very same image and thresholds
+    for path_id in (hb.HAC_PATH_MMA, hb.HAC_PATH_GEMV):
+        Dp, Ip = dst.search(q[:4], 100, path=path_id)
+        assert np.array_equal(Ip, I0[:4]) and np.array_equal(Dp, D0[:4])
+    _check(q, x, 100, D1, I1, also_fp32_oracle=False)
+    dst.add(x[:500])                                                           # a loaded shard keeps growing
+    assert dst.ntotal == 41503
+    D2, I2 = dst.search(q, 10)
+    _check(q, np.concatenate([x, x[:500]], 0), 10, D2, I2, also_fp32_oracle=False)
+    with pytest.raises(RuntimeError):
+        dst.load_shard(path)                                                   # not empty
+    other_d = hb.FlatIPIndex(256)
+    with pytest.raises(ValueError):
+        other_d.load_shard(path)
+    # several segments: rows only, image rebuilt on load
+    ragged = hb.FlatIPIndex(768)
+    ragged.add(x[:9000])
+    ragged.add(x[9000:30001])
+    path2 = str(tmp_path / "shard_ragged.hacs")
+    ragged.save_shard(path2)
+    back = hb.FlatIPIndex(768)
+    back.load_shard(path2)
+    Dr, Ir = ragged.search(q, 100)
+    Db, Ib = back.search(q, 100)
+    assert np.array_equal(Ib, Ir) and np.array_equal(Db, Dr)
+    # no int8 image wanted on the loading side: the sections are skipped
+    plain = hb.FlatIPIndex(768)
+    plain.set_option("build_i8", 0)
+    plain.load_shard(path)
+    Dq, Iq = plain.search(q, 100)
+    assert plain.stats()["path"] == hb.HAC_PATH_MMA and plain.stats()["bytes_i8"] == 0
+    assert np.array_equal(Iq, I0) and np.array_equal(Dq, D0)

@@ -128,3 +128,58 @@ def test_share_rule_bounds_the_global_kth_best():
             assert bound <= kth
             if split == "even" and n >= 50 * k:
                 assert np.sum(s >= bound) <= 4 * k     # close to the k-th best for mixed shards
+
+
+def _exchange_ranks(k, G):
+    """The ranks every shard publishes (mirror of search_batch_i8 in csrc/hac_api.cu)."""
+    ks = -(-k // G)
+    r = [min(k, max(1, int(m * ks + 0.5))) for m in (0.3, 0.5, 0.7, 0.85, 1.0, 1.2, 1.5, 2.0, 3.0, 5.0)]
+    r += [min(k, max(1, k // 2)), k]
+    return sorted(set(r))[-12:]
+
+
+def _claims_bound(shards, ranks, k):
+    """refresh_kernel's rule: the largest published score T at which sum_r max{c : L_r(c) >= T} >= k (None if none)."""
+    claims = []
+    for x in shards:
+        top = np.sort(x)[::-1]
+        claims.append([(c, top[c - 1]) for c in ranks if len(top) >= c])
+    best = None
+    for T in sorted({v for cl in claims for _, v in cl}, reverse=True):
+        total = sum(max([c for c, v in cl if v >= T], default=0) for cl in claims)
+        if total >= k:
+            best = T
+            break
+    return best
+
+
+def test_multi_rank_claims_bound_the_global_kth_best_and_beat_the_share_rule():
+    """Cross-shard exchange of round 2: every shard publishes its best scores at a few ranks; the largest T at which
+    the claims add up to k rows never exceeds the global k-th best (valid for ANY split of the rows), is at least as
+    tight as the single-rank share rule, and for evenly mixed shards admits far fewer rows above it."""
+    rng = np.random.default_rng(12)
+    gain = []
+    for G, k, n in ((2, 100, 5000), (8, 100, 40000), (8, 10, 999), (3, 7, 50), (16, 100, 30000), (4, 1, 100), (8, 128, 20000)):
+        ranks = _exchange_ranks(k, G)
+        assert ranks[-1] == k and len(ranks) <= 12 and all(1 <= c <= k for c in ranks)
+        ks = -(-k // G)
+        assert ks in ranks or G == 1
+        for trial in range(6):
+            s = rng.standard_normal(n).astype(np.float32)
+            if trial % 2 == 0:
+                shards = np.array_split(rng.permutation(s), G)
+            else:
+                order = np.sort(s)[::-1]
+                cuts = np.sort(rng.choice(np.arange(1, n - 1), G - 1, replace=False))
+                shards = np.split(order, cuts)
+            kth = np.sort(s)[::-1][k - 1]
+            T = _claims_bound(shards, ranks, k)
+            assert T is None or T <= kth                           # no claim set reaching k = no bound (still valid)
+            if T is not None and all(len(x) >= ks for x in shards):
+                share = min(np.sort(x)[::-1][ks - 1] for x in shards)
+                assert T >= share
+                if trial % 2 == 0 and n >= 200 * k:
+                    gain.append((np.sum(s >= share), np.sum(s >= T), k))
+    # evenly mixed shards: rows above the bound (what a shard still has to rescore) shrink towards k
+    assert np.mean([b / k for _, b, k in gain]) < np.mean([a / k for a, _, k in gain])
+    assert np.mean([b / k for _, b, k in gain]) < 1.6
