@@ -545,11 +545,11 @@ def run_ours(args):
                                  "path": index.local.stats()["path"], "scan_ms": st_k["scan_ms"],
                                  "rescored_pairs": st_k["candidates_rescored"]}
             secondary["ksweep"] = sweep
+        roofline = roofline_tensor(h, st_avg, ms_per_step, args.queries, i8)     # (max over ranks: every rank takes part)
         if rank != 0:
             if world > 1:
                 dist.destroy_process_group()
             return
-        roofline = roofline_tensor(h, st_avg, ms_per_step, args.queries, i8)
         cpu_baseline = None
         if not args.no_cpu_baseline and world == 1:
             from haconvdr_b200.index import synth_rows_device as srd
@@ -639,11 +639,12 @@ def run_ours(args):
                              "e2e_queries_per_s": args.queries / e2e_s, "path": stl["path"], "scan_ms": st_k["scan_ms"],
                              "rescored_pairs": st_k["candidates_rescored"], "launches": st_k["kernel_launches"],
                              "parity_ok": par["ok"], "d2h_bytes": args.queries * k * 12}
+        s100 = sweep["100"]
+        roofline = roofline_tensor(h, {"scan_ms": s100["scan_ms"]}, s100["ms_per_step"], args.queries, True)   # all ranks
         if rank != 0:
             if world > 1:
                 dist.destroy_process_group()
             return
-        s100 = sweep["100"]
         config.update({"ks": list(SWEEP_KS), "l2": "inputs larger than L2"})
         line.update({
             "value": s100["queries_per_s"], "ms_per_step": s100["ms_per_step"],
@@ -651,7 +652,7 @@ def run_ours(args):
             "e2e": {"value": s100["e2e_queries_per_s"], "unit": "queries/s", "h2d_bytes_per_step": int(h.q_host.nbytes),
                     "d2h_bytes_per_step": int(args.queries * 100 * 12)},
             "gpu_launches": int(s100["launches"] * args.steps),
-            "roofline": roofline_tensor(h, {"scan_ms": s100["scan_ms"]}, s100["ms_per_step"], args.queries, True),
+            "roofline": roofline,
             "cpu_baseline": None, "clocks": clocks,
             "parity_check": {"ok": all(v["parity_ok"] for v in sweep.values()), "queries_checked": 16 * len(SWEEP_KS),
                              "order_checked": True, "how": "per k: fp64 re-scoring + prefix consistency across k"},

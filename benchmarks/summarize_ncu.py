@@ -4,6 +4,9 @@
   launches <csv>            `ncu --metrics gpu__time_duration.sum --clock-control none --csv` launch list ->
                             per-kernel time and share of the LAST complete search in the list (a search starts at
                             init_search_kernel and ends at final_select_kernel)
+  traffic <csv> [out.json] the same launch list taken with `--metrics gpu__time_duration.sum,dram__bytes_read.sum,
+                            dram__bytes_write.sum`: DRAM bytes read / written per kernel over the LAST complete search
+                            (what bench.py reports as `roofline.traffic_step`), printed and optionally written as JSON
   raw <csv> [kernel-regex]  `ncu -i x.ncu-rep --page raw --csv` -> the roofline-relevant metrics of the first
                             matching kernel, one `name [unit] = value` line each
 """
@@ -56,6 +59,55 @@ def launches(path):
     print("%-44s      %12.1f us" % ("total (one search, launches %d..%d)" % (start, end), total / 1e3))
 
 
+def _value(r):
+    v = float(r["Metric Value"].replace(",", ""))
+    u = r["Metric Unit"]
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "ns": 1.0, "nsecond": 1.0, "us": 1e3, "usecond": 1e3,
+             "ms": 1e6, "msecond": 1e6, "s": 1e9, "second": 1e9}
+    return v * scale.get(u, 1.0)
+
+
+def traffic(path, out_json=None):
+    import json
+    per_launch = {}
+    for r in rows_of(path):
+        key = int(r["ID"])
+        ent = per_launch.setdefault(key, {"name": short(r["Kernel Name"])})
+        ent[r["Metric Name"]] = _value(r)
+    ids = sorted(per_launch)
+    names = [per_launch[i]["name"] for i in ids]
+    ends = [i for i, n in enumerate(names) if n.startswith("final_select_kernel")]
+    if not ends:
+        sys.exit("no final_select_kernel in the launch list")
+    end = ends[-1]
+    start = max(i for i, n in enumerate(names[:end]) if n.startswith("init_search_kernel"))
+    agg, order = {}, []
+    for i in ids[start:end + 1]:
+        e = per_launch[i]
+        n = e["name"]
+        if n not in agg:
+            agg[n] = {"launches": 0, "time_us": 0.0, "dram_read_bytes": 0.0, "dram_write_bytes": 0.0}
+            order.append(n)
+        agg[n]["launches"] += 1
+        agg[n]["time_us"] += e.get("gpu__time_duration.sum", 0.0) / 1e3
+        agg[n]["dram_read_bytes"] += e.get("dram__bytes_read.sum", 0.0)
+        agg[n]["dram_write_bytes"] += e.get("dram__bytes_write.sum", 0.0)
+    tot_r = sum(v["dram_read_bytes"] for v in agg.values())
+    tot_w = sum(v["dram_write_bytes"] for v in agg.values())
+    tot_t = sum(v["time_us"] for v in agg.values())
+    for n in order:
+        v = agg[n]
+        print("%-44s x%-3d %10.1f us  read %9.3f GB  write %8.3f GB" % (n[:44], v["launches"], v["time_us"],
+                                                                       v["dram_read_bytes"] / 1e9, v["dram_write_bytes"] / 1e9))
+    print("%-44s      %10.1f us  read %9.3f GB  write %8.3f GB" % ("total (one search)", tot_t, tot_r / 1e9, tot_w / 1e9))
+    if out_json:
+        with open(out_json, "w") as f:
+            json.dump({"what": "DRAM bytes of every kernel of ONE search (ncu --metrics dram__bytes_read.sum,"
+                               "dram__bytes_write.sum,gpu__time_duration.sum --clock-control none; serialised launches)",
+                       "dram_read_bytes": tot_r, "dram_write_bytes": tot_w, "dram_bytes": tot_r + tot_w,
+                       "kernel_time_us_serialised": tot_t, "per_kernel": {n: agg[n] for n in order}}, f, indent=1)
+
+
 def raw(path, pattern):
     rows = rows_of(path)
     # --page raw --csv: one row per launch, one column per metric; row 0 after the header holds the units
@@ -72,9 +124,11 @@ def raw(path, pattern):
 
 
 if __name__ == "__main__":
-    if len(sys.argv) < 3 or sys.argv[1] not in ("launches", "raw"):
+    if len(sys.argv) < 3 or sys.argv[1] not in ("launches", "raw", "traffic"):
         sys.exit(__doc__)
     if sys.argv[1] == "launches":
         launches(sys.argv[2])
+    elif sys.argv[1] == "traffic":
+        traffic(sys.argv[2], sys.argv[3] if len(sys.argv) > 3 else None)
     else:
         raw(sys.argv[2], sys.argv[3] if len(sys.argv) > 3 else ".")

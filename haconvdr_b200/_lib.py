@@ -33,7 +33,7 @@ class HacStats(ctypes.Structure):
         ("screen_err_max", ctypes.c_float), ("scan_ms", ctypes.c_float), ("total_ms", ctypes.c_float),
         ("ntotal", ctypes.c_int64), ("bytes_fp32", ctypes.c_int64), ("bytes_shadow", ctypes.c_int64),
         ("bytes_i8", ctypes.c_int64), ("n_sync_chunks", ctypes.c_int32), ("pipelined", ctypes.c_int32),
-        ("tail_ms", ctypes.c_float), ("reserved0", ctypes.c_float),
+        ("tail_ms", ctypes.c_float), ("warm_rows", ctypes.c_int32),
     ]
 
     def as_dict(self):

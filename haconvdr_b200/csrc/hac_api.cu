@@ -138,6 +138,22 @@ struct hac_index {
     int i8_b_slots = 0;                     // measured: 54.1 ms of scan with the tile resident (7 or 8 slots) vs 34.8 ms streamed
     bool i8_pipeline = false;               // measured on one GPU: 47.1 ms pipelined vs 46.2 ms synchronous (the scan is power-bound: co-running rescores slow it by what they save)
     int i8_pipe_dist = 2;                   // 1 = every scan waits for the previous chunk's worker (no overlap)
+    // pipelined chunks: SMs the scan grid may occupy (0 = all).  The SMs it leaves free run the workers (rescore +
+    // refresh of the previous chunk) at full occupancy instead of one squeezed-in CTA per scan SM.
+    int i8_scan_sms = 0;
+    // Warm start of the int8 search: an f16 image of the FIRST rows of the first segment (a few hundred MB).  A search
+    // first runs the f16 screen over those rows - its margin is ~20x tighter, so it finds their exact top-k with ~10x
+    // fewer rescored pairs than the int8 screen's loose early chunks (which emit k * e^(m8*z/sigma) pairs per query for
+    // every e-fold of rows seen, whatever the chunk size) - and the int8 scan of the remaining rows starts with an
+    // exact threshold.  -1 = automatic size, 0 = off, > 0 = rows.
+    int64_t i8_warm_rows = -1;
+    struct WarmSlab {
+        uint8_t* shadow = nullptr;
+        OperandStats* stats = nullptr;
+        const float* src = nullptr;         // rows pointer of the segment the image was built from
+        int64_t cap_rows = 0, rows = 0;     // rows [0, rows) are present
+    } warm;
+    bool i8_scan_exclusive = false;         // pipelined chunks: the scan CTA claims its SM's whole shared memory
     double i8_pipe_growth = 0.125;          // pipelined chunks: max(i8_pipe_min_rows, growth * rows seen so far)
     int64_t i8_pipe_min_rows = 0;           // 0 = by batch size (about 75 us of scan per chunk)
     // the f16 image (rows*d*2 bytes) is only read by the f16 screen (k > i8_auto_max_k, int8 overflow fallback, forced
@@ -237,6 +253,61 @@ void convert_f16_rows(hac_index* idx, Segment* seg, int64_t end, cudaStream_t s)
     launch_convert_rows(src, m, n_pad, d, seg->shadow, r0, seg->stats, nullptr, nullptr, idx->drop_bits_x,
                         idx->center_valid ? idx->center : nullptr, s);
     seg->f16_rows = end;
+}
+
+// rows the int8 search scans with the f16 screen first (multiple of kRowAlign; 0 = no warm start)
+int64_t pick_warm_rows(const hac_index* idx, int nq, int k) {
+    if (idx->segs.empty() || idx->i8_warm_rows == 0 || k > 128) return 0;
+    const int64_t have = idx->segs[0].n_rows / kRowAlign * kRowAlign;
+    int64_t want = idx->i8_warm_rows;
+    if (want < 0) {
+        // tensor-bound batches only: an f16 row costs twice an int8 row, every e-fold of warm rows saves one e-fold of
+        // loosely filtered int8 emission (optimum ~4e5 rows whatever the corpus size, flat around it)
+        if (nq < 256) return 0;
+        want = std::min<int64_t>(393216, std::max<int64_t>(32768, idx->ntotal / 32));
+        if (idx->ntotal < 8 * want) return 0;
+    }
+    want = std::min(want / kRowAlign * kRowAlign, have);
+    return want >= 4096 ? want : 0;
+}
+
+void free_warm(hac_index* idx) {
+    if (idx->warm.shadow) cudaFree(idx->warm.shadow);
+    if (idx->warm.stats) cudaFree(idx->warm.stats);
+    idx->warm = hac_index::WarmSlab{};
+}
+
+// f16 image of rows [0, want) of the first segment (built once per corpus, extended when `want` grows)
+int ensure_warm(hac_index* idx, int64_t want, cudaStream_t s) {
+    auto& wm = idx->warm;
+    Segment& s0 = idx->segs[0];
+    if (wm.src != s0.rows) wm.rows = 0;                      // another corpus (reset / reload): rebuild
+    if (wm.cap_rows < want) {
+        if (wm.shadow) cudaFree(wm.shadow);
+        wm.shadow = nullptr;
+        wm.cap_rows = 0;
+        wm.rows = 0;
+        const int64_t cap = round_up(want, kRowAlign);
+        cudaError_t e = cudaMalloc(&wm.shadow, (size_t)shadow_bytes(cap, idx->d));
+        if (e != cudaSuccess) return fail_cuda(e, "warm-start image allocation");
+        wm.cap_rows = cap;
+    }
+    if (wm.stats == nullptr) CU(cudaMalloc(&wm.stats, sizeof(OperandStats)));
+    if (wm.rows == 0) CU(cudaMemsetAsync(wm.stats, 0, sizeof(OperandStats), s));
+    if (wm.rows < want) {
+        Segment view;                                        // the slab seen as a segment of its own
+        view.rows = s0.rows;
+        view.shadow = wm.shadow;
+        view.stats = wm.stats;
+        view.f16_rows = wm.rows;
+        view.cap_rows = wm.cap_rows;
+        view.n_rows = want;
+        convert_f16_rows(idx, &view, want, s);
+        wm.rows = want;
+        wm.src = s0.rows;
+        CU(cudaGetLastError());
+    }
+    return HAC_OK;
 }
 
 // the f16 screen is about to run: allocate / complete the f16 image of every segment (no-op when it is up to date)
@@ -457,8 +528,9 @@ struct ChunkPlan {
     int dist;          // the scan waits for the worker of chunk (index - dist)
 };
 
-void plan_chunks_i8(const hac_index* idx, int nq, int nq_pad, int k, uint32_t log_cap, std::vector<ChunkPlan>& out,
-                    int* n_sync) {
+// start_row: rows [0, start_row) of the first segment have been searched already (warm start); max_chunks: event budget
+void plan_chunks_i8(const hac_index* idx, int nq, int nq_pad, int k, uint32_t log_cap, int64_t start_row, int max_chunks,
+                    std::vector<ChunkPlan>& out, int* n_sync) {
     const bool few = nq <= 4 && k <= 128;
     const int n_qtiles = nq_pad / kTileRows;
     const int cg = (idx->i8_cta_group == 2 && n_qtiles % 2 == 0) ? 2 : 1;
@@ -494,10 +566,10 @@ void plan_chunks_i8(const hac_index* idx, int nq, int nq_pad, int k, uint32_t lo
     for (int attempt = 0; attempt < 8; ++attempt) {
         out.clear();
         *n_sync = 0;
-        int64_t rows_done = 0;
+        int64_t rows_done = start_row;
         for (size_t si = 0; si < idx->segs.size(); ++si) {
             const Segment& seg = idx->segs[si];
-            int64_t r = 0;
+            int64_t r = si == 0 ? start_row : 0;
             while (r < seg.n_rows) {
                 const bool piped = pipeline && rows_done >= min_rows;
                 int64_t size;
@@ -517,7 +589,7 @@ void plan_chunks_i8(const hac_index* idx, int nq, int nq_pad, int k, uint32_t lo
                 r = r1;
             }
         }
-        if ((int)out.size() <= kMaxChunks) return;
+        if ((int)out.size() <= max_chunks) return;
         pipe_growth *= 1.5;                  // too many chunks for the event pool: coarser schedule
         sync_growth *= 1.5;
     }
@@ -549,10 +621,13 @@ int search_batch_i8(hac_index* idx, int nq, int nq_pad, const float* q_dev, int 
         lg[i].emitted = cb.emitted;
     }
     HostReadback* hr = static_cast<HostReadback*>(w.host_pinned);
+    // warm start: the first rows are searched with the f16 screen (tight margin), the int8 scan continues behind them
+    constexpr int kMaxWarmChunks = 8;
+    const int64_t warm_rows = pick_warm_rows(idx, nq, k);
     std::vector<ChunkPlan> plan;
     int n_sync = 0;
-    plan_chunks_i8(idx, nq, nq_pad, k, log_cap, plan, &n_sync);
-    if ((int)plan.size() > kMaxChunks) return fail(HAC_E_STATE, "int8 search: chunk plan exceeds the event pool");
+    plan_chunks_i8(idx, nq, nq_pad, k, log_cap, warm_rows, kMaxChunks - kMaxWarmChunks, plan, &n_sync);
+    if ((int)plan.size() > kMaxChunks - kMaxWarmChunks) return fail(HAC_E_STATE, "int8 search: chunk plan exceeds the event pool");
     const float* center = idx->center_valid ? idx->center : nullptr;
     // threshold exchange with the other shards: on when the caller armed an epoch for this search
     ThrExchange ex = idx->exchange;
@@ -590,11 +665,67 @@ int search_batch_i8(hac_index* idx, int nq, int nq_pad, const float* q_dev, int 
         launch_query_shift(q_dev, nq, nq_pad, d, center, w.q_shift, A);
         ++launches;
     }
-    launch_margins(nullptr, nullptr, nullptr, nullptr, d, w.margin, w.scalars + 1, nq, A);   // refresh margin = 0 (exact scores)
-    launch_margins_i8(w.q_consts, idx->corpus_stats, d, w.q_norm /*scratch*/, w.scalars + 1, nq, A);   // statistics
     cudaMemsetAsync(w.scalars + 2, 0, sizeof(float), A);
     cudaMemsetAsync(w.counters + 1, 0, sizeof(unsigned long long), A);
+    int n_warm = 0;                        // scan launches of the warm start (they take the first event pairs)
+    if (warm_rows > 0) {
+        rc = ensure_warm(idx, warm_rows, A);
+        if (rc != HAC_OK) return rc;
+        // f16 query image and the f16 screen margin against the slab's own statistics
+        cudaMemsetAsync(w.q_stats, 0, sizeof(OperandStats), A);
+        launch_absmax(q_dev, (int64_t)nq * d, w.scalars + 0, A);
+        launch_pick_scale(w.q_stats, w.scalars + 0, 0, A);
+        launch_convert_rows(q_dev, nq, nq_pad, d, w.q_shadow, 0, w.q_stats, w.q_norm, w.q_err, idx->drop_bits_q, nullptr, A);
+        launch_margins(w.q_norm, w.q_err, idx->warm.stats, center ? center + d : nullptr, d, w.margin, w.scalars + 1, nq, A);
+        launches += 4;
+        const Segment& s0 = idx->segs[0];
+        const double growth = std::min(idx->chunk_growth, std::max(1.0, (double)cap / (8.0 * k)));
+        int64_t r = 0;
+        while (r < warm_rows) {
+            int64_t size = r == 0 ? cap / 2 : (int64_t)(growth * (double)r);
+            size = std::max<int64_t>(kRowAlign, size / kRowAlign * kRowAlign);
+            int64_t r1 = std::min(warm_rows, r + size);
+            if (n_warm == kMaxWarmChunks - 1) r1 = warm_rows;
+            cudaEventRecord(idx->ev[2 + 2 * n_warm], A);
+            MmaScanArgs a;
+            a.q_shadow = w.q_shadow;
+            a.x_shadow = idx->warm.shadow;
+            a.q_stats = w.q_stats;
+            a.x_stats = idx->warm.stats;
+            a.x_tiles = nullptr;
+            a.q_consts = nullptr;
+            a.q_shift = center != nullptr ? w.q_shift : nullptr;
+            a.center_norm = nullptr;
+            a.thr = w.thr;
+            a.d = d;
+            a.tile_major = idx->scan_tile_major < 0 ? 0 : idx->scan_tile_major;
+            a.n_qtiles = nq_pad / kTileRows;
+            a.ct0 = r / kRowAlign;
+            a.ct1 = (r1 + kRowAlign - 1) / kRowAlign;
+            a.seg_rows = r1;
+            a.row_id_base = s0.base;
+            a.cb = cb;
+            CU(launch_scan_mma(a, idx->sm_count, idx->mma_cta_group, A));
+            cudaEventRecord(idx->ev[3 + 2 * n_warm], A);
+            launch_refresh(cb, k, w.margin, w.tau, w.thr, nq, A);
+            launches += 2;
+            ++n_warm;
+            r = r1;
+        }
+        // the survivors' exact scores replace their screen scores; the exact phase starts from them
+        cudaMemsetAsync(cb.sorted, 0, (size_t)nq_pad * sizeof(uint32_t), A);
+        launch_rescore_new(cb, q_dev, d, segs, nq, w.scalars + 2, w.counters + 1, A);
+        launch_fill_f32(w.tau, -INFINITY, nq, A);          // the k-th best SCREEN score is no bound on exact scores
+        launches += 2;
+    }
+    launch_margins(nullptr, nullptr, nullptr, nullptr, d, w.margin, w.scalars + 1, nq, A);   // refresh margin = 0 (exact scores)
+    launch_margins_i8(w.q_consts, idx->corpus_stats, d, w.q_norm /*scratch*/, w.scalars + 1, nq, A);   // statistics
     launches += 4;
+    if (warm_rows > 0) {
+        // tau = k-th best exact score of the warm rows = the first emission threshold of the int8 scan
+        launch_refresh(cb, k, w.margin, w.tau, w.thr, nq, A, use_ex ? &ex : nullptr);
+        ++launches;
+    }
     const int n_chunks = (int)plan.size();
     int waited = -1;                       // A has already been ordered after the workers of chunks <= waited
     for (int i = 0; i < n_chunks; ++i) {
@@ -605,7 +736,7 @@ int search_batch_i8(hac_index* idx, int nq, int nq_pad, const float* q_dev, int 
             CU(cudaStreamWaitEvent(A, idx->wdone[dep], 0));
             waited = dep;
         }
-        cudaEvent_t ev_start = idx->ev[2 + 2 * i], ev_stop = idx->ev[3 + 2 * i];
+        cudaEvent_t ev_start = idx->ev[2 + 2 * (n_warm + i)], ev_stop = idx->ev[3 + 2 * (n_warm + i)];
         cudaEventRecord(ev_start, A);
         MmaScanArgs a;
         a.q_shadow = w.q_shadow8;
@@ -629,7 +760,12 @@ int search_batch_i8(hac_index* idx, int nq, int nq_pad, const float* q_dev, int 
         a.seg_rows = std::min(seg.n_rows, ch.r1);
         a.row_id_base = seg.base;
         a.cb = lg[i & 1];
-        CU(launch_scan_mma_i8(a, idx->sm_count, idx->i8_cta_group, A));
+        int scan_sms = idx->sm_count;
+        if (ch.dist >= 2) {
+            if (idx->i8_scan_sms > 0) scan_sms = std::min(scan_sms, idx->i8_scan_sms);
+            a.exclusive = idx->i8_scan_exclusive ? 1 : 0;
+        }
+        CU(launch_scan_mma_i8(a, scan_sms, idx->i8_cta_group, A));
         CU(cudaEventRecord(ev_stop, A));
         // worker of the chunk, on the side stream
         CU(cudaStreamWaitEvent(B, ev_stop, 0));
@@ -638,6 +774,10 @@ int search_batch_i8(hac_index* idx, int nq, int nq_pad, const float* q_dev, int 
         launch_refresh(cb, k, w.margin, w.tau, w.thr, nq, B, use_ex ? &ex : nullptr, lg[i & 1].count, /*small_cta=*/true);
         CU(cudaEventRecord(idx->wdone[i], B));
         launches += 3;
+    }
+    if (n_chunks == 0) {                   // the whole shard was the warm start: B has not been ordered behind A yet
+        CU(cudaEventRecord(idx->ev_join, A));
+        CU(cudaStreamWaitEvent(B, idx->ev_join, 0));
     }
     launch_final_select(cb, k, nq, idx->id_table, idx->id_base, D_dev, I_dev, /*use_score=*/true, B);
     ++launches;
@@ -653,9 +793,10 @@ int search_batch_i8(hac_index* idx, int nq, int nq_pad, const float* q_dev, int 
         CU(cudaStreamWaitEvent(s, idx->ev_out, 0));
     }
     CU(cudaStreamSynchronize(A));
-    st.n_chunks = n_chunks;
-    st.n_sync_chunks = n_sync;
+    st.n_chunks = n_chunks + n_warm;
+    st.n_sync_chunks = n_sync + n_warm;
     st.pipelined = n_sync < n_chunks ? 1 : 0;
+    st.warm_rows = (int32_t)warm_rows;
     st.kernel_launches = launches;
     st.candidates_emitted = (int64_t)hr->emitted;
     st.candidates_rescored = (int64_t)hr->rescored;
@@ -663,12 +804,12 @@ int search_batch_i8(hac_index* idx, int nq, int nq_pad, const float* q_dev, int 
     st.screen_err_max = hr->screen_err_max;
     float ms = 0.f, scan_ms = 0.f, tail_ms = 0.f;
     cudaEventElapsedTime(&ms, idx->ev[0], idx->ev[1]);
-    for (int i = 0; i < n_chunks; ++i) {
+    for (int i = 0; i < n_chunks + n_warm; ++i) {
         float t = 0.f;
         cudaEventElapsedTime(&t, idx->ev[2 + 2 * i], idx->ev[3 + 2 * i]);
         scan_ms += t;
     }
-    if (n_chunks > 0) cudaEventElapsedTime(&tail_ms, idx->ev[3 + 2 * (n_chunks - 1)], idx->ev[1]);
+    if (n_chunks + n_warm > 0) cudaEventElapsedTime(&tail_ms, idx->ev[3 + 2 * (n_chunks + n_warm - 1)], idx->ev[1]);
     st.total_ms = ms;
     st.scan_ms = scan_ms;
     st.tail_ms = tail_ms;
@@ -712,6 +853,7 @@ int search_batch(hac_index* idx, int nq, const float* q_dev, int k, float* D_dev
     st.retries = 0;
     st.n_sync_chunks = 0;
     st.pipelined = 0;
+    st.warm_rows = 0;
     st.tail_ms = 0.f;
 
     SegTable segs;
@@ -1015,6 +1157,7 @@ int hac_destroy(hac_index* idx) {
     DeviceGuard guard(idx->device);
     cudaDeviceSynchronize();
     for (auto& s : idx->segs) free_segment(s);
+    free_warm(idx);
     free_workspace(idx->ws);
     if (idx->id_table) cudaFree(idx->id_table);
     if (idx->corpus_stats) cudaFree(idx->corpus_stats);
@@ -1103,6 +1246,7 @@ int hac_reset(hac_index* idx) {
         CU(cudaMemsetAsync(s.stats, 0, sizeof(OperandStats), idx->stream));
     }
     CU(cudaMemsetAsync(idx->corpus_stats, 0, sizeof(OperandStats), idx->stream));
+    idx->warm.rows = 0;                      // the warm-start image belongs to the rows that are gone
     if (idx->id_table) {
         cudaFree(idx->id_table);
         idx->id_table = nullptr;
@@ -1388,6 +1532,7 @@ int hac_load_shard(hac_index* idx, const char* path) {
     // one segment of exactly the file's capacity (an existing larger empty one is kept)
     for (auto& sg : idx->segs) free_segment(sg);
     idx->segs.clear();
+    idx->warm.rows = 0;
     Segment seg;
     int rc = alloc_segment(idx, (int64_t)h.cap_rows, &seg);
     if (rc != HAC_OK) return rc;
@@ -1492,6 +1637,17 @@ int hac_set_option(hac_index* idx, const char* name, int64_t value) {
         idx->i8_b_slots = (int)value;
         return HAC_OK;
     }
+    if (strcmp(name, "i8_warm_rows") == 0) {
+        if (value < -1 || value > (int64_t)1 << 26) return fail(HAC_E_INVALID, "i8_warm_rows out of range");
+        idx->i8_warm_rows = value;
+        return HAC_OK;
+    }
+    if (strcmp(name, "i8_scan_sms") == 0) {
+        if (value < 0 || (value > 0 && value < 2)) return fail(HAC_E_INVALID, "i8_scan_sms must be 0 (all) or >= 2");
+        idx->i8_scan_sms = (int)value;
+        return HAC_OK;
+    }
+    if (strcmp(name, "i8_scan_exclusive") == 0) { idx->i8_scan_exclusive = value != 0; return HAC_OK; }
     if (strcmp(name, "i8_pipe_dist") == 0) {
         if (value != 1 && value != 2) return fail(HAC_E_INVALID, "i8_pipe_dist must be 1 or 2");
         idx->i8_pipe_dist = (int)value;

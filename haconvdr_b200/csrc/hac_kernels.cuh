@@ -122,6 +122,7 @@ bool launch_rescore_log(CandBuf lg, CandBuf cb, const float* q, int d, SegTable 
 void launch_final_select(CandBuf cb, int k, int nq, const int64_t* id_table, int64_t id_base, float* D,
                          int64_t* I, bool use_score, cudaStream_t s);
 void launch_fill_empty(float* D, int64_t* I, int64_t n, cudaStream_t s);
+void launch_fill_f32(float* p, float value, int n, cudaStream_t s);
 // careful mode: undo the appends since the last refresh / cut the rescored shortlist to its exact top-k
 void launch_rollback(CandBuf cb, int nq, cudaStream_t s);
 void launch_exact_compact(CandBuf cb, int k, const float* margin, float* tau, float* thr, int nq, cudaStream_t s);
@@ -145,6 +146,7 @@ struct MmaScanArgs {
     int n_qtiles;
     int tile_major;         // 1: every CTA walks whole corpus tiles (all query tiles back to back); 0: units striped
     int b_slots = 0;        // int8 CTA pairs: > 0 = keep the corpus tile resident in a ring of this many 16 KiB slots (7-8)
+    int exclusive = 0;      // int8 CTA pairs: 1 = claim the SM's whole shared memory (no co-resident worker CTAs)
     int64_t ct0, ct1;       // 256-row tiles of the segment
     int64_t seg_rows;       // valid rows of the segment
     uint32_t row_id_base;

@@ -673,6 +673,14 @@ void launch_fill_empty(float* D, int64_t* I, int64_t n, cudaStream_t s) {
     fill_empty_kernel<<<(int)std::min<int64_t>((n + 255) / 256, 1184), 256, 0, s>>>(D, I, n);
 }
 
+__global__ void fill_f32_kernel(float* p, float value, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = value;
+}
+void launch_fill_f32(float* p, float value, int n, cudaStream_t s) {
+    if (n > 0) fill_f32_kernel<<<(n + 255) / 256, 256, 0, s>>>(p, value, n);
+}
+
 // ---------------------------------------------------------------------------------------------
 // k-way merge of n_lists SORTED lists per query (shards or corpus blocks) on the device, by rank
 // computation instead of a sort: the final position of an item is its position in its own list plus,

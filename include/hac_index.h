@@ -67,7 +67,7 @@ typedef struct hac_stats {
     int32_t n_sync_chunks;        /* chunks of the last search whose scan waited for the previous chunk's thresholds */
     int32_t pipelined;            /* 1 = the last search overlapped rescoring with the scans (int8 screen) */
     float   tail_ms;              /* device time between the end of the last scan and the end of the last search */
-    float   reserved0;
+    int32_t warm_rows;            /* int8 screen: leading rows the last search scanned with the f16 screen first ("i8_warm_rows") */
 } hac_stats;
 
 /* ---- lifetime ------------------------------------------------------------------------------
@@ -219,7 +219,24 @@ int hac_pinned_free(void* host);
  *                    k <= 128 and any batch size by default (its shortlist grows with k); 0 = never
  *   "f16_drop_bits_corpus" / "f16_drop_bits_queries"  low mantissa bits of the f16 image forced to zero
  *                    (0..8, default 3 / 0): sparser operands draw less tensor-core power, the screen margin
- *                    is computed from the actual rounding error so exactness is unaffected; corpus: empty index only */
+ *                    is computed from the actual rounding error so exactness is unaffected; corpus: empty index only
+ *   "lazy_f16"       -1 (default) = the f16 image is built on first use exactly when the int8 image exists, 0 / 1 = forced
+ *   "i8_chunk_growth_x100"  int8 screen, synchronous chunks: chunk = growth * rows seen so far, in percent (0 = by batch
+ *                    size and k)
+ *   "i8_pipeline"    1 = pipelined int8 search: after a synchronous prelude the scans run back to back and the rescore +
+ *                    refresh of chunk i run on a side stream beside the scan of chunk i+1 (HAC_I8_PIPELINE sets the
+ *                    default of new handles); "i8_pipe_dist" (1 / 2), "i8_pipe_growth_x1000", "i8_pipe_min_rows" shape
+ *                    its chunk schedule
+ *   "i8_warm_rows"   int8 screen warm start: the first rows of the shard are searched with the f16 screen (an f16 image
+ *                    of just those rows, ~0.6 GB at the default size), whose margin is ~20x tighter, so the int8 scan
+ *                    of the rest starts from an exact threshold instead of emitting through many loosely filtered
+ *                    early chunks; -1 (default) = automatic (tensor-bound batches on shards >= 8x the slab), 0 = off,
+ *                    > 0 = that many rows
+ *   "i8_scan_sms"    pipelined chunks: SMs the scan grid may occupy (0 = all); the SMs left free run the workers
+ *   "i8_scan_exclusive"  pipelined chunks: 1 = the scan CTA claims its SM's whole shared memory, so that no worker CTA
+ *                    is placed beside it
+ *   "i8_b_slots"     int8 CTA-pair scan: 0 (default) = both operands streamed per unit, 6..8 = the corpus tile stays
+ *                    resident in a ring of this many 16 KiB shared-memory slots across its query groups */
 int hac_set_option(hac_index* idx, const char* name, int64_t value);
 
 /* ---- introspection --------------------------------------------------------------------------- */

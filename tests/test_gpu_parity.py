@@ -711,6 +711,62 @@ def test_int8_pipelined_search_equals_the_synchronous_one(nq, n, k):
     assert np.array_equal(Id, I0) and np.array_equal(Dd, D0)
 
 
+@pytest.mark.parametrize("nq,n,k,warm", [(300, 150000, 100, 16384), (130, 90001, 10, 4096), (520, 70000, 1, 65536),
+                                         (64, 60000, 100, 8192), (3, 50000, 100, 8192)])
+def test_int8_warm_start_changes_nothing_but_the_work(nq, n, k, warm):
+    """Warm start of the int8 search: the first rows go through the f16 screen (tight margin), the int8 scan continues
+    behind them from an exact threshold.  Results are bitwise those of the plain int8 search and of the f16 screen,
+    with fewer rescored pairs; the slab follows resets, appends and a first segment smaller than the request."""
+    hb = _engine()
+    rng = np.random.default_rng(nq + n + k + warm)
+    x = rng.standard_normal((n, 768), dtype=np.float32)
+    q = rng.standard_normal((nq, 768), dtype=np.float32)
+    idx = hb.FlatIPIndex(768)
+    idx.reserve(n)
+    idx.add(x[: n // 2 + 7])
+    idx.add(x[n // 2 + 7:])
+    idx.set_option("i8_warm_rows", 0)
+    D0, I0 = idx.search(q, k, path=hb.HAC_PATH_I8)
+    st0 = idx.stats()
+    assert st0["path"] == hb.HAC_PATH_I8 and st0["retries"] == 0 and st0["warm_rows"] == 0, st0
+    _check(q, x, k, D0, I0, also_fp32_oracle=False)
+    for pipeline in (0, 1):
+        idx.set_option("i8_pipeline", pipeline)
+        idx.set_option("i8_pipe_min_rows", 4096 if pipeline else 0)
+        idx.set_option("i8_warm_rows", warm)
+        for _ in range(2):
+            D1, I1 = idx.search(q, k, path=hb.HAC_PATH_I8)
+            st = idx.stats()
+            assert st["path"] == hb.HAC_PATH_I8 and st["retries"] == 0, st
+            assert st["warm_rows"] == min(warm, n // 256 * 256), st
+            assert st["screen_err_max"] <= st["margin_max"], st
+            assert np.array_equal(I1, I0) and np.array_equal(D1, D0), (pipeline, st)
+        if nq >= 64 and pipeline == 0:
+            assert st["candidates_rescored"] < st0["candidates_rescored"], (st, st0)
+    idx.set_option("i8_pipeline", 0)
+    Dm, Im = idx.search(q, k, path=hb.HAC_PATH_MMA)
+    assert np.array_equal(Im, I0) and np.array_equal(Dm, D0)
+    # appended rows: the slab (first rows) stays valid, the new rows are scanned by the int8 screen
+    extra = rng.standard_normal((5000, 768), dtype=np.float32)
+    idx.add(extra)
+    x2 = np.concatenate([x, extra])
+    D2, I2 = idx.search(q, k, path=hb.HAC_PATH_I8)
+    assert idx.stats()["warm_rows"] > 0
+    _check(q, x2, k, D2, I2, also_fp32_oracle=False)
+    # reset + another corpus in ragged segments (no reserve): the slab is rebuilt and limited to the first segment
+    idx.reset()
+    y = rng.standard_normal((40000, 768), dtype=np.float32)
+    idx.add(y[:9000])
+    idx.add(y[9000:])
+    D3, I3 = idx.search(q, k, path=hb.HAC_PATH_I8)
+    st3 = idx.stats()
+    assert st3["path"] == hb.HAC_PATH_I8 and st3["retries"] == 0 and 0 < st3["warm_rows"] <= 40000, st3
+    _check(q, y, k, D3, I3, also_fp32_oracle=False)
+    idx.set_option("i8_warm_rows", 0)
+    D4, I4 = idx.search(q, k, path=hb.HAC_PATH_I8)
+    assert np.array_equal(I4, I3) and np.array_equal(D4, D3)
+
+
 def test_f16_image_is_built_lazily_and_kept_up_to_date():
     """With the int8 image present the f16 image (2 bytes per element of HBM) does not exist until a search needs the
     f16 screen; once built, later adds keep it complete; `lazy_f16 = 0` builds it on add as before."""
