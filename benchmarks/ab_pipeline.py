@@ -30,17 +30,9 @@ VARIANTS = [
     ("sync_w384k_g35", {"i8_warm_rows": 393216, "i8_chunk_growth_x100": 35}),
     ("sync_w384k_g100", {"i8_warm_rows": 393216, "i8_chunk_growth_x100": 100}),
     ("pipe_w384k", {"i8_pipeline": 1, "i8_warm_rows": 393216}),
-    ("pipe_w384k_s132x", {"i8_pipeline": 1, "i8_warm_rows": 393216, "i8_scan_sms": 132, "i8_scan_exclusive": 1}),
-    ("pipe_x", {"i8_pipeline": 1, "i8_scan_exclusive": 1}),
-    ("pipe_s140", {"i8_pipeline": 1, "i8_scan_sms": 140}),
-    ("pipe_s140x", {"i8_pipeline": 1, "i8_scan_sms": 140, "i8_scan_exclusive": 1}),
-    ("pipe_s132", {"i8_pipeline": 1, "i8_scan_sms": 132}),
-    ("pipe_s132x", {"i8_pipeline": 1, "i8_scan_sms": 132, "i8_scan_exclusive": 1}),
-    ("pipe_s124x", {"i8_pipeline": 1, "i8_scan_sms": 124, "i8_scan_exclusive": 1}),
-    ("pipe_s116x", {"i8_pipeline": 1, "i8_scan_sms": 116, "i8_scan_exclusive": 1}),
 ]
 DEFAULTS = {"i8_pipeline": 0, "i8_pipe_growth_x1000": 125, "i8_pipe_min_rows": 0, "i8_pipe_dist": 2, "i8_b_slots": 0,
-            "i8_chunk_growth_x100": 0, "i8_scan_sms": 0, "i8_scan_exclusive": 0, "i8_warm_rows": 0}
+            "i8_chunk_growth_x100": 0, "i8_warm_rows": 0}
 
 
 def main():

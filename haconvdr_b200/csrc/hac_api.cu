@@ -136,11 +136,11 @@ struct hac_index {
     // int8 CTA-pair scan: ring slots (16 KiB) that keep the corpus tile resident across its query groups (0 = off: both
     // operands streamed per unit).  8 leaves no room for a co-resident worker CTA; the pipelined search uses 7.
     int i8_b_slots = 0;                     // measured: 54.1 ms of scan with the tile resident (7 or 8 slots) vs 34.8 ms streamed
-    bool i8_pipeline = false;               // measured on one GPU: 47.1 ms pipelined vs 46.2 ms synchronous (the scan is power-bound: co-running rescores slow it by what they save)
+    // measured on one GPU: 47.1 ms pipelined vs 46.2 ms synchronous (the scan is power-bound: co-running rescores slow
+    // it by what they save).  Giving the workers SMs of their own does not help either: the scan slows in proportion
+    // to the SMs it gives up (132 of 148 SMs: 45.4 vs 40.8 ms of scan, profiles/r02_ab_warm_start_and_scan_sms.jsonl).
+    bool i8_pipeline = false;
     int i8_pipe_dist = 2;                   // 1 = every scan waits for the previous chunk's worker (no overlap)
-    // pipelined chunks: SMs the scan grid may occupy (0 = all).  The SMs it leaves free run the workers (rescore +
-    // refresh of the previous chunk) at full occupancy instead of one squeezed-in CTA per scan SM.
-    int i8_scan_sms = 0;
     // Warm start of the int8 search: an f16 image of the FIRST rows of the first segment (a few hundred MB).  A search
     // first runs the f16 screen over those rows - its margin is ~20x tighter, so it finds their exact top-k with ~10x
     // fewer rescored pairs than the int8 screen's loose early chunks (which emit k * e^(m8*z/sigma) pairs per query for
@@ -153,7 +153,6 @@ struct hac_index {
         const float* src = nullptr;         // rows pointer of the segment the image was built from
         int64_t cap_rows = 0, rows = 0;     // rows [0, rows) are present
     } warm;
-    bool i8_scan_exclusive = false;         // pipelined chunks: the scan CTA claims its SM's whole shared memory
     double i8_pipe_growth = 0.125;          // pipelined chunks: max(i8_pipe_min_rows, growth * rows seen so far)
     int64_t i8_pipe_min_rows = 0;           // 0 = by batch size (about 75 us of scan per chunk)
     // the f16 image (rows*d*2 bytes) is only read by the f16 screen (k > i8_auto_max_k, int8 overflow fallback, forced
@@ -264,7 +263,9 @@ int64_t pick_warm_rows(const hac_index* idx, int nq, int k) {
         // tensor-bound batches only: an f16 row costs twice an int8 row, every e-fold of warm rows saves one e-fold of
         // loosely filtered int8 emission (optimum ~4e5 rows whatever the corpus size, flat around it)
         if (nq < 256) return 0;
-        want = std::min<int64_t>(393216, std::max<int64_t>(32768, idx->ntotal / 32));
+        // measured at 25.7M x 2514 (profiles/r02_ab_warm_start_and_scan_sms.jsonl): 128k rows 46.2 ms, 256k 44.4, 384k 44.8,
+        // 768k 44.0 against 48.0 without; rescored pairs 19.9M -> 9.6M
+        want = std::min<int64_t>(786432, std::max<int64_t>(32768, idx->ntotal / 32));
         if (idx->ntotal < 8 * want) return 0;
     }
     want = std::min(want / kRowAlign * kRowAlign, have);
@@ -558,6 +559,8 @@ void plan_chunks_i8(const hac_index* idx, int nq, int nq_pad, int k, uint32_t lo
         // 0.6 -> 19.9M, 47.2 ms; 0.35 -> 18.5M, 46.9 ms); small batches keep few chunks (each costs ~40 us)
         sync_growth = idx->i8_chunk_growth > 0.0 ? idx->i8_chunk_growth
                       : few ? 4.0
+                      : (nq >= 512 && k <= 128 && start_row >= (1 << 17)) ? 0.35      // behind a warm start: few chunks, all long
+                      : (nq >= 512 && k <= 128 && start_row > 0) ? 0.5
                       : (nq >= 512 && k <= 128 && idx->ntotal >= (8ll << 20)) ? 0.6
                       : (nq >= 512 && k <= 128 && idx->ntotal >= (1ll << 20)) ? 1.0
                       : (k <= 128 ? 2.0 : 1.0);
@@ -760,12 +763,7 @@ int search_batch_i8(hac_index* idx, int nq, int nq_pad, const float* q_dev, int 
         a.seg_rows = std::min(seg.n_rows, ch.r1);
         a.row_id_base = seg.base;
         a.cb = lg[i & 1];
-        int scan_sms = idx->sm_count;
-        if (ch.dist >= 2) {
-            if (idx->i8_scan_sms > 0) scan_sms = std::min(scan_sms, idx->i8_scan_sms);
-            a.exclusive = idx->i8_scan_exclusive ? 1 : 0;
-        }
-        CU(launch_scan_mma_i8(a, scan_sms, idx->i8_cta_group, A));
+        CU(launch_scan_mma_i8(a, idx->sm_count, idx->i8_cta_group, A));
         CU(cudaEventRecord(ev_stop, A));
         // worker of the chunk, on the side stream
         CU(cudaStreamWaitEvent(B, ev_stop, 0));
@@ -863,7 +861,10 @@ int search_batch(hac_index* idx, int nq, const float* q_dev, int k, float* D_dev
         segs.rows[i] = idx->segs[i].rows;
     }
     if (path == HAC_PATH_I8) {
-        const int rc8 = search_batch_i8(idx, nq, nq_pad, q_dev, k, D_dev, I_dev, s, segs);
+        // CTA pairs take two query tiles per unit: an odd tile count (8209 queries = 65 tiles) would fall back to the
+        // single-CTA scan (measured 12 % slower), so one all-padding tile is added instead (it never emits)
+        const int nq_pad8 = (idx->i8_cta_group == 2 && nq > kTileRows) ? (int)round_up(nq, 2 * kTileRows) : nq_pad;
+        const int rc8 = search_batch_i8(idx, nq, nq_pad8, q_dev, k, D_dev, I_dev, s, segs);
         if (rc8 <= 0) return rc8;
         idx->i8_overflowed = true;
         path = HAC_PATH_MMA;            // shortlist overflow: redo with the f16 screen (and its careful mode)
@@ -1147,6 +1148,24 @@ int hac_create(int d, int device, hac_index** out) {
     if (e != cudaSuccess) {
         hac_destroy(idx);
         return fail_cuda(e, "create");
+    }
+    // HAC_OPTIONS="name=value,name=value": hac_set_option defaults for every new handle (A/B runs through callers
+    // that only know the faiss names); an unknown name or bad value fails the create
+    if (const char* opts = getenv("HAC_OPTIONS")) {
+        std::string all(opts);
+        size_t pos = 0;
+        while (pos < all.size()) {
+            size_t end = all.find(',', pos);
+            if (end == std::string::npos) end = all.size();
+            const std::string item = all.substr(pos, end - pos);
+            pos = end + 1;
+            if (item.empty()) continue;
+            const size_t eq = item.find('=');
+            if (eq == std::string::npos || hac_set_option(idx, item.substr(0, eq).c_str(), atoll(item.c_str() + eq + 1)) != HAC_OK) {
+                hac_destroy(idx);
+                return fail(HAC_E_INVALID, std::string("create: bad HAC_OPTIONS item '") + item + "'");
+            }
+        }
     }
     *out = idx;
     return HAC_OK;
@@ -1642,12 +1661,6 @@ int hac_set_option(hac_index* idx, const char* name, int64_t value) {
         idx->i8_warm_rows = value;
         return HAC_OK;
     }
-    if (strcmp(name, "i8_scan_sms") == 0) {
-        if (value < 0 || (value > 0 && value < 2)) return fail(HAC_E_INVALID, "i8_scan_sms must be 0 (all) or >= 2");
-        idx->i8_scan_sms = (int)value;
-        return HAC_OK;
-    }
-    if (strcmp(name, "i8_scan_exclusive") == 0) { idx->i8_scan_exclusive = value != 0; return HAC_OK; }
     if (strcmp(name, "i8_pipe_dist") == 0) {
         if (value != 1 && value != 2) return fail(HAC_E_INVALID, "i8_pipe_dist must be 1 or 2");
         idx->i8_pipe_dist = (int)value;

@@ -146,7 +146,6 @@ struct MmaScanArgs {
     int n_qtiles;
     int tile_major;         // 1: every CTA walks whole corpus tiles (all query tiles back to back); 0: units striped
     int b_slots = 0;        // int8 CTA pairs: > 0 = keep the corpus tile resident in a ring of this many 16 KiB slots (7-8)
-    int exclusive = 0;      // int8 CTA pairs: 1 = claim the SM's whole shared memory (no co-resident worker CTAs)
     int64_t ct0, ct1;       // 256-row tiles of the segment
     int64_t seg_rows;       // valid rows of the segment
     uint32_t row_id_base;

@@ -54,7 +54,6 @@ struct Cfg {
     static constexpr int kStageBytes = kABytes + kBBytes;
     static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 512 /*barriers*/;
 };
-constexpr int kSmemExclusive = 227 * 1024;                 // the opt-in maximum per CTA on sm_100
 constexpr int bres_smem_bytes(int b_slots) { return (kASlots + b_slots) * kPieceBytes + 1024 + 512; }
 
 struct Barriers {
@@ -554,9 +553,7 @@ cudaError_t scan_mma_configure() {
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(scan_mma_kernel<1, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<1>::kSmemBytes);
     if (e != cudaSuccess) return e;
-    // up to the whole shared memory of the SM: the pipelined search can ask for an SM-exclusive scan (no worker CTA
-    // squeezes in beside the scan CTA; the workers run on the SMs the scan grid leaves free)
-    e = cudaFuncSetAttribute(scan_mma_kernel<2, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemExclusive);
+    e = cudaFuncSetAttribute(scan_mma_kernel<2, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<2>::kSmemBytes);
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(scan_mma_kernel<2, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              bres_smem_bytes(kMaxBSlots));
@@ -590,9 +587,6 @@ cudaError_t launch_pairs(const MmaScanArgs& a, int sm_count, cudaStream_t s) {
             cfg.dynamicSmemBytes = bres_smem_bytes(a.b_slots);
             return cudaLaunchKernelEx(&cfg, scan_mma_kernel<2, true, true>, a);
         }
-    }
-    if constexpr (kI8) {
-        if (a.exclusive) cfg.dynamicSmemBytes = kSmemExclusive;
     }
     return cudaLaunchKernelEx(&cfg, scan_mma_kernel<2, kI8, false>, a);
 }

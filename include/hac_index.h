@@ -200,7 +200,8 @@ int hac_pinned_alloc(size_t bytes, void** out_host);
 int hac_pinned_free(void* host);
 
 /* ---- tuning knobs ---------------------------------------------------------------------------
- * Named integer options (unknown names -> HAC_E_INVALID):
+ * Named integer options (unknown names -> HAC_E_INVALID).  The environment variable HAC_OPTIONS
+ * ("name=value,name=value") applies them to every handle at hac_create - for callers that only know the faiss names:
  *   "mma_cta_group"  1 = one CTA per scan tile, 2 = CTA pairs sharing each MMA (cta_group::2)
  *   "chunk_growth_x100"  corpus-chunk growth factor of the threshold schedule, in percent (default 400)
  *   "default_path"   the scan path HAC_PATH_AUTO resolves to (HAC_PATH_GEMV / _MMA / _I8)
@@ -232,9 +233,6 @@ int hac_pinned_free(void* host);
  *                    of the rest starts from an exact threshold instead of emitting through many loosely filtered
  *                    early chunks; -1 (default) = automatic (tensor-bound batches on shards >= 8x the slab), 0 = off,
  *                    > 0 = that many rows
- *   "i8_scan_sms"    pipelined chunks: SMs the scan grid may occupy (0 = all); the SMs left free run the workers
- *   "i8_scan_exclusive"  pipelined chunks: 1 = the scan CTA claims its SM's whole shared memory, so that no worker CTA
- *                    is placed beside it
  *   "i8_b_slots"     int8 CTA-pair scan: 0 (default) = both operands streamed per unit, 6..8 = the corpus tile stays
  *                    resident in a ring of this many 16 KiB shared-memory slots across its query groups */
 int hac_set_option(hac_index* idx, const char* name, int64_t value);

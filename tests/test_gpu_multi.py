@@ -135,9 +135,11 @@ def _two_shards(x, split):
     return a, b
 
 
-@pytest.mark.parametrize("nq,n,k,concurrent", [(150, 60000, 100, True), (150, 60000, 100, False), (3, 40000, 10, True),
-                                               (300, 90001, 1, True), (40, 30000, 128, False)])
-def test_threshold_exchange_and_peer_merge_two_shards_one_device(nq, n, k, concurrent):
+@pytest.mark.parametrize("nq,n,k,concurrent,warm", [(150, 60000, 100, True, 0), (150, 60000, 100, False, 0),
+                                                    (3, 40000, 10, True, 0), (300, 90001, 1, True, 0),
+                                                    (40, 30000, 128, False, 0), (300, 90001, 100, True, 8192),
+                                                    (150, 60000, 100, False, 4096)])
+def test_threshold_exchange_and_peer_merge_two_shards_one_device(nq, n, k, concurrent, warm):
     """hac_set_threshold_exchange + hac_merge_topk_peers_device with same-device "peer" pointers: two shards search
     (concurrently from two host threads on two streams, or one after the other), publish their ceil(k/2)-th best
     scores to each other, return only their share of the global top-k, and the peer-pointer merge of the two lists
@@ -158,6 +160,7 @@ def test_threshold_exchange_and_peer_merge_two_shards_one_device(nq, n, k, concu
     words = [torch.zeros(cap, dtype=torch.int64, device=dev) for _ in range(2)]
     for r, sh in enumerate(shards):
         sh.set_threshold_exchange(words[r].data_ptr(), [words[1 - r].data_ptr()], cap)
+        sh.set_option("i8_warm_rows", warm)      # > 0: the shard's first rows go through the f16 screen first
     qd = torch.from_numpy(q).to(dev)
     D64, I64 = brute_force_fp64(q, x, k)
     x64 = x.astype(np.float64)
@@ -197,6 +200,7 @@ def test_threshold_exchange_and_peer_merge_two_shards_one_device(nq, n, k, concu
         assert np.array_equal(I1, I0) and np.array_equal(D1, D0), epoch
         for st in st_on:
             assert st["retries"] == 0 and st["screen_err_max"] <= st["margin_max"], st
+            assert st["warm_rows"] == warm, st
     if not concurrent:
         # shard 1 searched after shard 0 had published its final bounds: it keeps only rows that can reach the global
         # top-k, so it returns fillers where its own k-th best would have been
