@@ -22,7 +22,11 @@ VARIANTS = [
     ("sync_b7", {"i8_pipeline": 0, "i8_b_slots": 7}),
     ("pipe_b0", {"i8_pipeline": 1, "i8_b_slots": 0}),
     ("pipe_b6", {"i8_pipeline": 1, "i8_b_slots": 6}),
-    ("sync_w0", {"i8_warm_rows": 0}),
+    ("v0", {"i8_warm_rows": -1, "scan_variant": 0}),
+    ("v1", {"i8_warm_rows": -1, "scan_variant": 1}),
+    ("v0_k1", {"i8_warm_rows": -1, "scan_variant": 0, "_k": 1}),
+    ("v1_k1", {"i8_warm_rows": -1, "scan_variant": 1, "_k": 1}),
+    ("sync_w0", {"i8_warm_rows": 0, "scan_variant": 1}),
     ("sync_w128k", {"i8_warm_rows": 131072}),
     ("sync_w256k", {"i8_warm_rows": 262144}),
     ("sync_w384k", {"i8_warm_rows": 393216}),
@@ -32,7 +36,7 @@ VARIANTS = [
     ("pipe_w384k", {"i8_pipeline": 1, "i8_warm_rows": 393216}),
 ]
 DEFAULTS = {"i8_pipeline": 0, "i8_pipe_growth_x1000": 125, "i8_pipe_min_rows": 0, "i8_pipe_dist": 2, "i8_b_slots": 0,
-            "i8_chunk_growth_x100": 0, "i8_warm_rows": 0}
+            "i8_chunk_growth_x100": 0, "i8_warm_rows": 0, "scan_variant": 1}
 
 
 def main():
@@ -62,16 +66,21 @@ def main():
         wall = {name: [] for name, _ in variants}
         for r in range(args.reps + 1):
             for name, opts in variants:
+                k = 100
                 for kk, vv in {**DEFAULTS, **opts}.items():
-                    idx.set_option(kk, vv)
+                    if kk == "_k":
+                        k = vv                                   # pseudo-option: top-k of this variant
+                    else:
+                        idx.set_option(kk, vv)
                 torch.cuda.synchronize()
                 t0 = time.perf_counter()
-                D, I = idx.search(q, 100)
+                D, I = idx.search(q, k)
                 torch.cuda.synchronize()
                 dt = (time.perf_counter() - t0) * 1e3
-                if ref is None:
+                if ref is None and k == 100:
                     ref = (D.clone(), I.clone())
-                assert torch.equal(I, ref[1]) and torch.equal(D, ref[0]), name
+                if ref is not None:
+                    assert torch.equal(I, ref[1][:, :k]) and torch.equal(D, ref[0][:, :k]), name
                 if r >= 1:
                     acc[name].append(idx.stats())
                     wall[name].append(dt)

@@ -147,6 +147,7 @@ struct hac_index {
     // every e-fold of rows seen, whatever the chunk size) - and the int8 scan of the remaining rows starts with an
     // exact threshold.  -1 = automatic size, 0 = off, > 0 = rows.
     int64_t i8_warm_rows = -1;
+    int scan_variant = 1;                   // MmaScanArgs::variant (in-process A/B of the scan epilogue)
     struct WarmSlab {
         uint8_t* shadow = nullptr;
         OperandStats* stats = nullptr;
@@ -703,6 +704,7 @@ int search_batch_i8(hac_index* idx, int nq, int nq_pad, const float* q_dev, int 
             a.d = d;
             a.tile_major = idx->scan_tile_major < 0 ? 0 : idx->scan_tile_major;
             a.n_qtiles = nq_pad / kTileRows;
+            a.variant = idx->scan_variant;
             a.ct0 = r / kRowAlign;
             a.ct1 = (r1 + kRowAlign - 1) / kRowAlign;
             a.seg_rows = r1;
@@ -758,6 +760,7 @@ int search_batch_i8(hac_index* idx, int nq, int nq_pad, const float* q_dev, int 
         const int want_b = (n_sync < n_chunks) ? std::min(idx->i8_b_slots, 6) : idx->i8_b_slots;
         a.b_slots = (a.tile_major && d / kBlockK8 <= want_b) ? want_b : 0;
         a.n_qtiles = nq_pad / kTileRows;
+        a.variant = idx->scan_variant;
         a.ct0 = ch.r0 / kRowAlign;
         a.ct1 = (ch.r1 + kRowAlign - 1) / kRowAlign;
         a.seg_rows = std::min(seg.n_rows, ch.r1);
@@ -929,6 +932,7 @@ int search_batch(hac_index* idx, int nq, const float* q_dev, int k, float* D_dev
                 a.d = d;
                 a.tile_major = idx->scan_tile_major < 0 ? 0 : idx->scan_tile_major;
                 a.n_qtiles = nq_pad / kTileRows;
+                a.variant = idx->scan_variant;
                 a.ct0 = r / kRowAlign;
                 a.ct1 = (r1 + kRowAlign - 1) / kRowAlign;
                 a.seg_rows = std::min(seg.n_rows, r1);     // rows past r1 belong to a later chunk
@@ -1654,6 +1658,11 @@ int hac_set_option(hac_index* idx, const char* name, int64_t value) {
     if (strcmp(name, "i8_b_slots") == 0) {
         if (value != 0 && (value < 6 || value > 8)) return fail(HAC_E_INVALID, "i8_b_slots must be 0 or in [6, 8]");
         idx->i8_b_slots = (int)value;
+        return HAC_OK;
+    }
+    if (strcmp(name, "scan_variant") == 0) {
+        if (value != 0 && value != 1) return fail(HAC_E_INVALID, "scan_variant must be 0 or 1");
+        idx->scan_variant = (int)value;
         return HAC_OK;
     }
     if (strcmp(name, "i8_warm_rows") == 0) {

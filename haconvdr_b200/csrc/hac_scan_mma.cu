@@ -41,7 +41,7 @@ namespace {
 constexpr int kTileM = 128;                                // queries per CTA tile (TMEM lanes)
 constexpr int kTileN = 256;                                // corpus rows per tile (TMEM columns)
 constexpr int kThreads = 320;                              // producer warp, MMA warp, 8 epilogue warps
-constexpr int kStash = 8;                                  // per-thread survivors kept until the TMEM buffer is released
+constexpr int kStash = 16;                                 // per-thread survivors kept until the TMEM buffer is released
 constexpr int kMaxStages = 14;                             // barrier slots: stages, or A ring + B ring (kBRes)
 constexpr int kASlots = 6;                                 // kBRes: ring of query K blocks (one unit deep)
 constexpr int kMaxBSlots = 8;                              // kBRes: ring of corpus K blocks (6 resident + spares)
@@ -118,12 +118,15 @@ __device__ __forceinline__ float fmax3(float a, float b, float c) {
 struct UnitSchedule {
     int64_t G, b, body_rounds, body_units, n_mine;
     int n_qg;
+    int g_div, g_mod;                // G = g_div * n_qg + g_mod: one striped step advances g_div tiles and g_mod query groups
     __device__ UnitSchedule(int64_t n_ct, int n_qgroups, int64_t n_groups, int64_t group, bool tile_major) {
         G = n_groups; b = group; n_qg = n_qgroups;
         body_rounds = tile_major ? n_ct / G : 0;
         body_units = body_rounds * n_qg;
         const int64_t tail_units = (n_ct - body_rounds * G) * n_qg;
         n_mine = body_units + (tail_units > b ? (tail_units - b + G - 1) / G : 0);
+        g_div = (int)(G / n_qg);
+        g_mod = (int)(G - (int64_t)g_div * n_qg);
     }
     // i-th unit of this group -> (corpus tile relative to ct0, query group)
     __device__ __forceinline__ void get(int64_t i, int64_t& ct_rel, int& qg) const {
@@ -140,8 +143,38 @@ struct UnitSchedule {
     }
 };
 
-template <int kCG, bool kI8, bool kBRes>
+// Walks a CTA group's units in order.  UnitSchedule::get costs two 64-bit divisions (~200 instructions); every one of
+// the 256 epilogue threads needs the current and the next unit, which made the bookkeeping of a unit three times
+// as long as the drain of its accumulator columns.  kInc = true steps incrementally instead (additions only; one
+// get() at the start and one where the striped tail begins).
+template <bool kInc>
+struct UnitIter {
+    const UnitSchedule& s;
+    int64_t i, ct_rel;
+    int qg;
+    __device__ explicit UnitIter(const UnitSchedule& sched) : s(sched), i(0), ct_rel(0), qg(0) {
+        if (s.n_mine > 0) s.get(0, ct_rel, qg);
+    }
+    __device__ __forceinline__ bool valid() const { return i < s.n_mine; }
+    __device__ __forceinline__ void next() {
+        ++i;
+        if (i >= s.n_mine) return;
+        if (!kInc || i == s.body_units) {
+            s.get(i, ct_rel, qg);
+        } else if (i < s.body_units) {           // tile-major body: all query groups of a tile, then the tile G further
+            if (++qg == s.n_qg) { qg = 0; ct_rel += s.G; }
+        } else {                                 // striped tail: unit index advances by G
+            ct_rel += s.g_div;
+            qg += s.g_mod;
+            if (qg >= s.n_qg) { qg -= s.n_qg; ++ct_rel; }
+        }
+    }
+};
+
+// kV: 0 = the round-1 epilogue / bookkeeping, 1 = incremental unit walk + survivor search by column octets (below)
+template <int kCG, bool kI8, bool kBRes, int kV>
 __global__ void __launch_bounds__(kThreads, 1) scan_mma_kernel(const MmaScanArgs a) {
+    using Iter = UnitIter<kV != 0>;
     static_assert(!kBRes || (kCG == 2 && kI8), "the resident-corpus-tile variant exists for int8 CTA pairs only");
     using C = Cfg<kCG>;
     extern __shared__ uint8_t smem_raw[];
@@ -212,12 +245,9 @@ __global__ void __launch_bounds__(kThreads, 1) scan_mma_kernel(const MmaScanArgs
                 }
             } else {
             uint32_t stage = 0, phase = 0;
-            for (int64_t i = 0; i < sched.n_mine; ++i) {
-                int64_t ct_rel;
-                int qg;
-                sched.get(i, ct_rel, qg);
-                const int64_t ct = a.ct0 + ct_rel;
-                const int qt = qg * kCG + (int)cta_rank;
+            for (Iter u(sched); u.valid(); u.next()) {
+                const int64_t ct = a.ct0 + u.ct_rel;
+                const int qt = u.qg * kCG + (int)cta_rank;
                 const uint8_t* srcA = a.q_shadow + (size_t)qt * kb_count * kPieceBytes;
                 // kCG = 1: both 128-row halves of the corpus tile; kCG = 2: this CTA's half only
                 const uint8_t* srcB = a.x_shadow + (size_t)(2 * ct + (kCG == 2 ? cta_rank : 0)) * kb_count * kPieceBytes;
@@ -391,11 +421,8 @@ __global__ void __launch_bounds__(kThreads, 1) scan_mma_kernel(const MmaScanArgs
             QueryQ8 qc;
             TileQ8 t0, t1;
         };
-        auto fetch = [&](int64_t i) {
+        auto fetch = [&](int64_t ct_rel, int qg) {
             UnitConsts c;
-            int64_t ct_rel;
-            int qg;
-            sched.get(i, ct_rel, qg);
             const int64_t ct = a.ct0 + ct_rel;
             const int q = (qg * kCG + (int)cta_rank) * kTileM + quarter * 32 + lane;
             // the thresholds rise WHILE this launch runs (the previous chunks' rescore / refresh work on a side
@@ -410,14 +437,13 @@ __global__ void __launch_bounds__(kThreads, 1) scan_mma_kernel(const MmaScanArgs
             return c;
         };
         UnitConsts cur{};
-        if (sched.n_mine > 0) cur = fetch(0);
-        for (int64_t i = 0; i < sched.n_mine; ++i, ++it) {
+        Iter u(sched), ahead(sched);
+        if (u.valid()) cur = fetch(u.ct_rel, u.qg);
+        ahead.next();
+        for (; u.valid(); u.next(), ahead.next(), ++it) {
             const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
-            int64_t ct_rel;
-            int qg;
-            sched.get(i, ct_rel, qg);
-            const int64_t ct = a.ct0 + ct_rel;
-            const int qt = qg * kCG + (int)cta_rank;
+            const int64_t ct = a.ct0 + u.ct_rel;
+            const int qt = u.qg * kCG + (int)cta_rank;
             const int q = qt * kTileM + quarter * 32 + lane;
             // threshold in accumulator units (power-of-two scale); the accumulator lacks the per-query constant
             // q.c of a centred image, so it is taken off the threshold (rounded down: may only lower it) and added
@@ -437,7 +463,7 @@ __global__ void __launch_bounds__(kThreads, 1) scan_mma_kernel(const MmaScanArgs
                 deq[1] = cur.qc.t * cur.t1.alpha;
             }
             UnitConsts nxt{};
-            if (i + 1 < sched.n_mine) nxt = fetch(i + 1);
+            if (ahead.valid()) nxt = fetch(ahead.ct_rel, ahead.qg);
             uint32_t stash_n = 0;
             // one 32-column group of this thread's query: compare, stash or append the survivors
             auto process = [&](const uint32_t (&v)[32], int c) {
@@ -455,7 +481,40 @@ __global__ void __launch_bounds__(kThreads, 1) scan_mma_kernel(const MmaScanArgs
                 // compare (16 + 1 instructions instead of a compare and a predicate-or per column) - at int8 rates the
                 // epilogue warps have only ~3000 cycles per tile and were co-limiting the scan
                 bool any;
-                if constexpr (kI8) {
+                bool hit[4] = {true, true, true, true};        // kV = 1: which column octets hold a survivor
+                if constexpr (kV != 0) {
+                    // four independent chains of eight columns (same instruction count as one chain of 32, more ILP);
+                    // their maxima tell the survivor search below which octet to look into
+                    if constexpr (kI8) {
+                        int m[4];
+#pragma unroll
+                        for (int g = 0; g < 4; ++g) {
+                            m[g] = __vimax3_s32((int)v[8 * g], (int)v[8 * g + 1], (int)v[8 * g + 2]);
+                            m[g] = __vimax3_s32(m[g], (int)v[8 * g + 3], (int)v[8 * g + 4]);
+                            m[g] = __vimax3_s32(m[g], (int)v[8 * g + 5], (int)v[8 * g + 6]);
+                            m[g] = max(m[g], (int)v[8 * g + 7]);
+                        }
+                        any = max(__vimax3_s32(m[0], m[1], m[2]), m[3]) >= thr_c;
+                        if (any) {
+#pragma unroll
+                            for (int g = 0; g < 4; ++g) hit[g] = m[g] >= thr_c;
+                        }
+                    } else {
+                        float m[4];
+#pragma unroll
+                        for (int g = 0; g < 4; ++g) {
+                            m[g] = fmax3(__uint_as_float(v[8 * g]), __uint_as_float(v[8 * g + 1]), __uint_as_float(v[8 * g + 2]));
+                            m[g] = fmax3(m[g], __uint_as_float(v[8 * g + 3]), __uint_as_float(v[8 * g + 4]));
+                            m[g] = fmax3(m[g], __uint_as_float(v[8 * g + 5]), __uint_as_float(v[8 * g + 6]));
+                            m[g] = fmaxf(m[g], __uint_as_float(v[8 * g + 7]));
+                        }
+                        any = fmaxf(fmax3(m[0], m[1], m[2]), m[3]) >= thr_s;
+                        if (any) {
+#pragma unroll
+                            for (int g = 0; g < 4; ++g) hit[g] = m[g] >= thr_s;
+                        }
+                    }
+                } else if constexpr (kI8) {
                     int m = (int)v[0];
 #pragma unroll
                     for (int j = 1; j + 1 < 32; j += 2) m = __vimax3_s32(m, (int)v[j], (int)v[j + 1]);
@@ -468,7 +527,31 @@ __global__ void __launch_bounds__(kThreads, 1) scan_mma_kernel(const MmaScanArgs
                     m = fmaxf(m, __uint_as_float(v[31]));
                     any = m >= thr_s;
                 }
-                if (any) {
+                // Survivors are rare once a threshold exists (a few per 100 000 columns), but a warp takes this branch
+                // whenever ONE of its 32 queries has one - every seventh 32-column group at k = 100 - so its length
+                // is what the epilogue's time depends on (k = 1 vs k = 100: 34.4 vs 38.6 ms of scan with the mask code
+                // below alone).  Sparse case: only the octets that hold a survivor are expanded, straight into the stash.
+                const int n_hit = (int)hit[0] + (int)hit[1] + (int)hit[2] + (int)hit[3];
+                if (kV != 0 && any && n_hit < 4 && stash_n + 8u * (uint32_t)n_hit <= (uint32_t)kStash &&
+                    a.seg_rows - (row0 + c * 32) >= 32) {
+                    const uint32_t row_id = a.row_id_base + (uint32_t)(row0 + c * 32);
+                    const uint32_t before = stash_n;
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) {
+                        if (hit[g]) {
+#pragma unroll
+                            for (int jj = 0; jj < 8; ++jj) {
+                                const int j = 8 * g + jj;
+                                if (passes(v[j])) {
+                                    stash_v[it & 1][stash_n] = value(v[j]);
+                                    stash_r[it & 1][stash_n] = row_id + j;
+                                    ++stash_n;
+                                }
+                            }
+                        }
+                    }
+                    emitted += stash_n - before;
+                } else if (any) {
                     uint32_t mask = 0;
 #pragma unroll
                     for (int j = 0; j < 32; ++j) mask |= (passes(v[j]) ? 1u : 0u) << j;
@@ -548,18 +631,20 @@ __global__ void __launch_bounds__(kThreads, 1) scan_mma_kernel(const MmaScanArgs
 }  // namespace
 
 cudaError_t scan_mma_configure() {
-    cudaError_t e = cudaFuncSetAttribute(scan_mma_kernel<1, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         Cfg<1>::kSmemBytes);
-    if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(scan_mma_kernel<1, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<1>::kSmemBytes);
-    if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(scan_mma_kernel<2, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<2>::kSmemBytes);
-    if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(scan_mma_kernel<2, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             bres_smem_bytes(kMaxBSlots));
-    if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(scan_mma_kernel<2, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                Cfg<2>::kSmemBytes);
+    cudaError_t e = cudaSuccess;
+    auto set = [&](auto kernel, int bytes) {
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    };
+    set(scan_mma_kernel<1, false, false, 0>, Cfg<1>::kSmemBytes);
+    set(scan_mma_kernel<1, false, false, 1>, Cfg<1>::kSmemBytes);
+    set(scan_mma_kernel<1, true, false, 0>, Cfg<1>::kSmemBytes);
+    set(scan_mma_kernel<1, true, false, 1>, Cfg<1>::kSmemBytes);
+    set(scan_mma_kernel<2, false, false, 0>, Cfg<2>::kSmemBytes);
+    set(scan_mma_kernel<2, false, false, 1>, Cfg<2>::kSmemBytes);
+    set(scan_mma_kernel<2, true, false, 0>, Cfg<2>::kSmemBytes);
+    set(scan_mma_kernel<2, true, false, 1>, Cfg<2>::kSmemBytes);
+    set(scan_mma_kernel<2, true, true, 0>, bres_smem_bytes(kMaxBSlots));
+    return e;
 }
 
 namespace {
@@ -585,10 +670,11 @@ cudaError_t launch_pairs(const MmaScanArgs& a, int sm_count, cudaStream_t s) {
         if (a.b_slots > 0) {
             if (a.b_slots > kMaxBSlots || a.b_slots < a.d / kBlockK8) return cudaErrorInvalidValue;
             cfg.dynamicSmemBytes = bres_smem_bytes(a.b_slots);
-            return cudaLaunchKernelEx(&cfg, scan_mma_kernel<2, true, true>, a);
+            return cudaLaunchKernelEx(&cfg, scan_mma_kernel<2, true, true, 0>, a);
         }
     }
-    return cudaLaunchKernelEx(&cfg, scan_mma_kernel<2, kI8, false>, a);
+    if (a.variant != 0) return cudaLaunchKernelEx(&cfg, scan_mma_kernel<2, kI8, false, 1>, a);
+    return cudaLaunchKernelEx(&cfg, scan_mma_kernel<2, kI8, false, 0>, a);
 }
 }  // namespace
 
@@ -598,7 +684,8 @@ cudaError_t launch_scan_mma_i8(const MmaScanArgs& a, int sm_count, int cta_group
     if (a.x_tiles == nullptr || a.q_consts == nullptr || a.d % kBlockK8 != 0) return cudaErrorInvalidValue;
     if (cta_group == 2 && (a.n_qtiles % 2) == 0) return launch_pairs<true>(a, sm_count, s);
     const int grid = (int)(n_units < sm_count ? n_units : sm_count);
-    scan_mma_kernel<1, true, false><<<grid, kThreads, Cfg<1>::kSmemBytes, s>>>(a);
+    if (a.variant != 0) scan_mma_kernel<1, true, false, 1><<<grid, kThreads, Cfg<1>::kSmemBytes, s>>>(a);
+    else scan_mma_kernel<1, true, false, 0><<<grid, kThreads, Cfg<1>::kSmemBytes, s>>>(a);
     return cudaGetLastError();
 }
 
@@ -608,7 +695,8 @@ cudaError_t launch_scan_mma(const MmaScanArgs& a, int sm_count, int cta_group, c
     if (cta_group == 2 && (a.n_qtiles % 2) == 0) return launch_pairs<false>(a, sm_count, s);
     const int64_t n_units = n_ctiles * a.n_qtiles;
     const int grid = (int)(n_units < sm_count ? n_units : sm_count);
-    scan_mma_kernel<1, false, false><<<grid, kThreads, Cfg<1>::kSmemBytes, s>>>(a);
+    if (a.variant != 0) scan_mma_kernel<1, false, false, 1><<<grid, kThreads, Cfg<1>::kSmemBytes, s>>>(a);
+    else scan_mma_kernel<1, false, false, 0><<<grid, kThreads, Cfg<1>::kSmemBytes, s>>>(a);
     return cudaGetLastError();
 }
 

@@ -663,8 +663,13 @@ def test_int8_screen_cta_pairs_and_unit_schedules(nq, n, k):
                 st = idx.stats()
                 assert st["path"] == hb.HAC_PATH_I8 and st["retries"] == 0, (cg, tile_major, b_slots, st)
                 assert np.array_equal(I8, Im) and np.array_equal(D8, Dm), (cg, tile_major, b_slots)
-            Df, If = idx.search(q, k, path=hb.HAC_PATH_MMA)          # the f16 scan under the same schedule
-            assert np.array_equal(If, Im) and np.array_equal(Df, Dm), (cg, tile_major)
+            for variant in (0, 1):                                   # both epilogue / bookkeeping variants of the kernel
+                idx.set_option("scan_variant", variant)
+                idx.set_option("i8_b_slots", 0)
+                D8, I8 = idx.search(q, k, path=hb.HAC_PATH_I8)
+                assert np.array_equal(I8, Im) and np.array_equal(D8, Dm), (cg, tile_major, variant)
+                Df, If = idx.search(q, k, path=hb.HAC_PATH_MMA)      # the f16 scan under the same schedule
+                assert np.array_equal(If, Im) and np.array_equal(Df, Dm), (cg, tile_major, variant)
     _check(q, x, k, Dm, Im, also_fp32_oracle=False)
 
 
