@@ -1,8 +1,7 @@
 #!/usr/bin/env python
 """Round-2 A/B on one GPU (full TopiOCQA-scale corpus by default): the pipelined int8 search (scans back to back,
-rescore + refresh on a side stream beside the next scan) against the chunk-synchronous schedule of round 1, and the
-resident-corpus-tile CTA-pair scan (i8_b_slots) against the streamed-operand one, for the headline batch and for the
-small turn batches, alternating in one process.
+rescore + refresh on a side stream beside the next scan) against the chunk-synchronous schedule, and the warm-start /
+chunk-growth settings, for the headline batch and for the small turn batches, alternating in one process.
 
 One JSON line per (batch, variant).  Usage: python benchmarks/ab_pipeline.py [--rows N] [--reps R] [--only big,small]
 """
@@ -17,16 +16,18 @@ def med(xs):
 
 VARIANTS = [
     # name, options
-    ("sync_b0", {"i8_pipeline": 0, "i8_b_slots": 0}),
-    ("sync_b8", {"i8_pipeline": 0, "i8_b_slots": 8}),
-    ("sync_b7", {"i8_pipeline": 0, "i8_b_slots": 7}),
-    ("pipe_b0", {"i8_pipeline": 1, "i8_b_slots": 0}),
-    ("pipe_b6", {"i8_pipeline": 1, "i8_b_slots": 6}),
-    ("v0", {"i8_warm_rows": -1, "scan_variant": 0}),
-    ("v1", {"i8_warm_rows": -1, "scan_variant": 1}),
-    ("v0_k1", {"i8_warm_rows": -1, "scan_variant": 0, "_k": 1}),
-    ("v1_k1", {"i8_warm_rows": -1, "scan_variant": 1, "_k": 1}),
-    ("sync_w0", {"i8_warm_rows": 0, "scan_variant": 1}),
+    ("sync_b0", {"i8_pipeline": 0}),
+    ("pipe_b0", {"i8_pipeline": 1}),
+    ("w768k_g35", {"i8_warm_rows": 786432, "i8_chunk_growth_x100": 35}),
+    ("w768k_g25", {"i8_warm_rows": 786432, "i8_chunk_growth_x100": 25}),
+    ("w768k_g18", {"i8_warm_rows": 786432, "i8_chunk_growth_x100": 18}),
+    ("w768k_g50", {"i8_warm_rows": 786432, "i8_chunk_growth_x100": 50}),
+    ("w1536k_g35", {"i8_warm_rows": 1572864, "i8_chunk_growth_x100": 35}),
+    ("w1536k_g25", {"i8_warm_rows": 1572864, "i8_chunk_growth_x100": 25}),
+    ("w384k_g25", {"i8_warm_rows": 393216, "i8_chunk_growth_x100": 25}),
+    ("w3072k_g25", {"i8_warm_rows": 3145728, "i8_chunk_growth_x100": 25}),
+    ("pipe_w768k", {"i8_pipeline": 1, "i8_warm_rows": 786432}),
+    ("sync_w0", {"i8_warm_rows": 0}),
     ("sync_w128k", {"i8_warm_rows": 131072}),
     ("sync_w256k", {"i8_warm_rows": 262144}),
     ("sync_w384k", {"i8_warm_rows": 393216}),
@@ -35,8 +36,8 @@ VARIANTS = [
     ("sync_w384k_g100", {"i8_warm_rows": 393216, "i8_chunk_growth_x100": 100}),
     ("pipe_w384k", {"i8_pipeline": 1, "i8_warm_rows": 393216}),
 ]
-DEFAULTS = {"i8_pipeline": 0, "i8_pipe_growth_x1000": 125, "i8_pipe_min_rows": 0, "i8_pipe_dist": 2, "i8_b_slots": 0,
-            "i8_chunk_growth_x100": 0, "i8_warm_rows": 0, "scan_variant": 1}
+DEFAULTS = {"i8_pipeline": 0, "i8_pipe_growth_x1000": 125, "i8_pipe_min_rows": 0, "i8_pipe_dist": 2,
+            "i8_chunk_growth_x100": 0, "i8_warm_rows": 0}
 
 
 def main():

@@ -11,7 +11,6 @@ def main():
     ap.add_argument("--rows", type=int, default=25_700_592)
     ap.add_argument("--queries", type=int, default=1)
     ap.add_argument("--cta-group", type=int, default=1)
-    ap.add_argument("--b-slots", type=int, default=-1, help="i8_b_slots (resident corpus tile ring); -1 = engine default")
     ap.add_argument("--k", type=int, default=100)
     args = ap.parse_args()
     from haconvdr_b200 import FlatIPIndex, HAC_PATH_I8
@@ -19,8 +18,6 @@ def main():
     idx = FlatIPIndex(768, 0)
     idx.set_option("build_i8", 1)
     idx.set_option("i8_cta_group", args.cta_group)
-    if args.b_slots >= 0:
-        idx.set_option("i8_b_slots", args.b_slots)
     idx.reserve(args.rows)
     idx.add_synthetic(args.rows, seed=42)
     q = synth_rows_device(args.queries, 768, seed=4242)

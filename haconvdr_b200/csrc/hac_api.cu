@@ -133,9 +133,6 @@ struct hac_index {
     // large) the scans run back to back on `stream` while chunk i's rescore + refresh run on `side` beside the scan of
     // chunk i+1: scan i only waits for the worker of chunk i - i8_pipe_dist.  A stale threshold is a valid lower
     // bound, so nothing but the number of emitted rows depends on the overlap.
-    // int8 CTA-pair scan: ring slots (16 KiB) that keep the corpus tile resident across its query groups (0 = off: both
-    // operands streamed per unit).  8 leaves no room for a co-resident worker CTA; the pipelined search uses 7.
-    int i8_b_slots = 0;                     // measured: 54.1 ms of scan with the tile resident (7 or 8 slots) vs 34.8 ms streamed
     // measured on one GPU: 47.1 ms pipelined vs 46.2 ms synchronous (the scan is power-bound: co-running rescores slow
     // it by what they save).  Giving the workers SMs of their own does not help either: the scan slows in proportion
     // to the SMs it gives up (132 of 148 SMs: 45.4 vs 40.8 ms of scan, profiles/r02_ab_warm_start_and_scan_sms.jsonl).
@@ -147,7 +144,6 @@ struct hac_index {
     // every e-fold of rows seen, whatever the chunk size) - and the int8 scan of the remaining rows starts with an
     // exact threshold.  -1 = automatic size, 0 = off, > 0 = rows.
     int64_t i8_warm_rows = -1;
-    int scan_variant = 1;                   // MmaScanArgs::variant (in-process A/B of the scan epilogue)
     struct WarmSlab {
         uint8_t* shadow = nullptr;
         OperandStats* stats = nullptr;
@@ -704,7 +700,6 @@ int search_batch_i8(hac_index* idx, int nq, int nq_pad, const float* q_dev, int 
             a.d = d;
             a.tile_major = idx->scan_tile_major < 0 ? 0 : idx->scan_tile_major;
             a.n_qtiles = nq_pad / kTileRows;
-            a.variant = idx->scan_variant;
             a.ct0 = r / kRowAlign;
             a.ct1 = (r1 + kRowAlign - 1) / kRowAlign;
             a.seg_rows = r1;
@@ -755,12 +750,7 @@ int search_batch_i8(hac_index* idx, int nq, int nq_pad, const float* q_dev, int 
         a.thr = w.thr;
         a.d = d;
         a.tile_major = idx->scan_tile_major < 0 ? 1 : idx->scan_tile_major;
-        // resident corpus tile (ring of b_slots 16 KiB slots); the pipelined schedule keeps 34 KB of shared memory
-        // free for the co-resident worker CTAs (rescore 3 KB, refresh 17 KB), i.e. at most 6 slots
-        const int want_b = (n_sync < n_chunks) ? std::min(idx->i8_b_slots, 6) : idx->i8_b_slots;
-        a.b_slots = (a.tile_major && d / kBlockK8 <= want_b) ? want_b : 0;
         a.n_qtiles = nq_pad / kTileRows;
-        a.variant = idx->scan_variant;
         a.ct0 = ch.r0 / kRowAlign;
         a.ct1 = (ch.r1 + kRowAlign - 1) / kRowAlign;
         a.seg_rows = std::min(seg.n_rows, ch.r1);
@@ -932,7 +922,6 @@ int search_batch(hac_index* idx, int nq, const float* q_dev, int k, float* D_dev
                 a.d = d;
                 a.tile_major = idx->scan_tile_major < 0 ? 0 : idx->scan_tile_major;
                 a.n_qtiles = nq_pad / kTileRows;
-                a.variant = idx->scan_variant;
                 a.ct0 = r / kRowAlign;
                 a.ct1 = (r1 + kRowAlign - 1) / kRowAlign;
                 a.seg_rows = std::min(seg.n_rows, r1);     // rows past r1 belong to a later chunk
@@ -1655,16 +1644,6 @@ int hac_set_option(hac_index* idx, const char* name, int64_t value) {
         return HAC_OK;
     }
     if (strcmp(name, "i8_pipeline") == 0) { idx->i8_pipeline = value != 0; return HAC_OK; }
-    if (strcmp(name, "i8_b_slots") == 0) {
-        if (value != 0 && (value < 6 || value > 8)) return fail(HAC_E_INVALID, "i8_b_slots must be 0 or in [6, 8]");
-        idx->i8_b_slots = (int)value;
-        return HAC_OK;
-    }
-    if (strcmp(name, "scan_variant") == 0) {
-        if (value != 0 && value != 1) return fail(HAC_E_INVALID, "scan_variant must be 0 or 1");
-        idx->scan_variant = (int)value;
-        return HAC_OK;
-    }
     if (strcmp(name, "i8_warm_rows") == 0) {
         if (value < -1 || value > (int64_t)1 << 26) return fail(HAC_E_INVALID, "i8_warm_rows out of range");
         idx->i8_warm_rows = value;

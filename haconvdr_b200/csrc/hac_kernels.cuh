@@ -145,8 +145,6 @@ struct MmaScanArgs {
     int d;
     int n_qtiles;
     int tile_major;         // 1: every CTA walks whole corpus tiles (all query tiles back to back); 0: units striped
-    int variant = 1;        // 0 = round-1 epilogue and unit bookkeeping, 1 = incremental unit walk + octet survivor search
-    int b_slots = 0;        // int8 CTA pairs: > 0 = keep the corpus tile resident in a ring of this many 16 KiB slots (7-8)
     int64_t ct0, ct1;       // 256-row tiles of the segment
     int64_t seg_rows;       // valid rows of the segment
     uint32_t row_id_base;

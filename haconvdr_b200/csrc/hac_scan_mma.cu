@@ -16,12 +16,6 @@
 //            the MMAs; the peer forwards "my half has landed" to the leader through a remote
 //            mbarrier arrive; tcgen05.commit multicasts slot-free / accumulator-ready to both CTAs.
 //   Defaults: int8 -> kCG = 2 (single-tile batches run kCG = 1), f16 -> kCG = 1 (power-bound either way).
-//   kBRes (int8 CTA pairs only): the corpus tile stays RESIDENT in shared memory while the pair walks all query groups
-//            of that tile (the tile-major order runs them back to back).  Shared memory is cut into 14 slots of
-//            16 KiB: a ring of 6 for the query K blocks (streamed, one unit deep) and a ring of 7-8 for the corpus K
-//            blocks - 6 in use, the spare ones take the next tile's first blocks, the others are refilled as the last
-//            query group's MMAs retire.  Operand bytes moved from L2 into shared memory per unit drop from 2 x 192 KiB
-//            to 192 + 19 KiB at 10 query groups; the scan is power-bound and that traffic is its largest overhead.
 // Warp roles (320 threads, persistent): warp 0 = copy producer, warp 1 = MMA issuer (leader) or
 // forwarder (peer) and owner of the TMEM allocation, warps 2..9 = epilogue (TMEM lane quarter =
 // warp % 4, one query per thread; warps 2..5 drain columns 0..127 of a tile, warps 6..9 columns 128..255).
@@ -42,9 +36,7 @@ constexpr int kTileM = 128;                                // queries per CTA ti
 constexpr int kTileN = 256;                                // corpus rows per tile (TMEM columns)
 constexpr int kThreads = 320;                              // producer warp, MMA warp, 8 epilogue warps
 constexpr int kStash = 16;                                 // per-thread survivors kept until the TMEM buffer is released
-constexpr int kMaxStages = 14;                             // barrier slots: stages, or A ring + B ring (kBRes)
-constexpr int kASlots = 6;                                 // kBRes: ring of query K blocks (one unit deep)
-constexpr int kMaxBSlots = 8;                              // kBRes: ring of corpus K blocks (6 resident + spares)
+constexpr int kMaxStages = 6;                              // barrier slots (pipeline stages)
 
 template <int kCG>
 struct Cfg {
@@ -54,7 +46,6 @@ struct Cfg {
     static constexpr int kStageBytes = kABytes + kBBytes;
     static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 512 /*barriers*/;
 };
-constexpr int bres_smem_bytes(int b_slots) { return (kASlots + b_slots) * kPieceBytes + 1024 + 512; }
 
 struct Barriers {
     uint64_t full[kMaxStages];       // this CTA's operand bytes of the stage have landed
@@ -145,9 +136,8 @@ struct UnitSchedule {
 
 // Walks a CTA group's units in order.  UnitSchedule::get costs two 64-bit divisions (~200 instructions); every one of
 // the 256 epilogue threads needs the current and the next unit, which made the bookkeeping of a unit three times
-// as long as the drain of its accumulator columns.  kInc = true steps incrementally instead (additions only; one
+// as long as the drain of its accumulator columns.  The iterator steps incrementally instead (additions only; one
 // get() at the start and one where the striped tail begins).
-template <bool kInc>
 struct UnitIter {
     const UnitSchedule& s;
     int64_t i, ct_rel;
@@ -159,7 +149,7 @@ struct UnitIter {
     __device__ __forceinline__ void next() {
         ++i;
         if (i >= s.n_mine) return;
-        if (!kInc || i == s.body_units) {
+        if (i == s.body_units) {
             s.get(i, ct_rel, qg);
         } else if (i < s.body_units) {           // tile-major body: all query groups of a tile, then the tile G further
             if (++qg == s.n_qg) { qg = 0; ct_rel += s.G; }
@@ -171,17 +161,13 @@ struct UnitIter {
     }
 };
 
-// kV: 0 = the round-1 epilogue / bookkeeping, 1 = incremental unit walk + survivor search by column octets (below)
-template <int kCG, bool kI8, bool kBRes, int kV>
+template <int kCG, bool kI8>
 __global__ void __launch_bounds__(kThreads, 1) scan_mma_kernel(const MmaScanArgs a) {
-    using Iter = UnitIter<kV != 0>;
-    static_assert(!kBRes || (kCG == 2 && kI8), "the resident-corpus-tile variant exists for int8 CTA pairs only");
     using C = Cfg<kCG>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    const int b_slots = kBRes ? a.b_slots : 0;              // kBRes: slots [0, 6) = A ring, [6, 6 + b_slots) = B ring
-    Barriers* bars = reinterpret_cast<Barriers*>(smem + (kBRes ? (kASlots + b_slots) * kPieceBytes : C::kStages * C::kStageBytes));
-    const int n_bar_slots = kBRes ? kASlots + b_slots : C::kStages;
+    Barriers* bars = reinterpret_cast<Barriers*>(smem + C::kStages * C::kStageBytes);
+    constexpr int n_bar_slots = C::kStages;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int kb_count = a.d / (kI8 ? kBlockK8 : kBlockK);
@@ -213,39 +199,8 @@ __global__ void __launch_bounds__(kThreads, 1) scan_mma_kernel(const MmaScanArgs
     if (warp == 0) {
         // ---------------- producer: shadow pieces -> shared memory ----------------
         if (elect_one()) {
-            if constexpr (kBRes) {
-                // A ring: one 16 KiB query K block per slot, streamed for every unit.  B ring: the 6 K blocks of this
-                // CTA's half of the corpus tile, loaded once per corpus tile; a slot is refilled when the MMAs of the
-                // tile's LAST query group that read it have retired (b "empty" barrier = slot kASlots + s).
-                uint32_t a_slot = 0, a_phase = 0, b_slot = 0, b_phase = 0;
-                int64_t prev_ct = -1;
-                for (int64_t i = 0; i < sched.n_mine; ++i) {
-                    int64_t ct_rel;
-                    int qg;
-                    sched.get(i, ct_rel, qg);
-                    const int64_t ct = a.ct0 + ct_rel;
-                    const bool new_tile = ct != prev_ct;
-                    prev_ct = ct;
-                    const int qt = qg * 2 + (int)cta_rank;
-                    const uint8_t* srcA = a.q_shadow + (size_t)qt * kb_count * kPieceBytes;
-                    const uint8_t* srcB = a.x_shadow + (size_t)(2 * ct + cta_rank) * kb_count * kPieceBytes;
-                    for (int kb = 0; kb < kb_count; ++kb) {
-                        if (new_tile) {
-                            uint64_t* full = &bars->full[kASlots + b_slot];
-                            wait_or_trap(&bars->empty[kASlots + b_slot], b_phase ^ 1);
-                            mbar_arrive_expect_tx(full, kPieceBytes);
-                            bulk_g2s(smem + (kASlots + b_slot) * kPieceBytes, srcB + (size_t)kb * kPieceBytes, kPieceBytes, full);
-                            if (++b_slot == (uint32_t)b_slots) { b_slot = 0; b_phase ^= 1; }
-                        }
-                        wait_or_trap(&bars->empty[a_slot], a_phase ^ 1);
-                        mbar_arrive_expect_tx(&bars->full[a_slot], kPieceBytes);
-                        bulk_g2s(smem + a_slot * kPieceBytes, srcA + (size_t)kb * kPieceBytes, kPieceBytes, &bars->full[a_slot]);
-                        if (++a_slot == kASlots) { a_slot = 0; a_phase ^= 1; }
-                    }
-                }
-            } else {
             uint32_t stage = 0, phase = 0;
-            for (Iter u(sched); u.valid(); u.next()) {
+            for (UnitIter u(sched); u.valid(); u.next()) {
                 const int64_t ct = a.ct0 + u.ct_rel;
                 const int qt = u.qg * kCG + (int)cta_rank;
                 const uint8_t* srcA = a.q_shadow + (size_t)qt * kb_count * kPieceBytes;
@@ -264,51 +219,12 @@ __global__ void __launch_bounds__(kThreads, 1) scan_mma_kernel(const MmaScanArgs
                     if (++stage == C::kStages) { stage = 0; phase ^= 1; }
                 }
             }
-            }
         }
     } else if (warp == 1) {
         if (leader) {
             // ---------------- MMA issuer ----------------
             if (elect_one()) {
                 constexpr uint32_t idesc = kI8 ? umma_idesc_i8(kTileM * kCG, kTileN) : umma_idesc_f16(kTileM * kCG, kTileN);
-                if constexpr (kBRes) {
-                    uint32_t a_slot = 0, a_phase = 0, b_slot = 0, b_phase = 0, it = 0;
-                    uint32_t cur_b[8];                       // B-ring slot of K block kb of the resident corpus tile (d <= 1024)
-                    int64_t prev_ct = -1;
-                    for (int64_t i = 0; i < sched.n_mine; ++i, ++it) {
-                        int64_t ct_rel, ct_next = -1;
-                        int qg, qg_next;
-                        sched.get(i, ct_rel, qg);
-                        if (i + 1 < sched.n_mine) sched.get(i + 1, ct_next, qg_next);
-                        const bool new_tile = ct_rel != prev_ct;
-                        const bool last_of_tile = ct_next != ct_rel;     // the tile's slots are released behind this unit
-                        prev_ct = ct_rel;
-                        const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
-                        wait_or_trap(&bars->tmem_empty[acc], acc_phase ^ 1);
-                        tc_fence_after();
-                        const uint32_t tmem_d = tmem_base + acc * kTileN;
-                        for (int kb = 0; kb < kb_count; ++kb) {
-                            if (new_tile) {
-                                cur_b[kb] = b_slot;
-                                wait_or_trap(&bars->full[kASlots + b_slot], b_phase);
-                                wait_or_trap(&bars->peer_full[kASlots + b_slot], b_phase);
-                                if (++b_slot == (uint32_t)b_slots) { b_slot = 0; b_phase ^= 1; }
-                            }
-                            wait_or_trap(&bars->full[a_slot], a_phase);
-                            wait_or_trap(&bars->peer_full[a_slot], a_phase);
-                            tc_fence_after();
-                            const uint64_t descA = umma_desc_k128(smem_u32(smem + a_slot * kPieceBytes));
-                            const uint64_t descB = umma_desc_k128(smem_u32(smem + (kASlots + cur_b[kb]) * kPieceBytes));
-#pragma unroll
-                            for (int k = 0; k < 4; ++k)
-                                umma_i8<2>(tmem_d, descA + 2 * k, descB + 2 * k, idesc, (kb | k) != 0);
-                            umma_commit_2cta(&bars->empty[a_slot], 0b11);
-                            if (last_of_tile) umma_commit_2cta(&bars->empty[kASlots + cur_b[kb]], 0b11);
-                            if (kb == kb_count - 1) umma_commit_2cta(&bars->tmem_full[acc], 0b11);
-                            if (++a_slot == kASlots) { a_slot = 0; a_phase ^= 1; }
-                        }
-                    }
-                } else {
                 uint32_t stage = 0, phase = 0, it = 0;
                 for (int64_t i = 0; i < sched.n_mine; ++i, ++it) {
                     const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
@@ -340,32 +256,10 @@ __global__ void __launch_bounds__(kThreads, 1) scan_mma_kernel(const MmaScanArgs
                         if (++stage == C::kStages) { stage = 0; phase ^= 1; }
                     }
                 }
-                }
             }
         } else {
             // ---------------- peer forwarder: my half of the stage has landed ----------------
             if (elect_one()) {
-                if constexpr (kBRes) {
-                    uint32_t a_slot = 0, a_phase = 0, b_slot = 0, b_phase = 0;
-                    int64_t prev_ct = -1;
-                    for (int64_t i = 0; i < sched.n_mine; ++i) {
-                        int64_t ct_rel;
-                        int qg;
-                        sched.get(i, ct_rel, qg);
-                        const bool new_tile = ct_rel != prev_ct;
-                        prev_ct = ct_rel;
-                        for (int kb = 0; kb < kb_count; ++kb) {
-                            if (new_tile) {
-                                wait_or_trap(&bars->full[kASlots + b_slot], b_phase);
-                                mbar_arrive_cluster(&bars->peer_full[kASlots + b_slot], 0);
-                                if (++b_slot == (uint32_t)b_slots) { b_slot = 0; b_phase ^= 1; }
-                            }
-                            wait_or_trap(&bars->full[a_slot], a_phase);
-                            mbar_arrive_cluster(&bars->peer_full[a_slot], 0);
-                            if (++a_slot == kASlots) { a_slot = 0; a_phase ^= 1; }
-                        }
-                    }
-                } else {
                 uint32_t stage = 0, phase = 0;
                 for (int64_t i = 0; i < sched.n_mine; ++i) {
                     for (int kb = 0; kb < kb_count; ++kb) {
@@ -373,7 +267,6 @@ __global__ void __launch_bounds__(kThreads, 1) scan_mma_kernel(const MmaScanArgs
                         mbar_arrive_cluster(&bars->peer_full[stage], 0);
                         if (++stage == C::kStages) { stage = 0; phase ^= 1; }
                     }
-                }
                 }
             }
         }
@@ -437,7 +330,7 @@ __global__ void __launch_bounds__(kThreads, 1) scan_mma_kernel(const MmaScanArgs
             return c;
         };
         UnitConsts cur{};
-        Iter u(sched), ahead(sched);
+        UnitIter u(sched), ahead(sched);
         if (u.valid()) cur = fetch(u.ct_rel, u.qg);
         ahead.next();
         for (; u.valid(); u.next(), ahead.next(), ++it) {
@@ -477,62 +370,50 @@ __global__ void __launch_bounds__(kThreads, 1) scan_mma_kernel(const MmaScanArgs
                     if constexpr (kI8) return fmaf((float)(int)bits, out_scale, shift);
                     else return fmaf(__uint_as_float(bits), out_scale, shift);
                 };
-                // the common case is "no survivor in these 32 columns": one 3-input max per two columns and a single
-                // compare (16 + 1 instructions instead of a compare and a predicate-or per column) - at int8 rates the
-                // epilogue warps have only ~3000 cycles per tile and were co-limiting the scan
+                // The common case is "no survivor in these 32 columns".  Four independent chains of eight columns, one
+                // 3-input max per two columns, and a single compare: 18 instructions, dependency depth 6.  (One chain
+                // of 32 is one instruction shorter and measurably slower - the drain is latency-bound: 37.8 vs 35.4 ms
+                // of scan, profiles/r02_ab_scan_epilogue_hybrid.jsonl.)  The octet maxima also tell the survivor
+                // search below where to look.
                 bool any;
-                bool hit[4] = {true, true, true, true};        // kV = 1: which column octets hold a survivor
-                if constexpr (kV != 0) {
-                    // four independent chains of eight columns (same instruction count as one chain of 32, more ILP);
-                    // their maxima tell the survivor search below which octet to look into
-                    if constexpr (kI8) {
-                        int m[4];
+                bool hit[4] = {true, true, true, true};        // which column octets hold a survivor
+                if constexpr (kI8) {
+                    int m[4];
 #pragma unroll
-                        for (int g = 0; g < 4; ++g) {
-                            m[g] = __vimax3_s32((int)v[8 * g], (int)v[8 * g + 1], (int)v[8 * g + 2]);
-                            m[g] = __vimax3_s32(m[g], (int)v[8 * g + 3], (int)v[8 * g + 4]);
-                            m[g] = __vimax3_s32(m[g], (int)v[8 * g + 5], (int)v[8 * g + 6]);
-                            m[g] = max(m[g], (int)v[8 * g + 7]);
-                        }
-                        any = max(__vimax3_s32(m[0], m[1], m[2]), m[3]) >= thr_c;
-                        if (any) {
-#pragma unroll
-                            for (int g = 0; g < 4; ++g) hit[g] = m[g] >= thr_c;
-                        }
-                    } else {
-                        float m[4];
-#pragma unroll
-                        for (int g = 0; g < 4; ++g) {
-                            m[g] = fmax3(__uint_as_float(v[8 * g]), __uint_as_float(v[8 * g + 1]), __uint_as_float(v[8 * g + 2]));
-                            m[g] = fmax3(m[g], __uint_as_float(v[8 * g + 3]), __uint_as_float(v[8 * g + 4]));
-                            m[g] = fmax3(m[g], __uint_as_float(v[8 * g + 5]), __uint_as_float(v[8 * g + 6]));
-                            m[g] = fmaxf(m[g], __uint_as_float(v[8 * g + 7]));
-                        }
-                        any = fmaxf(fmax3(m[0], m[1], m[2]), m[3]) >= thr_s;
-                        if (any) {
-#pragma unroll
-                            for (int g = 0; g < 4; ++g) hit[g] = m[g] >= thr_s;
-                        }
+                    for (int g = 0; g < 4; ++g) {
+                        m[g] = __vimax3_s32((int)v[8 * g], (int)v[8 * g + 1], (int)v[8 * g + 2]);
+                        m[g] = __vimax3_s32(m[g], (int)v[8 * g + 3], (int)v[8 * g + 4]);
+                        m[g] = __vimax3_s32(m[g], (int)v[8 * g + 5], (int)v[8 * g + 6]);
+                        m[g] = max(m[g], (int)v[8 * g + 7]);
                     }
-                } else if constexpr (kI8) {
-                    int m = (int)v[0];
+                    any = max(__vimax3_s32(m[0], m[1], m[2]), m[3]) >= thr_c;
+                    if (any) {
 #pragma unroll
-                    for (int j = 1; j + 1 < 32; j += 2) m = __vimax3_s32(m, (int)v[j], (int)v[j + 1]);
-                    m = max(m, (int)v[31]);
-                    any = m >= thr_c;
+                        for (int g = 0; g < 4; ++g) hit[g] = m[g] >= thr_c;
+                    }
                 } else {
-                    float m = __uint_as_float(v[0]);
+                    float m[4];
 #pragma unroll
-                    for (int j = 1; j + 1 < 32; j += 2) m = fmax3(m, __uint_as_float(v[j]), __uint_as_float(v[j + 1]));
-                    m = fmaxf(m, __uint_as_float(v[31]));
-                    any = m >= thr_s;
+                    for (int g = 0; g < 4; ++g) {
+                        m[g] = fmax3(__uint_as_float(v[8 * g]), __uint_as_float(v[8 * g + 1]), __uint_as_float(v[8 * g + 2]));
+                        m[g] = fmax3(m[g], __uint_as_float(v[8 * g + 3]), __uint_as_float(v[8 * g + 4]));
+                        m[g] = fmax3(m[g], __uint_as_float(v[8 * g + 5]), __uint_as_float(v[8 * g + 6]));
+                        m[g] = fmaxf(m[g], __uint_as_float(v[8 * g + 7]));
+                    }
+                    any = fmaxf(fmax3(m[0], m[1], m[2]), m[3]) >= thr_s;
+                    if (any) {
+#pragma unroll
+                        for (int g = 0; g < 4; ++g) hit[g] = m[g] >= thr_s;
+                    }
                 }
                 // Survivors are rare once a threshold exists (a few per 100 000 columns), but a warp takes this branch
                 // whenever ONE of its 32 queries has one - every seventh 32-column group at k = 100 - so its length
-                // is what the epilogue's time depends on (k = 1 vs k = 100: 34.4 vs 38.6 ms of scan with the mask code
-                // below alone).  Sparse case: only the octets that hold a survivor are expanded, straight into the stash.
+                // decides how often a tile's drain outlasts the next tile's MMAs (the round-1 code built a 32-bit mask and
+                // walked 32 predicated stores, ~300 instructions: 40.4 vs 35.8 ms of scan, k = 1 vs k = 100 34.4 vs
+                // 38.6 ms).  Sparse case: only the octets that hold a survivor are expanded, straight into the stash.
+                // (Narrowing further to quads is slower again - more branches: 36.6 vs 35.8 ms.)
                 const int n_hit = (int)hit[0] + (int)hit[1] + (int)hit[2] + (int)hit[3];
-                if (kV != 0 && any && n_hit < 4 && stash_n + 8u * (uint32_t)n_hit <= (uint32_t)kStash &&
+                if (any && n_hit < 4 && stash_n + 8u * (uint32_t)n_hit <= (uint32_t)kStash &&
                     a.seg_rows - (row0 + c * 32) >= 32) {
                     const uint32_t row_id = a.row_id_base + (uint32_t)(row0 + c * 32);
                     const uint32_t before = stash_n;
@@ -552,6 +433,7 @@ __global__ void __launch_bounds__(kThreads, 1) scan_mma_kernel(const MmaScanArgs
                     }
                     emitted += stash_n - before;
                 } else if (any) {
+                    // dense case (no threshold yet, ragged segment end, stash full): mask of the 32 columns
                     uint32_t mask = 0;
 #pragma unroll
                     for (int j = 0; j < 32; ++j) mask |= (passes(v[j]) ? 1u : 0u) << j;
@@ -635,15 +517,10 @@ cudaError_t scan_mma_configure() {
     auto set = [&](auto kernel, int bytes) {
         if (e == cudaSuccess) e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
     };
-    set(scan_mma_kernel<1, false, false, 0>, Cfg<1>::kSmemBytes);
-    set(scan_mma_kernel<1, false, false, 1>, Cfg<1>::kSmemBytes);
-    set(scan_mma_kernel<1, true, false, 0>, Cfg<1>::kSmemBytes);
-    set(scan_mma_kernel<1, true, false, 1>, Cfg<1>::kSmemBytes);
-    set(scan_mma_kernel<2, false, false, 0>, Cfg<2>::kSmemBytes);
-    set(scan_mma_kernel<2, false, false, 1>, Cfg<2>::kSmemBytes);
-    set(scan_mma_kernel<2, true, false, 0>, Cfg<2>::kSmemBytes);
-    set(scan_mma_kernel<2, true, false, 1>, Cfg<2>::kSmemBytes);
-    set(scan_mma_kernel<2, true, true, 0>, bres_smem_bytes(kMaxBSlots));
+    set(scan_mma_kernel<1, false>, Cfg<1>::kSmemBytes);
+    set(scan_mma_kernel<1, true>, Cfg<1>::kSmemBytes);
+    set(scan_mma_kernel<2, false>, Cfg<2>::kSmemBytes);
+    set(scan_mma_kernel<2, true>, Cfg<2>::kSmemBytes);
     return e;
 }
 
@@ -665,16 +542,7 @@ cudaError_t launch_pairs(const MmaScanArgs& a, int sm_count, cudaStream_t s) {
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    if constexpr (kI8) {
-        // resident corpus tile: needs the tile's K blocks (d / 128) to fit the B ring
-        if (a.b_slots > 0) {
-            if (a.b_slots > kMaxBSlots || a.b_slots < a.d / kBlockK8) return cudaErrorInvalidValue;
-            cfg.dynamicSmemBytes = bres_smem_bytes(a.b_slots);
-            return cudaLaunchKernelEx(&cfg, scan_mma_kernel<2, true, true, 0>, a);
-        }
-    }
-    if (a.variant != 0) return cudaLaunchKernelEx(&cfg, scan_mma_kernel<2, kI8, false, 1>, a);
-    return cudaLaunchKernelEx(&cfg, scan_mma_kernel<2, kI8, false, 0>, a);
+    return cudaLaunchKernelEx(&cfg, scan_mma_kernel<2, kI8>, a);
 }
 }  // namespace
 
@@ -684,8 +552,7 @@ cudaError_t launch_scan_mma_i8(const MmaScanArgs& a, int sm_count, int cta_group
     if (a.x_tiles == nullptr || a.q_consts == nullptr || a.d % kBlockK8 != 0) return cudaErrorInvalidValue;
     if (cta_group == 2 && (a.n_qtiles % 2) == 0) return launch_pairs<true>(a, sm_count, s);
     const int grid = (int)(n_units < sm_count ? n_units : sm_count);
-    if (a.variant != 0) scan_mma_kernel<1, true, false, 1><<<grid, kThreads, Cfg<1>::kSmemBytes, s>>>(a);
-    else scan_mma_kernel<1, true, false, 0><<<grid, kThreads, Cfg<1>::kSmemBytes, s>>>(a);
+    scan_mma_kernel<1, true><<<grid, kThreads, Cfg<1>::kSmemBytes, s>>>(a);
     return cudaGetLastError();
 }
 
@@ -695,8 +562,7 @@ cudaError_t launch_scan_mma(const MmaScanArgs& a, int sm_count, int cta_group, c
     if (cta_group == 2 && (a.n_qtiles % 2) == 0) return launch_pairs<false>(a, sm_count, s);
     const int64_t n_units = n_ctiles * a.n_qtiles;
     const int grid = (int)(n_units < sm_count ? n_units : sm_count);
-    if (a.variant != 0) scan_mma_kernel<1, false, false, 1><<<grid, kThreads, Cfg<1>::kSmemBytes, s>>>(a);
-    else scan_mma_kernel<1, false, false, 0><<<grid, kThreads, Cfg<1>::kSmemBytes, s>>>(a);
+    scan_mma_kernel<1, false><<<grid, kThreads, Cfg<1>::kSmemBytes, s>>>(a);
     return cudaGetLastError();
 }
 

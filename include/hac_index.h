@@ -233,8 +233,7 @@ int hac_pinned_free(void* host);
  *                    of the rest starts from an exact threshold instead of emitting through many loosely filtered
  *                    early chunks; -1 (default) = automatic (tensor-bound batches on shards >= 8x the slab), 0 = off,
  *                    > 0 = that many rows
- *   "i8_b_slots"     int8 CTA-pair scan: 0 (default) = both operands streamed per unit, 6..8 = the corpus tile stays
- *                    resident in a ring of this many 16 KiB shared-memory slots across its query groups */
+ */
 int hac_set_option(hac_index* idx, const char* name, int64_t value);
 
 /* ---- introspection --------------------------------------------------------------------------- */

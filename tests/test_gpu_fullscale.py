@@ -74,16 +74,15 @@ def test_headline_batch_all_query_tiles_against_fp64_arbiter(big_index):
     assert np.all(np.diff(Dn, axis=1) <= 0) and In.min() >= 0 and In.max() < N_ROWS
     for i in range(n_planted):
         assert In[i, 0] == N_ROWS - n_planted + i
-    # the pipelined schedule, the streamed-operand CTA-pair scan and the single-CTA scan return bitwise the same
-    # 2514 x 100 result as the default (chunk-synchronous schedule, resident corpus tile)
-    assert st["pipelined"] == 0
+    # the pipelined schedule, the search without the f16 warm start and the single-CTA scan return bitwise the same
+    # 2514 x 100 result as the default (chunk-synchronous schedule behind a warm start, CTA pairs)
+    assert st["pipelined"] == 0 and st["warm_rows"] > 0, st
     idx.set_option("i8_pipeline", 1)
-    idx.set_option("i8_b_slots", 6)
     D2, I2 = idx.search(q_all, 100)
     assert idx.stats()["pipelined"] == 1
     idx.set_option("i8_pipeline", 0)
     assert torch.equal(I2, I) and torch.equal(D2, D)
-    for opt, val, back in (("i8_b_slots", 0, 8), ("i8_b_slots", 7, 8), ("i8_cta_group", 1, 2)):
+    for opt, val, back in (("i8_warm_rows", 0, -1), ("i8_warm_rows", 65536, -1), ("i8_cta_group", 1, 2)):
         idx.set_option(opt, val)
         D3, I3 = idx.search(q_all, 100)
         idx.set_option(opt, back)

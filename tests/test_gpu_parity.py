@@ -654,22 +654,14 @@ def test_int8_screen_cta_pairs_and_unit_schedules(nq, n, k):
     Dm, Im = idx.search(q, k, path=hb.HAC_PATH_MMA)
     for cg in (1, 2):
         for tile_major in (0, 1):
-            # b_slots: the CTA-pair scan keeps the corpus tile resident across its query groups (ring of 7 / 8 slots)
-            for b_slots in ((0, 7, 8) if (cg == 2 and tile_major == 1) else (8,)):
-                idx.set_option("i8_cta_group", cg)
-                idx.set_option("scan_tile_major", tile_major)
-                idx.set_option("i8_b_slots", b_slots)
-                D8, I8 = idx.search(q, k, path=hb.HAC_PATH_I8)
-                st = idx.stats()
-                assert st["path"] == hb.HAC_PATH_I8 and st["retries"] == 0, (cg, tile_major, b_slots, st)
-                assert np.array_equal(I8, Im) and np.array_equal(D8, Dm), (cg, tile_major, b_slots)
-            for variant in (0, 1):                                   # both epilogue / bookkeeping variants of the kernel
-                idx.set_option("scan_variant", variant)
-                idx.set_option("i8_b_slots", 0)
-                D8, I8 = idx.search(q, k, path=hb.HAC_PATH_I8)
-                assert np.array_equal(I8, Im) and np.array_equal(D8, Dm), (cg, tile_major, variant)
-                Df, If = idx.search(q, k, path=hb.HAC_PATH_MMA)      # the f16 scan under the same schedule
-                assert np.array_equal(If, Im) and np.array_equal(Df, Dm), (cg, tile_major, variant)
+            idx.set_option("i8_cta_group", cg)
+            idx.set_option("scan_tile_major", tile_major)
+            D8, I8 = idx.search(q, k, path=hb.HAC_PATH_I8)
+            st = idx.stats()
+            assert st["path"] == hb.HAC_PATH_I8 and st["retries"] == 0, (cg, tile_major, st)
+            assert np.array_equal(I8, Im) and np.array_equal(D8, Dm), (cg, tile_major)
+            Df, If = idx.search(q, k, path=hb.HAC_PATH_MMA)          # the f16 scan under the same schedule
+            assert np.array_equal(If, Im) and np.array_equal(Df, Dm), (cg, tile_major)
     _check(q, x, k, Dm, Im, also_fp32_oracle=False)
 
 
