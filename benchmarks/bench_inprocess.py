@@ -83,7 +83,8 @@ def main():
                       "exchange": bool(sharded and index.threshold_exchange),
                       "rescored_pairs_per_shard": [int(s["candidates_rescored"]) for s in st],
                       "local_total_ms_per_shard": [round(float(s["total_ms"]), 3) for s in st],
-                      "setup_s": round(setup_s, 2)}))
+                      "setup_s": round(setup_s, 2),
+                      "host_phases_ms_last_search": getattr(index, "last_phase_ms", None)}))
     assert ok
 
 

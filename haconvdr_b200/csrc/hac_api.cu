@@ -259,7 +259,7 @@ int64_t pick_warm_rows(const hac_index* idx, int nq, int k) {
     if (want < 0) {
         // tensor-bound batches only: an f16 row costs twice an int8 row, every e-fold of warm rows saves one e-fold of
         // loosely filtered int8 emission (optimum ~4e5 rows whatever the corpus size, flat around it)
-        if (nq < 256) return 0;
+        if (nq < 128) return 0;                               // Q = 128: 4.04 vs 4.15 ms with it, Q <= 32: slower (HBM-bound, an f16 row is twice the bytes)
         // measured at 25.7M x 2514 (profiles/r02_ab_warm_start_and_scan_sms.jsonl): 128k rows 46.2 ms, 256k 44.4, 384k 44.8,
         // 768k 44.0 against 48.0 without; rescored pairs 19.9M -> 9.6M
         want = std::min<int64_t>(786432, std::max<int64_t>(32768, idx->ntotal / 32));
@@ -650,7 +650,10 @@ int search_batch_i8(hac_index* idx, int nq, int nq_pad, const float* q_dev, int 
     }
     // A: scans (and everything before the first one); B: workers and the final select.  The caller's stream is
     // ordered before A at the start and after A at the end.
-    cudaStream_t A = idx->stream, B = idx->side;
+    // Without pipelined chunks everything is one dependency chain: it runs on A alone (no cross-stream event hops at the
+    // chunk boundaries, two driver calls less per chunk).
+    const bool two_streams = n_sync < (int)plan.size();
+    cudaStream_t A = idx->stream, B = two_streams ? idx->side : idx->stream;
     if (s != A) {
         CU(cudaEventRecord(idx->ev_in, s));
         CU(cudaStreamWaitEvent(A, idx->ev_in, 0));
@@ -732,7 +735,7 @@ int search_batch_i8(hac_index* idx, int nq, int nq_pad, const float* q_dev, int 
         const ChunkPlan& ch = plan[i];
         const Segment& seg = idx->segs[ch.seg];
         const int dep = i - ch.dist;
-        if (dep > waited) {
+        if (two_streams && dep > waited) {
             CU(cudaStreamWaitEvent(A, idx->wdone[dep], 0));
             waited = dep;
         }
@@ -758,22 +761,20 @@ int search_batch_i8(hac_index* idx, int nq, int nq_pad, const float* q_dev, int 
         a.cb = lg[i & 1];
         CU(launch_scan_mma_i8(a, idx->sm_count, idx->i8_cta_group, A));
         CU(cudaEventRecord(ev_stop, A));
-        // worker of the chunk, on the side stream
-        CU(cudaStreamWaitEvent(B, ev_stop, 0));
+        // worker of the chunk (on the side stream when chunks are pipelined)
+        if (two_streams) CU(cudaStreamWaitEvent(B, ev_stop, 0));
         if (!launch_rescore_log(lg[i & 1], cb, q_dev, d, segs, nq, w.tau, w.scalars + 2, w.counters + 1, B))
             return fail(HAC_E_INVALID, "int8 search: unsupported dimension");
-        launch_refresh(cb, k, w.margin, w.tau, w.thr, nq, B, use_ex ? &ex : nullptr, lg[i & 1].count, /*small_cta=*/true);
-        CU(cudaEventRecord(idx->wdone[i], B));
+        launch_refresh(cb, k, w.margin, w.tau, w.thr, nq, B, use_ex ? &ex : nullptr, lg[i & 1].count, /*small_cta=*/two_streams);
+        if (two_streams) CU(cudaEventRecord(idx->wdone[i], B));
         launches += 3;
-    }
-    if (n_chunks == 0) {                   // the whole shard was the warm start: B has not been ordered behind A yet
-        CU(cudaEventRecord(idx->ev_join, A));
-        CU(cudaStreamWaitEvent(B, idx->ev_join, 0));
     }
     launch_final_select(cb, k, nq, idx->id_table, idx->id_base, D_dev, I_dev, /*use_score=*/true, B);
     ++launches;
-    CU(cudaEventRecord(idx->ev_join, B));
-    CU(cudaStreamWaitEvent(A, idx->ev_join, 0));
+    if (two_streams) {
+        CU(cudaEventRecord(idx->ev_join, B));
+        CU(cudaStreamWaitEvent(A, idx->ev_join, 0));
+    }
     cudaEventRecord(idx->ev[1], A);
     CU(cudaGetLastError());
     CU(cudaMemcpyAsync(&hr->overflow, cb.overflow, sizeof(uint32_t), cudaMemcpyDeviceToHost, A));

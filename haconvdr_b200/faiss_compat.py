@@ -138,6 +138,7 @@ class ShardedInProcessIndex:
         self._res_cap = 0
         self._q_pinned = None
         self._out_pinned = None
+        self.last_phase_ms = None
 
     def _set_ids(self, g):
         rows = self._rows[g]
@@ -190,8 +191,10 @@ class ShardedInProcessIndex:
             self._words_cap = cap
 
     def search(self, q, k):
+        import time
         torch = self._torch
         from .index import merge_topk_peers_device
+        t_start = time.perf_counter()
         q = np.ascontiguousarray(q, dtype=np.float32)
         assert q.ndim == 2 and q.shape[1] == self.d, "search: expected [nq, %d] float32" % self.d
         nq, k, G = q.shape[0], int(k), len(self.shards)
@@ -204,17 +207,24 @@ class ShardedInProcessIndex:
         armed = self.threshold_exchange and self._peer_ok and self._words is not None and G > 1
         outs = [(D[:nq * k].view(nq, k), I[:nq * k].view(nq, k)) for D, I in self._res]
 
+        t_shard = [None] * G
+
         def one(g):
+            t0 = time.perf_counter()
             dev, sh = self.devices[g], self.shards[g]
             with torch.cuda.device(dev), torch.cuda.stream(self._streams[g]):
                 qd = qp.to(torch.device("cuda", dev), non_blocking=True)
                 sh.set_option("exchange_epoch", self._epoch if armed else 0)
+                t1 = time.perf_counter()
                 try:
                     sh.search(qd, k, out=outs[g])
                 finally:
                     sh.set_option("exchange_epoch", 0)
                 self._events[g].record(self._streams[g])
+            t_shard[g] = (t0 - t_start, t1 - t_start, time.perf_counter() - t_start)
+        t_prep = time.perf_counter()
         list(self._pool.map(one, range(G)))              # re-raises the first shard failure after all have finished
+        t_threads = time.perf_counter()
         dev0 = self.devices[0]
         with torch.cuda.device(dev0), torch.cuda.stream(self._streams[0]):
             for ev in self._events[1:]:
@@ -233,7 +243,14 @@ class ShardedInProcessIndex:
             Dh.copy_(Dm, non_blocking=True)
             Ih.copy_(Im, non_blocking=True)
             self._streams[0].synchronize()
-        return Dh.numpy().copy(), Ih.numpy().copy()
+        t_merge = time.perf_counter()
+        out = Dh.numpy().copy(), Ih.numpy().copy()
+        # host-side phases of the last search, ms since entry: query staging, per-shard (thread start, C call start, C call
+        # end), merge + D2H, result copies
+        self.last_phase_ms = {"prep": 1e3 * (t_prep - t_start), "shards": [[round(1e3 * v, 3) for v in t] for t in t_shard],
+                              "threads_done": 1e3 * (t_threads - t_start), "merge_d2h_done": 1e3 * (t_merge - t_start),
+                              "total": 1e3 * (time.perf_counter() - t_start)}
+        return out
 
     def stats(self):
         return [sh.stats() for sh in self.shards]
