@@ -648,7 +648,7 @@ def run_ours(args):
         config.update({"ks": list(SWEEP_KS), "l2": "inputs larger than L2"})
         line.update({
             "value": s100["queries_per_s"], "ms_per_step": s100["ms_per_step"],
-            "dtype": "int8 screen (k <= 128) / f16 screen (k = 1000) + f32 exact rescore", "config": config, "sweep": sweep,
+            "dtype": "int8 screen (s32 accumulate; f16 warm slab sized by k) + f32 exact rescore", "config": config, "sweep": sweep,
             "e2e": {"value": s100["e2e_queries_per_s"], "unit": "queries/s", "h2d_bytes_per_step": int(h.q_host.nbytes),
                     "d2h_bytes_per_step": int(args.queries * 100 * 12)},
             "gpu_launches": int(s100["launches"] * args.steps),

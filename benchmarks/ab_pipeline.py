@@ -35,9 +35,13 @@ VARIANTS = [
     ("sync_w384k_g35", {"i8_warm_rows": 393216, "i8_chunk_growth_x100": 35}),
     ("sync_w384k_g100", {"i8_warm_rows": 393216, "i8_chunk_growth_x100": 100}),
     ("pipe_w384k", {"i8_pipeline": 1, "i8_warm_rows": 393216}),
+    # unit order of the int8 scan behind the default warm start: tile-major (every pair streams queries AND corpus) against
+    # query-stationary (a pair keeps its query tiles in shared memory, lanes of pairs walk the corpus in step)
+    ("def_tm", {"i8_warm_rows": -1, "scan_tile_major": 1}),
+    ("def_qs", {"i8_warm_rows": -1, "scan_tile_major": 2}),
 ]
 DEFAULTS = {"i8_pipeline": 0, "i8_pipe_growth_x1000": 125, "i8_pipe_min_rows": 0, "i8_pipe_dist": 2,
-            "i8_chunk_growth_x100": 0, "i8_warm_rows": 0}
+            "i8_chunk_growth_x100": 0, "i8_warm_rows": 0, "scan_tile_major": -1}
 
 
 def main():

@@ -17,7 +17,7 @@ CSRC = os.path.join(_HERE, "csrc")
 HAC_PATH_AUTO, HAC_PATH_GEMV, HAC_PATH_MMA, HAC_PATH_I8 = 0, 1, 2, 3
 HAC_MAX_K = 1024
 
-HAC_ABI_VERSION = 2
+HAC_ABI_VERSION = 3
 HAC_EXCHANGE_WORDS_PER_QUERY = 16
 
 c_i64 = ctypes.c_int64
@@ -63,6 +63,13 @@ SIGNATURES = {
     "hac_merge_topk_peers_device": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, c_i64, ctypes.c_int,
                                                    ctypes.POINTER(_VP), ctypes.POINTER(_VP), ctypes.c_int, _VP, _VP, _VP]),
     "hac_enable_peer_access": (ctypes.c_int, [ctypes.c_int, ctypes.c_int]),
+    "hac_shards_create": (ctypes.c_int, [ctypes.POINTER(_VP), ctypes.c_int, ctypes.POINTER(_VP)]),
+    "hac_shards_destroy": (ctypes.c_int, [_VP]),
+    "hac_shards_search": (ctypes.c_int, [_VP, c_i64, _VP, ctypes.c_int, _VP, _VP]),
+    "hac_shards_search_device": (ctypes.c_int, [_VP, c_i64, _VP, ctypes.c_int, _VP, _VP, _VP]),
+    "hac_shards_set_exchange": (ctypes.c_int, [_VP, ctypes.c_int]),
+    "hac_shards_peer_access": (ctypes.c_int, [_VP]),
+    "hac_shards_last_phases": (ctypes.c_int, [_VP, c_f32p, ctypes.c_int]),
     "hac_gather_ids_device": (ctypes.c_int, [ctypes.c_int, _VP, c_i64, _VP, c_i64, _VP, _VP]),
     "hac_set_threshold_exchange": (ctypes.c_int, [_VP, _VP, ctypes.POINTER(_VP), ctypes.c_int, c_i64]),
     "hac_reciprocal_rank_device": (ctypes.c_int, [ctypes.c_int, _VP, c_i64, ctypes.c_int, _VP, _VP, _VP, _VP, _VP]),

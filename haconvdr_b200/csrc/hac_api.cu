@@ -83,6 +83,11 @@ struct Workspace {
 
 }  // namespace
 
+namespace hac {
+// hac_shards.cu reports its failures through the same per-thread message as every other entry point
+int set_last_error(int code, const std::string& msg) { return fail(code, msg); }
+}  // namespace hac
+
 struct hac_index {
     int d = 0, device = 0, sm_count = 148;
     // stream: the handle's own stream (host API) and the stream every int8 scan runs on - highest priority, so that
@@ -155,7 +160,10 @@ struct hac_index {
     // the f16 image (rows*d*2 bytes) is only read by the f16 screen (k > i8_auto_max_k, int8 overflow fallback, forced
     // HAC_PATH_MMA): with the int8 image present it is built on first use instead of on add (25.7M rows: 138 -> 99 GB)
     int lazy_f16 = -1;                      // -1 = lazy exactly when the int8 image is built; 0 / 1 = forced
-    int i8_auto_max_k = 128;                // HAC_PATH_AUTO takes the int8 screen up to this k (its shortlist grows with k * e^(m8*z/sigma))
+    // HAC_PATH_AUTO takes the int8 screen up to this k.  Its shortlist grows with k * e^(m8*z/sigma): with a warm slab
+    // sized by k it still wins at k = 1000 (70.7 vs 75.5 ms at 25.7M x 2514, 49.1 vs 72.4 ms at k = 250) and the 39 GB
+    // f16 image of the corpus is never built
+    int i8_auto_max_k = HAC_MAX_K;
     int default_path = HAC_PATH_MMA;        // what HAC_PATH_AUTO resolves to
     int i8_auto_max_queries = kMaxQueryBatch;          // HAC_PATH_AUTO takes the int8 screen up to this batch size when the image exists
 };
@@ -253,17 +261,25 @@ void convert_f16_rows(hac_index* idx, Segment* seg, int64_t end, cudaStream_t s)
 
 // rows the int8 search scans with the f16 screen first (multiple of kRowAlign; 0 = no warm start)
 int64_t pick_warm_rows(const hac_index* idx, int nq, int k) {
-    if (idx->segs.empty() || idx->i8_warm_rows == 0 || k > 128) return 0;
+    if (idx->segs.empty() || idx->i8_warm_rows == 0) return 0;
     const int64_t have = idx->segs[0].n_rows / kRowAlign * kRowAlign;
     int64_t want = idx->i8_warm_rows;
     if (want < 0) {
         // tensor-bound batches only: an f16 row costs twice an int8 row, every e-fold of warm rows saves one e-fold of
-        // loosely filtered int8 emission (optimum ~4e5 rows whatever the corpus size, flat around it)
+        // loosely filtered int8 emission (~k * A rescored rows per query, A = e^(m8*z/sigma) ~ 6-9).  The two marginal
+        // costs meet at ~5000 * k rows whatever the corpus or batch size, and the optimum is flat around it.
         if (nq < 128) return 0;                               // Q = 128: 4.04 vs 4.15 ms with it, Q <= 32: slower (HBM-bound, an f16 row is twice the bytes)
-        // measured at 25.7M x 2514 (profiles/r02_ab_warm_start_and_scan_sms.jsonl): 128k rows 46.2 ms, 256k 44.4, 384k 44.8,
-        // 768k 44.0 against 48.0 without; rescored pairs 19.9M -> 9.6M
-        want = std::min<int64_t>(786432, std::max<int64_t>(32768, idx->ntotal / 32));
-        if (idx->ntotal < 8 * want) return 0;
+        if (k <= 128) {
+            // measured at 25.7M x 2514 (profiles/r02_ab_warm_start_and_scan_sms.jsonl): 128k rows 46.2 ms, 256k 44.4, 384k 44.8,
+            // 768k 44.0 against 48.0 without; rescored pairs 19.9M -> 9.6M
+            want = std::min<int64_t>(786432, std::max<int64_t>(32768, idx->ntotal / 32));
+            if (idx->ntotal < 8 * want) return 0;
+        } else {
+            // k = 250: 49.1 ms with 768k rows, 50.8 with 1.5M, 51.1 with 3M (f16 screen alone: 72.4); k = 1000: 77.8 / 73.9 /
+            // 70.7 (f16: 75.5; without a warm start 117.5) - profiles/r02_ab_k_large.jsonl
+            want = std::min<int64_t>((int64_t)6144 * k, idx->ntotal / 4);
+            if (want < 32768) return 0;
+        }
     }
     want = std::min(want / kRowAlign * kRowAlign, have);
     return want >= 4096 ? want : 0;
@@ -557,6 +573,7 @@ void plan_chunks_i8(const hac_index* idx, int nq, int nq_pad, int k, uint32_t lo
         sync_growth = idx->i8_chunk_growth > 0.0 ? idx->i8_chunk_growth
                       : few ? 4.0
                       : (nq >= 512 && k <= 128 && start_row >= (1 << 17)) ? 0.35      // behind a warm start: few chunks, all long
+                      : (nq >= 512 && k > 128 && start_row > 0) ? 0.5                 // k = 250: 0.35 / 0.5 / 1.0 -> 49.1 / 49.2 / 51.7 ms; k = 1000: 77.8 / 78.1 / 82.4
                       : (nq >= 512 && k <= 128 && start_row > 0) ? 0.5
                       : (nq >= 512 && k <= 128 && idx->ntotal >= (8ll << 20)) ? 0.6
                       : (nq >= 512 && k <= 128 && idx->ntotal >= (1ll << 20)) ? 1.0
@@ -818,10 +835,10 @@ int search_batch(hac_index* idx, int nq, const float* q_dev, int k, float* D_dev
     bool have_i8 = !idx->segs.empty();
     for (const auto& sg : idx->segs) have_i8 = have_i8 && sg.shadow8 != nullptr;
     if (path == HAC_PATH_AUTO) {
-        // with the int8 image present its screen wins whenever the shortlist stays small (k <= 128): large batches run
-        // the tensor pipe at the int8 rate (38.5 vs 74.4 ms of scan at 25.7M x 2514), small ones stream half the bytes
-        // (Q=1: 2.8 vs 5.4 ms); rescoring its ~10^4 emitted rows per query runs at the HBM rate.  Larger k and corpora
-        // that overflowed it go to the f16 screen.
+        // with the int8 image present its screen wins at every k and batch size: large batches run the tensor pipe at
+        // the int8 rate (38.5 vs 74.4 ms of scan at 25.7M x 2514), small ones stream half the bytes (Q=1: 2.8 vs 5.4
+        // ms); rescoring its ~10^4 emitted rows per query (k = 100) runs at the HBM rate, and for larger k the f16 warm
+        // slab grows with k.  Corpora that overflowed it go to the f16 screen.
         const bool take_i8 = have_i8 && idx->default_path == HAC_PATH_MMA && !idx->i8_overflowed &&
                              k <= idx->i8_auto_max_k && nq <= idx->i8_auto_max_queries;
         path = take_i8 ? HAC_PATH_I8 : idx->default_path;
@@ -1632,7 +1649,11 @@ int hac_set_option(hac_index* idx, const char* name, int64_t value) {
         }
         return HAC_OK;
     }
-    if (strcmp(name, "scan_tile_major") == 0) { idx->scan_tile_major = value < 0 ? -1 : (value != 0); return HAC_OK; }
+    if (strcmp(name, "scan_tile_major") == 0) {
+        if (value > 2) return fail(HAC_E_INVALID, "scan_tile_major must be -1, 0, 1 or 2");
+        idx->scan_tile_major = value < 0 ? -1 : (int)value;
+        return HAC_OK;
+    }
     if (strcmp(name, "i8_cta_group") == 0) {
         if (value != 1 && value != 2) return fail(HAC_E_INVALID, "i8_cta_group must be 1 or 2");
         idx->i8_cta_group = (int)value;

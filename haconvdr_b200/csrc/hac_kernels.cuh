@@ -144,7 +144,8 @@ struct MmaScanArgs {
     const float* center_norm;   // int8 path: pointer to ||c|| (device), or nullptr
     int d;
     int n_qtiles;
-    int tile_major;         // 1: every CTA walks whole corpus tiles (all query tiles back to back); 0: units striped
+    int tile_major;         // 1: every CTA walks whole corpus tiles (all query tiles back to back); 0: units striped;
+                            // 2: query-stationary CTA pairs (int8 screen with CTA pairs only, else as 1)
     int64_t ct0, ct1;       // 256-row tiles of the segment
     int64_t seg_rows;       // valid rows of the segment
     uint32_t row_id_base;

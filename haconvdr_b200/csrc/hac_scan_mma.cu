@@ -22,8 +22,15 @@
 // Unit order (UnitSchedule): tile-major for int8 (every CTA group takes whole 256-row corpus tiles and runs all
 // query tiles of a tile back to back: one HBM fetch per tile, L2 re-reads from the same SMs), striped for f16
 // (consecutive CTAs take the query tiles of one corpus tile) - each measured faster for its kind.
+// Query-stationary form (kQS, int8 CTA pairs, "scan_tile_major" = 2): a CTA pair keeps ONE query tile pair for the whole
+// launch - its int8 image (d/128 pieces of 16 KiB per CTA) is loaded once and stays in shared memory - and only the
+// corpus pieces stream through an 8-stage ring.  The pairs form lanes of n_qgroups pairs that walk the same corpus
+// tiles at the same time (one HBM fetch, L2 hits for the others), so the L2 -> SM operand traffic per MMA is half of
+// the tile-major form's, which is what the power-capped clock pays for.
 // Roofline: tensor pipe (HBM for batches of one query tile); algorithmic work = 2 * queries * rows * d per launch.
 #include <limits.h>
+
+#include <algorithm>
 
 #include "hac_common.cuh"
 #include "hac_kernels.cuh"
@@ -36,7 +43,8 @@ constexpr int kTileM = 128;                                // queries per CTA ti
 constexpr int kTileN = 256;                                // corpus rows per tile (TMEM columns)
 constexpr int kThreads = 320;                              // producer warp, MMA warp, 8 epilogue warps
 constexpr int kStash = 16;                                 // per-thread survivors kept until the TMEM buffer is released
-constexpr int kMaxStages = 6;                              // barrier slots (pipeline stages)
+constexpr int kMaxStages = 8;                              // barrier slots (pipeline stages)
+constexpr int kSmemQS = 232448;                            // query-stationary form: all 227 KiB a CTA may have
 
 template <int kCG>
 struct Cfg {
@@ -53,6 +61,8 @@ struct Barriers {
     uint64_t empty[kMaxStages];      // the MMAs reading the stage have retired
     uint64_t tmem_full[2];           // accumulator buffer complete
     uint64_t tmem_empty[2];          // (leader only when kCG = 2) accumulator buffer drained
+    uint64_t a_full;                 // query-stationary form: this CTA's resident query pieces have landed
+    uint64_t peer_a_full;            // (leader only) the peer CTA's resident query pieces have landed
     uint32_t tmem_base;
 };
 
@@ -106,12 +116,31 @@ __device__ __forceinline__ float fmax3(float a, float b, float c) {
 // staying in step; the int8 scan, whose units are half as long, drifted apart and re-fetched every tile ~7 times:
 // ncu DRAM read 93.6 GB for 13.2 GB of rows, L2 hit rate 64 %.)
 // Tail: the last (n_ct mod G) tiles, fewer than one per group, are striped unit by unit for load balance.
+// Query-stationary (mode 2): group b keeps query group b % n_qg and belongs to lane b / n_qg of G / n_qg lanes; lane l takes
+// the corpus tiles l, l + lanes, l + 2 lanes, ... - the n_qg groups of a lane read the same tile at the same time.
 struct UnitSchedule {
     int64_t G, b, body_rounds, body_units, n_mine;
     int n_qg;
     int g_div, g_mod;                // G = g_div * n_qg + g_mod: one striped step advances g_div tiles and g_mod query groups
-    __device__ UnitSchedule(int64_t n_ct, int n_qgroups, int64_t n_groups, int64_t group, bool tile_major) {
+    bool qs;
+    int64_t qs_lanes, qs_lane;
+    int qs_qg;
+    __device__ UnitSchedule(int64_t n_ct, int n_qgroups, int64_t n_groups, int64_t group, int mode) {
         G = n_groups; b = group; n_qg = n_qgroups;
+        qs = mode == 2;
+        const bool tile_major = mode != 0;
+        if (qs) {
+            qs_lanes = G / n_qg;
+            qs_lane = b / n_qg;
+            qs_qg = (int)(b - qs_lane * n_qg);
+            body_rounds = 0;
+            n_mine = (qs_lane < qs_lanes && qs_lane < n_ct) ? (n_ct - qs_lane + qs_lanes - 1) / qs_lanes : 0;
+            body_units = n_mine;
+            g_div = g_mod = 0;
+            return;
+        }
+        qs_lanes = qs_lane = 0;
+        qs_qg = 0;
         body_rounds = tile_major ? n_ct / G : 0;
         body_units = body_rounds * n_qg;
         const int64_t tail_units = (n_ct - body_rounds * G) * n_qg;
@@ -121,7 +150,10 @@ struct UnitSchedule {
     }
     // i-th unit of this group -> (corpus tile relative to ct0, query group)
     __device__ __forceinline__ void get(int64_t i, int64_t& ct_rel, int& qg) const {
-        if (i < body_units) {
+        if (qs) {
+            ct_rel = qs_lane + i * qs_lanes;
+            qg = qs_qg;
+        } else if (i < body_units) {
             const int64_t r = i / n_qg;
             ct_rel = r * G + b;
             qg = (int)(i - r * n_qg);
@@ -149,7 +181,9 @@ struct UnitIter {
     __device__ __forceinline__ void next() {
         ++i;
         if (i >= s.n_mine) return;
-        if (i == s.body_units) {
+        if (s.qs) {
+            ct_rel += s.qs_lanes;
+        } else if (i == s.body_units) {
             s.get(i, ct_rel, qg);
         } else if (i < s.body_units) {           // tile-major body: all query groups of a tile, then the tile G further
             if (++qg == s.n_qg) { qg = 0; ct_rel += s.G; }
@@ -161,21 +195,27 @@ struct UnitIter {
     }
 };
 
-template <int kCG, bool kI8>
+template <int kCG, bool kI8, bool kQS = false>
 __global__ void __launch_bounds__(kThreads, 1) scan_mma_kernel(const MmaScanArgs a) {
     using C = Cfg<kCG>;
+    static_assert(!kQS || (kCG == 2 && kI8), "the query-stationary form exists for int8 CTA pairs");
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    Barriers* bars = reinterpret_cast<Barriers*>(smem + C::kStages * C::kStageBytes);
-    constexpr int n_bar_slots = C::kStages;
-
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int kb_count = a.d / (kI8 ? kBlockK8 : kBlockK);
+    // query-stationary: [resident query pieces][ring of corpus pieces]; else [ring of (query, corpus) stages]
+    const int resident_bytes = kQS ? kb_count * kPieceBytes : 0;
+    const int stage_bytes = kQS ? kPieceBytes : C::kStageBytes;
+    const int n_stages = kQS ? min(kMaxStages, (kSmemQS - 1024 - 512 - resident_bytes) / kPieceBytes) : C::kStages;
+    uint8_t* ring = smem + resident_bytes;
+    Barriers* bars = reinterpret_cast<Barriers*>(ring + n_stages * stage_bytes);
+    const int n_bar_slots = n_stages;
+
     const uint32_t cta_rank = kCG == 2 ? cluster_ctarank() : 0u;
     const bool leader = cta_rank == 0;
     // work unit: (corpus tile of 256 rows) x (query tile of 128*kCG queries); one unit per CTA group
     const int n_qgroups = a.n_qtiles / kCG;
-    const UnitSchedule sched(a.ct1 - a.ct0, n_qgroups, gridDim.x / kCG, blockIdx.x / kCG, a.tile_major != 0);
+    const UnitSchedule sched(a.ct1 - a.ct0, n_qgroups, gridDim.x / kCG, blockIdx.x / kCG, kQS ? 2 : (a.tile_major != 0 ? 1 : 0));
 
     if constexpr (kCG == 2) cluster_sync_all();          // both CTAs resident before any cross-CTA traffic
     if (threadIdx.x == 0) {
@@ -188,6 +228,8 @@ __global__ void __launch_bounds__(kThreads, 1) scan_mma_kernel(const MmaScanArgs
             mbar_init(&bars->tmem_full[i], 1);
             mbar_init(&bars->tmem_empty[i], 256 * kCG);      // every epilogue thread of the CTA group arrives
         }
+        mbar_init(&bars->a_full, 1);
+        mbar_init(&bars->peer_a_full, 1);
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc<kCG>(&bars->tmem_base, 512);
@@ -200,6 +242,15 @@ __global__ void __launch_bounds__(kThreads, 1) scan_mma_kernel(const MmaScanArgs
         // ---------------- producer: shadow pieces -> shared memory ----------------
         if (elect_one()) {
             uint32_t stage = 0, phase = 0;
+            if constexpr (kQS) {
+                if (sched.n_mine > 0) {                  // the pair's query tile: loaded once, resident for the launch
+                    const int qt = sched.qs_qg * kCG + (int)cta_rank;
+                    const uint8_t* srcA = a.q_shadow + (size_t)qt * kb_count * kPieceBytes;
+                    mbar_arrive_expect_tx(&bars->a_full, (uint32_t)resident_bytes);
+                    for (int kb = 0; kb < kb_count; ++kb)
+                        bulk_g2s(smem + kb * kPieceBytes, srcA + (size_t)kb * kPieceBytes, kPieceBytes, &bars->a_full);
+                }
+            }
             for (UnitIter u(sched); u.valid(); u.next()) {
                 const int64_t ct = a.ct0 + u.ct_rel;
                 const int qt = u.qg * kCG + (int)cta_rank;
@@ -208,15 +259,20 @@ __global__ void __launch_bounds__(kThreads, 1) scan_mma_kernel(const MmaScanArgs
                 const uint8_t* srcB = a.x_shadow + (size_t)(2 * ct + (kCG == 2 ? cta_rank : 0)) * kb_count * kPieceBytes;
                 for (int kb = 0; kb < kb_count; ++kb) {
                     wait_or_trap(&bars->empty[stage], phase ^ 1);
-                    uint8_t* sA = smem + stage * C::kStageBytes;
-                    uint8_t* sB = sA + C::kABytes;
-                    mbar_arrive_expect_tx(&bars->full[stage], C::kStageBytes);
-                    bulk_g2s(sA, srcA + (size_t)kb * kPieceBytes, kPieceBytes, &bars->full[stage]);
-                    bulk_g2s(sB, srcB + (size_t)kb * kPieceBytes, kPieceBytes, &bars->full[stage]);
-                    if constexpr (kCG == 1)
-                        bulk_g2s(sB + kPieceBytes, srcB + (size_t)(kb_count + kb) * kPieceBytes, kPieceBytes,
-                                 &bars->full[stage]);
-                    if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+                    if constexpr (kQS) {
+                        mbar_arrive_expect_tx(&bars->full[stage], kPieceBytes);
+                        bulk_g2s(ring + stage * kPieceBytes, srcB + (size_t)kb * kPieceBytes, kPieceBytes, &bars->full[stage]);
+                    } else {
+                        uint8_t* sA = ring + stage * C::kStageBytes;
+                        uint8_t* sB = sA + C::kABytes;
+                        mbar_arrive_expect_tx(&bars->full[stage], C::kStageBytes);
+                        bulk_g2s(sA, srcA + (size_t)kb * kPieceBytes, kPieceBytes, &bars->full[stage]);
+                        bulk_g2s(sB, srcB + (size_t)kb * kPieceBytes, kPieceBytes, &bars->full[stage]);
+                        if constexpr (kCG == 1)
+                            bulk_g2s(sB + kPieceBytes, srcB + (size_t)(kb_count + kb) * kPieceBytes, kPieceBytes,
+                                     &bars->full[stage]);
+                    }
+                    if (++stage == (uint32_t)n_stages) { stage = 0; phase ^= 1; }
                 }
             }
         }
@@ -226,6 +282,12 @@ __global__ void __launch_bounds__(kThreads, 1) scan_mma_kernel(const MmaScanArgs
             if (elect_one()) {
                 constexpr uint32_t idesc = kI8 ? umma_idesc_i8(kTileM * kCG, kTileN) : umma_idesc_f16(kTileM * kCG, kTileN);
                 uint32_t stage = 0, phase = 0, it = 0;
+                if constexpr (kQS) {
+                    if (sched.n_mine > 0) {
+                        wait_or_trap(&bars->a_full, 0);
+                        wait_or_trap(&bars->peer_a_full, 0);
+                    }
+                }
                 for (int64_t i = 0; i < sched.n_mine; ++i, ++it) {
                     const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
                     wait_or_trap(&bars->tmem_empty[acc], acc_phase ^ 1);
@@ -235,9 +297,10 @@ __global__ void __launch_bounds__(kThreads, 1) scan_mma_kernel(const MmaScanArgs
                         wait_or_trap(&bars->full[stage], phase);
                         if constexpr (kCG == 2) wait_or_trap(&bars->peer_full[stage], phase);
                         tc_fence_after();
-                        const uint32_t sA = smem_u32(smem + stage * C::kStageBytes);
+                        const uint32_t sA = kQS ? smem_u32(smem + kb * kPieceBytes) : smem_u32(ring + stage * C::kStageBytes);
+                        const uint32_t sB = kQS ? smem_u32(ring + stage * kPieceBytes) : sA + C::kABytes;
                         const uint64_t descA = umma_desc_k128(sA);
-                        const uint64_t descB = umma_desc_k128(sA + C::kABytes);
+                        const uint64_t descB = umma_desc_k128(sB);
 #pragma unroll
                         for (int k = 0; k < 4; ++k) {
                             // advance 32 B along K inside the swizzle atom (16 f16 or 32 int8 elements): +2 in the
@@ -253,7 +316,7 @@ __global__ void __launch_bounds__(kThreads, 1) scan_mma_kernel(const MmaScanArgs
                             umma_commit_2cta(&bars->empty[stage], 0b11);
                             if (kb == kb_count - 1) umma_commit_2cta(&bars->tmem_full[acc], 0b11);
                         }
-                        if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+                        if (++stage == (uint32_t)n_stages) { stage = 0; phase ^= 1; }
                     }
                 }
             }
@@ -261,11 +324,17 @@ __global__ void __launch_bounds__(kThreads, 1) scan_mma_kernel(const MmaScanArgs
             // ---------------- peer forwarder: my half of the stage has landed ----------------
             if (elect_one()) {
                 uint32_t stage = 0, phase = 0;
+                if constexpr (kQS) {
+                    if (sched.n_mine > 0) {
+                        wait_or_trap(&bars->a_full, 0);
+                        mbar_arrive_cluster(&bars->peer_a_full, 0);
+                    }
+                }
                 for (int64_t i = 0; i < sched.n_mine; ++i) {
                     for (int kb = 0; kb < kb_count; ++kb) {
                         wait_or_trap(&bars->full[stage], phase);
                         mbar_arrive_cluster(&bars->peer_full[stage], 0);
-                        if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+                        if (++stage == (uint32_t)n_stages) { stage = 0; phase ^= 1; }
                     }
                 }
             }
@@ -521,6 +590,7 @@ cudaError_t scan_mma_configure() {
     set(scan_mma_kernel<1, true>, Cfg<1>::kSmemBytes);
     set(scan_mma_kernel<2, false>, Cfg<2>::kSmemBytes);
     set(scan_mma_kernel<2, true>, Cfg<2>::kSmemBytes);
+    set(scan_mma_kernel<2, true, true>, kSmemQS);
     return e;
 }
 
@@ -542,6 +612,17 @@ cudaError_t launch_pairs(const MmaScanArgs& a, int sm_count, cudaStream_t s) {
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
+    if constexpr (kI8) {
+        // query-stationary form: lanes of n_qgroups pairs; needs at least one full lane and a ring of >= 4 stages
+        const int n_qg = a.n_qtiles / 2;
+        const int64_t lanes = std::min<int64_t>((sm_count / 2) / n_qg, a.ct1 - a.ct0);
+        const int ring = (kSmemQS - 1024 - 512 - (a.d / kBlockK8) * kPieceBytes) / kPieceBytes;
+        if (a.tile_major == 2 && lanes >= 1 && ring >= 4) {
+            cfg.gridDim = dim3((unsigned)(2 * lanes * n_qg));
+            cfg.dynamicSmemBytes = kSmemQS;
+            return cudaLaunchKernelEx(&cfg, scan_mma_kernel<2, true, true>, a);
+        }
+    }
     return cudaLaunchKernelEx(&cfg, scan_mma_kernel<2, kI8>, a);
 }
 }  // namespace
@@ -559,6 +640,11 @@ cudaError_t launch_scan_mma_i8(const MmaScanArgs& a, int sm_count, int cta_group
 cudaError_t launch_scan_mma(const MmaScanArgs& a, int sm_count, int cta_group, cudaStream_t s) {
     const int64_t n_ctiles = a.ct1 - a.ct0;
     if (n_ctiles <= 0 || a.n_qtiles <= 0) return cudaSuccess;
+    if (a.tile_major == 2) {                 // the query-stationary order is an int8 form: the f16 scan keeps its default
+        MmaScanArgs b = a;
+        b.tile_major = 0;
+        return launch_scan_mma(b, sm_count, cta_group, s);
+    }
     if (cta_group == 2 && (a.n_qtiles % 2) == 0) return launch_pairs<false>(a, sm_count, s);
     const int64_t n_units = n_ctiles * a.n_qtiles;
     const int grid = (int)(n_units < sm_count ? n_units : sm_count);

@@ -17,7 +17,7 @@ from __future__ import annotations
 
 import numpy as np
 
-from .index import FlatIPIndex, merge_topk_device
+from .index import FlatIPIndex
 
 
 class StandardGpuResources:
@@ -102,17 +102,18 @@ class IndexFlatIP:
 class ShardedInProcessIndex:
     """faiss IndexShards equivalent inside one process (`index_cpu_to_gpu_multiple` with ``co.shard = True``,
     `/root/reference/src/test_HAConvDR_topiocqa.py:55-66`): rows of every ``add`` are split into contiguous ranges,
-    one per device.  ``search`` is the same protocol as one process per GPU (``haconvdr_b200.sharded``):
+    one per device.  ``search`` is ONE call into the library (``hac_shards_search``, `csrc/hac_shards.cu`), the same
+    protocol as one process per GPU (``haconvdr_b200.sharded``):
 
-    * one persistent host thread and one CUDA stream per shard (the C-ABI calls release the GIL, so the devices run
-      concurrently); queries go up once per device from a reused page-locked buffer;
-    * the shards publish their best scores to each other WHILE they scan (``hac_set_threshold_exchange``: peer-mapped
-      device pointers, ``hac_enable_peer_access``), so every shard rescores only its share of the global top-k;
+    * one persistent native host thread per shard (as faiss' own IndexShards keeps) copies the queries to its device
+      and runs the single-shard search - no Python, no GIL on the search path;
+    * the shards publish their best scores to each other WHILE they scan (``hac_set_threshold_exchange`` over
+      peer-mapped device pointers owned by the group), so every shard rescores only its share of the global top-k;
     * results stay in per-device buffers; ONE merge kernel on the first device reads all of them in place over NVLink
-      (``hac_merge_topk_peers_device``) - no gather copies, no host round trip before the final D2H."""
+      - no gather copies, no host round trip before the final D2H into the caller's arrays."""
 
     def __init__(self, d: int, devices):
-        import torch
+        import ctypes
         from concurrent.futures import ThreadPoolExecutor
         from . import _lib
         self.d = int(d)
@@ -122,22 +123,12 @@ class ShardedInProcessIndex:
         self.ntotal = 0
         self.is_trained = True
         self.threshold_exchange = True
-        self._torch = torch
-        self._pool = ThreadPoolExecutor(len(self.devices), thread_name_prefix="hac-shard")
-        self._streams = [torch.cuda.Stream(device=dev) for dev in self.devices]
-        self._events = [torch.cuda.Event() for _ in self.devices]
-        self._peer_ok = True
-        for a in sorted(set(self.devices)):              # kernels on a read (merge) and write (exchange) memory of b
-            for b in sorted(set(self.devices)):
-                if a != b and _lib.lib().hac_enable_peer_access(a, b) != 0:
-                    self._peer_ok = False                # no peer access on this system: gather copies, no exchange
-        self._epoch = 0
-        self._words = None        # per shard: int64 CUDA tensor of exchange words, capacity in queries
-        self._words_cap = 0
-        self._res = None          # per shard: (D [cap] float32, I [cap] int64) result buffers
-        self._res_cap = 0
-        self._q_pinned = None
-        self._out_pinned = None
+        self._lib = _lib.lib()
+        self._pool = ThreadPoolExecutor(len(self.devices), thread_name_prefix="hac-shard-add")
+        handles = (ctypes.c_void_p * len(self.shards))(*[sh._h.value for sh in self.shards])
+        self._grp = ctypes.c_void_p()
+        _lib.check(self._lib.hac_shards_create(handles, len(self.shards), ctypes.byref(self._grp)), "hac_shards_create")
+        self.peer_access = bool(self._lib.hac_shards_peer_access(self._grp))
         self.last_phase_ms = None
 
     def _set_ids(self, g):
@@ -168,97 +159,63 @@ class ShardedInProcessIndex:
             self._rows[g] = []
         self.ntotal = 0
 
-    def _ensure_buffers(self, nq, k):
-        torch = self._torch
-        from ._lib import HAC_EXCHANGE_WORDS_PER_QUERY as WPQ
-        if nq * k > self._res_cap:
-            cap = 1 << 16
-            while cap < nq * k:
-                cap *= 2
-            self._res = [(torch.empty(cap, dtype=torch.float32, device="cuda:%d" % dev),
-                          torch.empty(cap, dtype=torch.int64, device="cuda:%d" % dev)) for dev in self.devices]
-            self._res_cap = cap
-        if self.threshold_exchange and self._peer_ok and nq > self._words_cap:
-            cap = 4096
-            while cap < nq:
-                cap *= 2
-            self._words = [torch.zeros(cap * WPQ, dtype=torch.int64, device="cuda:%d" % dev) for dev in self.devices]
-            for dev in set(self.devices):
-                torch.cuda.synchronize(dev)
-            for g, sh in enumerate(self.shards):
-                sh.set_threshold_exchange(self._words[g].data_ptr(),
-                                          [w.data_ptr() for h, w in enumerate(self._words) if h != g], cap * WPQ)
-            self._words_cap = cap
-
-    def search(self, q, k):
-        import time
-        torch = self._torch
-        from .index import merge_topk_peers_device
-        t_start = time.perf_counter()
-        q = np.ascontiguousarray(q, dtype=np.float32)
-        assert q.ndim == 2 and q.shape[1] == self.d, "search: expected [nq, %d] float32" % self.d
-        nq, k, G = q.shape[0], int(k), len(self.shards)
-        if self._q_pinned is None or self._q_pinned.shape[0] < nq:
-            self._q_pinned = torch.empty((max(nq, 256), self.d), dtype=torch.float32).pin_memory()
-        qp = self._q_pinned[:nq]
-        qp.copy_(torch.from_numpy(q))
-        self._ensure_buffers(nq, k)
-        self._epoch = self._epoch % 0x0FFFFFFF + 1
-        armed = self.threshold_exchange and self._peer_ok and self._words is not None and G > 1
-        outs = [(D[:nq * k].view(nq, k), I[:nq * k].view(nq, k)) for D, I in self._res]
-
-        t_shard = [None] * G
-
-        def one(g):
-            t0 = time.perf_counter()
-            dev, sh = self.devices[g], self.shards[g]
-            with torch.cuda.device(dev), torch.cuda.stream(self._streams[g]):
-                qd = qp.to(torch.device("cuda", dev), non_blocking=True)
-                sh.set_option("exchange_epoch", self._epoch if armed else 0)
-                t1 = time.perf_counter()
-                try:
-                    sh.search(qd, k, out=outs[g])
-                finally:
-                    sh.set_option("exchange_epoch", 0)
-                self._events[g].record(self._streams[g])
-            t_shard[g] = (t0 - t_start, t1 - t_start, time.perf_counter() - t_start)
-        t_prep = time.perf_counter()
-        list(self._pool.map(one, range(G)))              # re-raises the first shard failure after all have finished
-        t_threads = time.perf_counter()
-        dev0 = self.devices[0]
-        with torch.cuda.device(dev0), torch.cuda.stream(self._streams[0]):
-            for ev in self._events[1:]:
-                self._streams[0].wait_event(ev)
-            if self._peer_ok:
-                Dm, Im = merge_topk_peers_device([o[0].data_ptr() for o in outs], [o[1].data_ptr() for o in outs],
-                                                 nq, k, k, torch.device("cuda", dev0))
-            else:
-                Dm, Im = merge_topk_device(torch.stack([o[0].to("cuda:%d" % dev0) for o in outs]),
-                                           torch.stack([o[1].to("cuda:%d" % dev0) for o in outs]), k)
-            if self._out_pinned is None or self._out_pinned[0].numel() < nq * k:
-                n = max(nq * k, 1 << 16)
-                self._out_pinned = (torch.empty(n, dtype=torch.float32).pin_memory(),
-                                    torch.empty(n, dtype=torch.int64).pin_memory())
-            Dh, Ih = self._out_pinned[0][:nq * k].view(nq, k), self._out_pinned[1][:nq * k].view(nq, k)
-            Dh.copy_(Dm, non_blocking=True)
-            Ih.copy_(Im, non_blocking=True)
-            self._streams[0].synchronize()
-        t_merge = time.perf_counter()
-        out = Dh.numpy().copy(), Ih.numpy().copy()
-        # host-side phases of the last search, ms since entry: query staging, per-shard (thread start, C call start, C call
-        # end), merge + D2H, result copies
-        self.last_phase_ms = {"prep": 1e3 * (t_prep - t_start), "shards": [[round(1e3 * v, 3) for v in t] for t in t_shard],
-                              "threads_done": 1e3 * (t_threads - t_start), "merge_d2h_done": 1e3 * (t_merge - t_start),
-                              "total": 1e3 * (time.perf_counter() - t_start)}
-        return out
+    def search(self, q, k, D=None, I=None):
+        """NumPy in -> NumPy out (``D=`` / ``I=``: preallocated result arrays, as ``faiss.Index.search`` accepts);
+        CUDA tensors on the first shard's device in -> CUDA tensors out."""
+        import ctypes
+        from ._lib import HAC_MAX_K, check
+        from .index import _is_torch_tensor
+        k = int(k)
+        if k <= 0 or k > HAC_MAX_K:
+            raise ValueError("search: k=%d outside [1, %d]" % (k, HAC_MAX_K))
+        check(self._lib.hac_shards_set_exchange(self._grp, 1 if self.threshold_exchange else 0), "hac_shards_set_exchange")
+        if _is_torch_tensor(q) and q.is_cuda:
+            import torch
+            assert q.dim() == 2 and q.shape[1] == self.d, "search: expected [nq, %d]" % self.d
+            if q.device.index != self.devices[0]:
+                raise ValueError("search: tensor lives on cuda:%s, first shard on cuda:%d" % (q.device.index, self.devices[0]))
+            q = q.contiguous().float()
+            D = torch.empty((q.shape[0], k), dtype=torch.float32, device=q.device)
+            I = torch.empty((q.shape[0], k), dtype=torch.int64, device=q.device)
+            stream = torch.cuda.current_stream(q.device).cuda_stream
+            check(self._lib.hac_shards_search_device(self._grp, q.shape[0], q.data_ptr(), k, D.data_ptr(), I.data_ptr(),
+                                                     stream), "hac_shards_search_device")
+        else:
+            if _is_torch_tensor(q):
+                q = q.detach().cpu().numpy()
+            q = np.ascontiguousarray(q, dtype=np.float32)
+            assert q.ndim == 2 and q.shape[1] == self.d, "search: expected [nq, %d] float32" % self.d
+            if D is None:
+                D = np.empty((q.shape[0], k), dtype=np.float32)
+            if I is None:
+                I = np.empty((q.shape[0], k), dtype=np.int64)
+            assert D.shape == (q.shape[0], k) and D.dtype == np.float32 and D.flags.c_contiguous
+            assert I.shape == (q.shape[0], k) and I.dtype == np.int64 and I.flags.c_contiguous
+            check(self._lib.hac_shards_search(self._grp, q.shape[0], q.ctypes.data, k, D.ctypes.data, I.ctypes.data),
+                  "hac_shards_search")
+        ph = (ctypes.c_float * 4)()
+        self._lib.hac_shards_last_phases(self._grp, ph, 4)
+        # host-side milestones of the search, ms since the call began
+        self.last_phase_ms = {"fastest_shard_done": ph[3], "slowest_shard_done": ph[0], "merge_enqueued": ph[1],
+                              "results_on_host": ph[2]}
+        return D, I
 
     def stats(self):
         return [sh.stats() for sh in self.shards]
 
     def close(self):
-        self._pool.shutdown(wait=True)
+        if getattr(self, "_grp", None) is not None and self._grp.value:
+            self._lib.hac_shards_destroy(self._grp)      # before the shards it borrows
+            self._grp = None
+            self._pool.shutdown(wait=True)
         for sh in self.shards:
             sh.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 def index_cpu_to_gpu_multiple(vres, vdev, cpu_index, co=None):

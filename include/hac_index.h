@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define HAC_ABI_VERSION 2
+#define HAC_ABI_VERSION 3
 
 #define HAC_OK 0
 #define HAC_E_INVALID (-1)   /* bad argument (dimension mismatch, k out of range, null pointer) */
@@ -42,7 +42,7 @@ extern "C" {
 #define HAC_MAX_K 1024       /* faiss-gpu caps k at 2048; BASELINE's sweep tops out at 1000 */
 
 /* scan paths (hac_search*_ex `path` argument / hac_stats.path) */
-#define HAC_PATH_AUTO 0      /* int8 screen when its image exists and k <= 128, else the f16 screen */
+#define HAC_PATH_AUTO 0      /* int8 screen when its image exists (d % 128 == 0), else the f16 screen */
 #define HAC_PATH_GEMV 1      /* exact fp32 HBM-streaming scan, small query batches */
 #define HAC_PATH_MMA 2       /* tcgen05 f16 screen + exact fp32 rescore of the shortlist */
 #define HAC_PATH_I8 3        /* tcgen05 int8 screen (s32 accumulate) + exact fp32 rescore of every emitted row */
@@ -162,6 +162,35 @@ int hac_set_threshold_exchange(hac_index* idx, uint64_t* mine_dev, const uint64_
  * device pointers of the other GPUs.  With one process per GPU the same is achieved with symmetric memory. */
 int hac_enable_peer_access(int device, int peer);
 
+/* ---- shard group: the whole IndexShards search in one call --------------------------------------------------------
+ * hac_shards_create  <- faiss.index_cpu_to_gpu_multiple(vres, vdev, cpu_index, co) with co.shard = True
+ *                       (src/test_HAConvDR_topiocqa.py:55-66): groups n (<= 16) shard handles of the same dimension,
+ *                       one per device (several on one device are allowed), enables peer access between their devices
+ *                       and starts one host thread per shard - faiss' IndexShards keeps a C++ thread per sub-index too.
+ *                       The handles are borrowed: add / reset / id bases stay per shard (hac_add, hac_set_id_base),
+ *                       the group must be destroyed before them.
+ * hac_shards_search  <- D, I = index.search(query_embeddings, topN) on that sharded index (:102): every shard thread
+ *                       copies the host queries to its device and runs the single-shard search with the cross-shard
+ *                       threshold exchange armed (peer-mapped buffers owned by the group), then ONE merge kernel on the
+ *                       first shard's device reads all lists in place over NVLink and the merged [nq,k] lists go to the
+ *                       host.  Results are those of one index holding all rows (ids as the shards translate them).
+ * hac_shards_search_device  same with q / D / I on the FIRST shard's device; `stream` orders the merge (the queries
+ *                       must be complete on `stream`, which is synchronised first).
+ * hac_shards_set_exchange   0 = shards search independently (what faiss does), 1 (default) = threshold exchange.
+ * hac_shards_peer_access    1 when every device of the group can address every other one (else: gather copies, no
+ *                       exchange).
+ * hac_shards_last_phases    host-side milestones of the last search in ms since the call began: [0] slowest shard
+ *                       done, [1] merge enqueued, [2] results on the host, [3] fastest shard done. */
+typedef struct hac_shards hac_shards;
+int hac_shards_create(hac_index* const* shards, int n, hac_shards** out);
+int hac_shards_destroy(hac_shards* grp);
+int hac_shards_search(hac_shards* grp, int64_t nq, const float* q_host, int k, float* D_host, int64_t* I_host);
+int hac_shards_search_device(hac_shards* grp, int64_t nq, const float* q_dev, int k, float* D_dev, int64_t* I_dev,
+                             void* stream);
+int hac_shards_set_exchange(hac_shards* grp, int on);
+int hac_shards_peer_access(const hac_shards* grp);
+int hac_shards_last_phases(const hac_shards* grp, float* out_ms, int n);
+
 /* offset -> pid gather on the device (src/test_HAConvDR_topiocqa.py:250): out[i] =
  * table[ids[i]] for ids >= 0, -1 otherwise.  table/ids/out are device pointers. */
 int hac_gather_ids_device(int device, const int64_t* table_dev, int64_t table_n, const int64_t* ids_dev,
@@ -216,8 +245,9 @@ int hac_pinned_free(void* host);
  *                    reset, and the scan adds q.c back: embeddings with a large shared component (ANCE) get a
  *                    margin made of the centred norms; results are unaffected (exact rescore); empty index only
  *   "exchange_epoch"  arms the cross-shard threshold exchange for the next searches (see hac_set_threshold_exchange)
- *   "i8_auto_max_k" / "i8_auto_max_queries"  with the int8 image present, HAC_PATH_AUTO takes the int8 screen for
- *                    k <= 128 and any batch size by default (its shortlist grows with k); 0 = never
+ *   "i8_auto_max_k" / "i8_auto_max_queries"  with the int8 image present, HAC_PATH_AUTO takes the int8 screen up to
+ *                    this k / batch size (default: every k <= HAC_MAX_K, every batch); larger ones run the f16 screen,
+ *                    0 = never
  *   "f16_drop_bits_corpus" / "f16_drop_bits_queries"  low mantissa bits of the f16 image forced to zero
  *                    (0..8, default 3 / 0): sparser operands draw less tensor-core power, the screen margin
  *                    is computed from the actual rounding error so exactness is unaffected; corpus: empty index only
@@ -231,8 +261,8 @@ int hac_pinned_free(void* host);
  *   "i8_warm_rows"   int8 screen warm start: the first rows of the shard are searched with the f16 screen (an f16 image
  *                    of just those rows, ~0.6 GB at the default size), whose margin is ~20x tighter, so the int8 scan
  *                    of the rest starts from an exact threshold instead of emitting through many loosely filtered
- *                    early chunks; -1 (default) = automatic (tensor-bound batches on shards >= 8x the slab), 0 = off,
- *                    > 0 = that many rows
+ *                    early chunks; -1 (default) = automatic (tensor-bound batches; ~800 k rows for k <= 128 on shards
+ *                    >= 8x the slab, 6144 * k rows up to a quarter of the shard for larger k), 0 = off, > 0 = that many rows
  */
 int hac_set_option(hac_index* idx, const char* name, int64_t value);
 

@@ -24,6 +24,21 @@ def test_library_exports_every_declared_symbol():
     assert isinstance(_lib.last_error(), str)
 
 
+def test_shard_group_rejects_bad_arguments_without_a_gpu():
+    """hac_shards_* argument checks come before any CUDA call (error codes and messages as every other entry point)."""
+    import ctypes
+    L = _lib.lib()
+    grp = ctypes.c_void_p()
+    assert L.hac_shards_create(None, 0, ctypes.byref(grp)) == -1 and "shards" in _lib.last_error()
+    handles = (ctypes.c_void_p * 2)(None, None)
+    assert L.hac_shards_create(handles, 2, ctypes.byref(grp)) == -1 and not grp.value
+    assert L.hac_shards_create(handles, 2, None) == -1
+    assert L.hac_shards_search(None, 1, None, 10, None, None) == -1
+    assert L.hac_shards_set_exchange(None, 1) == -1
+    assert L.hac_shards_peer_access(None) == 0
+    assert L.hac_shards_destroy(None) == 0
+
+
 def test_library_is_sm100a_with_tcgen05_and_bulk_copy():
     import subprocess
     sass = subprocess.run(["cuobjdump", "-sass", _lib.LIB_PATH], capture_output=True, text=True).stdout

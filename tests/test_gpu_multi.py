@@ -138,7 +138,8 @@ def _two_shards(x, split):
 @pytest.mark.parametrize("nq,n,k,concurrent,warm", [(150, 60000, 100, True, 0), (150, 60000, 100, False, 0),
                                                     (3, 40000, 10, True, 0), (300, 90001, 1, True, 0),
                                                     (40, 30000, 128, False, 0), (300, 90001, 100, True, 8192),
-                                                    (150, 60000, 100, False, 4096)])
+                                                    (150, 60000, 100, False, 4096), (130, 60000, 1000, True, 0),
+                                                    (40, 30000, 300, False, 4096), (140, 70000, 1000, True, 16384)])
 def test_threshold_exchange_and_peer_merge_two_shards_one_device(nq, n, k, concurrent, warm):
     """hac_set_threshold_exchange + hac_merge_topk_peers_device with same-device "peer" pointers: two shards search
     (concurrently from two host threads on two streams, or one after the other), publish their ceil(k/2)-th best
@@ -234,5 +235,65 @@ def test_in_process_index_shards_on_one_device():
         assert_parity(D64, I64, D, I, rtol=1e-5, ref_scores_of=lambda qi, ids: x64[ids] @ q[qi].astype(np.float64))
     D2, I2 = index.search(q, 1)
     assert np.array_equal(I2, I) and np.array_equal(D2, D)
+    ph = index.last_phase_ms
+    assert 0.0 < ph["fastest_shard_done"] <= ph["slowest_shard_done"] <= ph["results_on_host"]
+    # faiss-style preallocated outputs, the CUDA-tensor form, and the independent-shards mode (no exchange): all bitwise equal
+    import torch
+    D100, I100 = index.search(q, 100)
+    Dp, Ip = np.empty((90, 100), np.float32), np.empty((90, 100), np.int64)
+    assert index.search(q, 100, D=Dp, I=Ip)[0] is Dp
+    assert np.array_equal(Ip, I100) and np.array_equal(Dp, D100)
+    Dt, It = index.search(torch.from_numpy(q).cuda(), 100)
+    assert Dt.is_cuda and np.array_equal(It.cpu().numpy(), I100) and np.array_equal(Dt.cpu().numpy(), D100)
+    index.threshold_exchange = False
+    Dn, In = index.search(q, 100)
+    assert np.array_equal(In, I100) and np.array_equal(Dn, D100)
+    index.threshold_exchange = True
+    for st in index.stats():
+        assert st["retries"] == 0 and st["screen_err_max"] <= st["margin_max"], st
+    # a batch larger than the exchange buffers' first size (4096 queries) regrows them; k outside the range is refused
+    qb = rng.standard_normal((4500, 768), dtype=np.float32)
+    Db, Ib = index.search(qb, 10)
+    D64b, I64b = brute_force_fp64(qb[:64], x, 10)
+    assert_parity(D64b, I64b, Db[:64], Ib[:64], rtol=1e-5, ref_scores_of=lambda qi, ids: x64[ids] @ qb[qi].astype(np.float64))
+    with pytest.raises(ValueError):
+        index.search(q, 2000)
     index.reset()
     assert index.ntotal == 0
+    D0, I0 = index.search(q[:3], 5)                      # empty shards: faiss' unfilled slots
+    assert (I0 == -1).all() and (D0 == np.float32(-3.4028235e38)).all()
+    index.add(x[:5000])
+    D5, I5 = index.search(q, 10)
+    D64s, I64s = brute_force_fp64(q, x[:5000], 10)
+    assert_parity(D64s, I64s, D5, I5, rtol=1e-5, ref_scores_of=lambda qi, ids: x64[ids] @ q[qi].astype(np.float64))
+    index.close()
+
+
+def test_shard_group_through_the_raw_c_abi():
+    """hac_shards_* called as a C host would: borrowed handles, mismatching dimensions refused, per-shard id bases and
+    options respected, argument errors reported through hac_last_error()."""
+    import ctypes
+    import haconvdr_b200 as hb
+    from haconvdr_b200 import _lib
+    L = _lib.lib()
+    a, b = hb.FlatIPIndex(768, 0), hb.FlatIPIndex(256, 0)
+    handles = (ctypes.c_void_p * 2)(a._h.value, b._h.value)
+    grp = ctypes.c_void_p()
+    assert L.hac_shards_create(handles, 2, ctypes.byref(grp)) == -1 and "dimensions differ" in _lib.last_error()
+    c = hb.FlatIPIndex(768, 0)
+    handles = (ctypes.c_void_p * 2)(a._h.value, c._h.value)
+    assert L.hac_shards_create(handles, 2, ctypes.byref(grp)) == 0
+    x = np.random.default_rng(2).standard_normal((3000, 768), dtype=np.float32)
+    a.add(x[:1500])
+    c.add(x[1500:])
+    c.set_id_base(1500)
+    c.set_option("default_path", hb.HAC_PATH_GEMV)       # one shard on the fp32 GEMV path (batches of 4), the other on int8
+    q = x[:9].copy()
+    D, I = np.empty((9, 5), np.float32), np.empty((9, 5), np.int64)
+    assert L.hac_shards_search(grp, 9, q.ctypes.data, 5, D.ctypes.data, I.ctypes.data) == 0, _lib.last_error()
+    assert np.array_equal(I[:, 0], np.arange(9))         # every row is its own best match
+    assert L.hac_shards_search(grp, 9, q.ctypes.data, 0, D.ctypes.data, I.ctypes.data) == -1
+    assert "k outside" in _lib.last_error()
+    assert L.hac_shards_destroy(grp) == 0
+    for h in (a, b, c):
+        h.close()

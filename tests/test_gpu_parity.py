@@ -535,8 +535,8 @@ def test_careful_mode_is_sticky_until_reset():
 
 @pytest.mark.parametrize("nq,k", [(1, 100), (4, 100), (32, 10), (129, 128), (300, 100), (64, 129), (40, 1000)])
 def test_auto_path_policy(nq, k):
-    """The int8 image is built by default; AUTO takes its screen for k <= 128 at every batch size and the f16 screen
-    for larger k (the int8 shortlist grows with k).  Same results either way."""
+    """The int8 image is built by default; AUTO takes its screen at every batch size and every k (for k > 128 behind a
+    larger f16 warm slab), the f16 screen only above "i8_auto_max_k".  Same results either way."""
     hb = _engine()
     rng = np.random.default_rng(80 + nq)
     x = rng.standard_normal((90000, 768), dtype=np.float32)
@@ -545,10 +545,13 @@ def test_auto_path_policy(nq, k):
     idx.add(x)
     D, I = idx.search(q, k)
     st = idx.stats()
-    assert st["path"] == (hb.HAC_PATH_I8 if k <= 128 else hb.HAC_PATH_MMA) and st["retries"] == 0, st
+    assert st["path"] == hb.HAC_PATH_I8 and st["retries"] == 0, st
     assert st["bytes_i8"] >= 90000 * 768                       # the int8 image is built on add ...
-    if k <= 128:
-        assert st["bytes_shadow"] == 0                         # ... the f16 image only when a search needs it
+    assert st["bytes_shadow"] == 0                             # ... the f16 image only when a search needs it
+    idx.set_option("i8_auto_max_k", 128)                       # the round-1 policy: larger k on the f16 screen
+    Dp, Ip = idx.search(q, k)
+    assert idx.stats()["path"] == (hb.HAC_PATH_I8 if k <= 128 else hb.HAC_PATH_MMA)
+    assert np.array_equal(Ip, I) and np.array_equal(Dp, D)
     Dm, Im = idx.search(q, k, path=hb.HAC_PATH_MMA)
     assert idx.stats()["bytes_shadow"] >= 90000 * 768 * 2
     assert np.array_equal(I, Im) and np.array_equal(D, Dm)
@@ -643,7 +646,7 @@ def test_int8_screen_on_anisotropic_rows_needs_the_centre():
 @pytest.mark.parametrize("nq,n,k", [(130, 50000, 100), (300, 120001, 100), (256, 4096, 1), (64, 70000, 1000),
                                     (700, 90000, 10)])
 def test_int8_screen_cta_pairs_and_unit_schedules(nq, n, k):
-    """cta_group::2 int8 scan (CTA pairs share each MMA) and both unit schedules: bitwise the same results."""
+    """cta_group::2 int8 scan (CTA pairs share each MMA) and all unit schedules: bitwise the same results."""
     hb = _engine()
     rng = np.random.default_rng(nq + n + k)
     x = rng.standard_normal((n, 768), dtype=np.float32)
@@ -653,7 +656,7 @@ def test_int8_screen_cta_pairs_and_unit_schedules(nq, n, k):
     idx.add(x)
     Dm, Im = idx.search(q, k, path=hb.HAC_PATH_MMA)
     for cg in (1, 2):
-        for tile_major in (0, 1):
+        for tile_major in (0, 1, 2):                                 # 2 = query-stationary pairs (cg = 2), else as 1
             idx.set_option("i8_cta_group", cg)
             idx.set_option("scan_tile_major", tile_major)
             D8, I8 = idx.search(q, k, path=hb.HAC_PATH_I8)
@@ -784,8 +787,8 @@ def test_f16_image_is_built_lazily_and_kept_up_to_date():
     Dm, Im = idx.search(q, 100, path=hb.HAC_PATH_MMA)
     assert np.array_equal(Im, I8) and np.array_equal(Dm, D8)
     _check(q, x, 100, Dm, Im, also_fp32_oracle=False)
-    Dk, Ik = idx.search(q[:40], 300)                           # AUTO with k > 128: the f16 screen
-    assert idx.stats()["path"] == hb.HAC_PATH_MMA
+    Dk, Ik = idx.search(q[:40], 300)                           # AUTO with k > 128: still the int8 screen
+    assert idx.stats()["path"] == hb.HAC_PATH_I8
     _check(q[:40], x, 300, Dk, Ik, also_fp32_oracle=False)
     idx.reset()
     idx.add(x[:5000])
@@ -797,6 +800,27 @@ def test_f16_image_is_built_lazily_and_kept_up_to_date():
     assert eager.stats()["bytes_shadow"] >= 9000 * 768 * 2
     De, Ie = eager.search(q, 10, path=hb.HAC_PATH_MMA)
     _check(q, x[:9000], 10, De, Ie, also_fp32_oracle=False)
+
+
+@pytest.mark.parametrize("nq,n,k", [(130, 140000, 300), (200, 150000, 1000)])
+def test_large_k_runs_the_int8_screen_behind_a_warm_slab_sized_by_k(nq, n, k):
+    """k > 128: AUTO = int8 screen, the automatic f16 warm slab is min(6144 k, rows / 4); bitwise the f16 screen's result."""
+    hb = _engine()
+    rng = np.random.default_rng(n + k)
+    x = rng.standard_normal((n, 768), dtype=np.float32)
+    q = rng.standard_normal((nq, 768), dtype=np.float32)
+    idx = hb.FlatIPIndex(768)
+    idx.add(x)
+    D, I = idx.search(q, k)
+    st = idx.stats()
+    assert st["path"] == hb.HAC_PATH_I8 and st["retries"] == 0 and st["bytes_shadow"] == 0, st
+    assert st["warm_rows"] == (n // 4) // 256 * 256 and st["screen_err_max"] <= st["margin_max"], st
+    Dm, Im = idx.search(q, k, path=hb.HAC_PATH_MMA)
+    assert np.array_equal(I, Im) and np.array_equal(D, Dm)
+    idx.set_option("i8_warm_rows", 0)
+    D0, I0 = idx.search(q, k)
+    assert idx.stats()["warm_rows"] == 0 and np.array_equal(I0, I) and np.array_equal(D0, D)
+    _check(q[:48], x, k, D[:48], I[:48], also_fp32_oracle=False)
 
 
 def test_default_path_gemv_batches_by_four():
