@@ -211,25 +211,55 @@ def run_reference(args):
 
 # ------------------------------------------------------------------------------------------------
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    """SM clock / power / throttle reasons sampled DURING the timed region: NVML in-process every 10 ms
+    (nvidia_ml_py), falling back to one `nvidia-smi` query per 100 ms when NVML cannot be loaded."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+    BITS = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
 
     def __init__(self, gpu_index):
         self.gpu, self.samples, self._stop, self._t = gpu_index, [], threading.Event(), None
+        self.source, self._nvml, self._h, self._max = "nvidia-smi", None, None, None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self._nvml = pynvml
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(int(gpu_index))
+            self._max = float(pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM))
+            self.source = "nvml"
+        except Exception:
+            self._nvml = None
+
+    def _sample_nvml(self):
+        n = self._nvml
+        sm = float(n.nvmlDeviceGetClockInfo(self._h, n.NVML_CLOCK_SM))
+        mask = int(n.nvmlDeviceGetCurrentClocksThrottleReasons(self._h))
+        try:
+            watts = n.nvmlDeviceGetPowerUsage(self._h) / 1000.0
+        except Exception:
+            watts = 0.0
+        return [sm, self._max, watts] + [bool(mask & self.BITS[k]) for k in self.NAMES]
+
+    def _sample_smi(self):
+        out = subprocess.run(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits"],
+                             capture_output=True, text=True, timeout=5).stdout.strip()
+        v = [x.strip() for x in out.split(",")]
+        if len(v) < 7 or not v[0].replace(".", "").isdigit():
+            return None
+        watts = float(v[2]) if v[2].replace(".", "").isdigit() else 0.0
+        return [float(v[0]), float(v[1]), watts] + [x == "Active" for x in v[3:7]]
 
     def _run(self):
         while not self._stop.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
-                                      "--format=csv,noheader,nounits"], capture_output=True, text=True,
-                                     timeout=5).stdout.strip()
-                if out:
-                    self.samples.append([v.strip() for v in out.split(",")])
+                smp = self._sample_nvml() if self._nvml is not None else self._sample_smi()
+                if smp:
+                    self.samples.append(smp)
             except Exception:
                 pass
-            self._stop.wait(0.1)
+            self._stop.wait(0.01 if self._nvml is not None else 0.1)
 
     def start(self):
         self._t = threading.Thread(target=self._run, daemon=True)
@@ -239,12 +269,13 @@ class ClockSampler:
         self._stop.set()
         if self._t:
             self._t.join(timeout=6)
-        sm = sorted(float(s[0]) for s in self.samples if s and s[0].replace(".", "").isdigit())
-        mx = [float(s[1]) for s in self.samples if len(s) > 1 and s[1].replace(".", "").isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({n for s in self.samples if len(s) >= 7 for n, v in zip(names, s[3:7]) if v == "Active"})
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(self.samples)}
+        sm = sorted(s[0] for s in self.samples)
+        mx = [s[1] for s in self.samples if s[1]]
+        reasons = sorted({n for s in self.samples for n, v in zip(self.NAMES, s[3:7]) if v})
+        watts = [s[2] for s in self.samples if s[2]]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_mhz_min": sm[0] if sm else None,
+                "sm_max_mhz": max(mx) if mx else None, "power_w_max": max(watts) if watts else None,
+                "reasons": reasons, "samples": len(self.samples), "source": self.source}
 
 
 def measured_peaks():
