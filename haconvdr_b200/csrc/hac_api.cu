@@ -161,9 +161,14 @@ struct hac_index {
     // HAC_PATH_MMA): with the int8 image present it is built on first use instead of on add (25.7M rows: 138 -> 99 GB)
     int lazy_f16 = -1;                      // -1 = lazy exactly when the int8 image is built; 0 / 1 = forced
     // HAC_PATH_AUTO takes the int8 screen up to this k.  Its shortlist grows with k * e^(m8*z/sigma): with a warm slab
-    // sized by k it still wins at k = 1000 (70.7 vs 75.5 ms at 25.7M x 2514, 49.1 vs 72.4 ms at k = 250) and the 39 GB
-    // f16 image of the corpus is never built
+    // sized by k it still wins at k = 1000 on a large shard (70.7 vs 75.5 ms at 25.7M x 2514, 49.1 vs 72.4 ms at k = 250)
+    // and the 39 GB f16 image of the corpus is never built ...
     int i8_auto_max_k = HAC_MAX_K;
+    // ... for k > 128 only on shards of at least this many rows per k.  The int8 scan saves (rows - slab) x one int8
+    // row of tensor time, the price is ~k * A * ln(rows / slab) more rescored rows per query: break-even ~10^4 rows per
+    // k (k = 1000: 25.7M rows 70.7 vs 75.5 ms, 12.9M rows 37.7 vs ~37.6 ms, 3.2M rows 18.0 vs ~10.5 ms).  Batches below
+    // 128 queries run no warm slab and stream at the HBM rate: they need 256 rows per k and query.
+    int64_t i8_large_k_rows_per_k = 12288;
     int default_path = HAC_PATH_MMA;        // what HAC_PATH_AUTO resolves to
     int i8_auto_max_queries = kMaxQueryBatch;          // HAC_PATH_AUTO takes the int8 screen up to this batch size when the image exists
 };
@@ -839,8 +844,14 @@ int search_batch(hac_index* idx, int nq, const float* q_dev, int k, float* D_dev
         // the int8 rate (38.5 vs 74.4 ms of scan at 25.7M x 2514), small ones stream half the bytes (Q=1: 2.8 vs 5.4
         // ms); rescoring its ~10^4 emitted rows per query (k = 100) runs at the HBM rate, and for larger k the f16 warm
         // slab grows with k.  Corpora that overflowed it go to the f16 screen.
+        bool big_enough = true;
+        if (k > 128) {
+            const int64_t per_k = nq >= 128 ? idx->i8_large_k_rows_per_k
+                                            : std::max<int64_t>(idx->i8_large_k_rows_per_k, 256 * (int64_t)nq);
+            big_enough = idx->i8_large_k_rows_per_k == 0 || idx->ntotal >= per_k * k;
+        }
         const bool take_i8 = have_i8 && idx->default_path == HAC_PATH_MMA && !idx->i8_overflowed &&
-                             k <= idx->i8_auto_max_k && nq <= idx->i8_auto_max_queries;
+                             k <= idx->i8_auto_max_k && nq <= idx->i8_auto_max_queries && big_enough;
         path = take_i8 ? HAC_PATH_I8 : idx->default_path;
     }
     if (path == HAC_PATH_I8 && !have_i8) path = HAC_PATH_MMA;      // d % 128 != 0 or int8 image disabled
@@ -1699,6 +1710,11 @@ int hac_set_option(hac_index* idx, const char* name, int64_t value) {
     if (strcmp(name, "i8_chunk_growth_x100") == 0) {
         if (value != 0 && (value < 10 || value > 1600)) return fail(HAC_E_INVALID, "i8_chunk_growth_x100 must be 0 or in [10, 1600]");
         idx->i8_chunk_growth = (double)value / 100.0;
+        return HAC_OK;
+    }
+    if (strcmp(name, "i8_large_k_rows_per_k") == 0) {
+        if (value < 0) return fail(HAC_E_INVALID, "i8_large_k_rows_per_k must be >= 0");
+        idx->i8_large_k_rows_per_k = value;
         return HAC_OK;
     }
     if (strcmp(name, "i8_auto_max_k") == 0) {

@@ -42,7 +42,7 @@ extern "C" {
 #define HAC_MAX_K 1024       /* faiss-gpu caps k at 2048; BASELINE's sweep tops out at 1000 */
 
 /* scan paths (hac_search*_ex `path` argument / hac_stats.path) */
-#define HAC_PATH_AUTO 0      /* int8 screen when its image exists (d % 128 == 0), else the f16 screen */
+#define HAC_PATH_AUTO 0      /* int8 screen when its image exists (d % 128 == 0; large k: on large shards), else the f16 screen */
 #define HAC_PATH_GEMV 1      /* exact fp32 HBM-streaming scan, small query batches */
 #define HAC_PATH_MMA 2       /* tcgen05 f16 screen + exact fp32 rescore of the shortlist */
 #define HAC_PATH_I8 3        /* tcgen05 int8 screen (s32 accumulate) + exact fp32 rescore of every emitted row */
@@ -248,6 +248,9 @@ int hac_pinned_free(void* host);
  *   "i8_auto_max_k" / "i8_auto_max_queries"  with the int8 image present, HAC_PATH_AUTO takes the int8 screen up to
  *                    this k / batch size (default: every k <= HAC_MAX_K, every batch); larger ones run the f16 screen,
  *                    0 = never
+ *   "i8_large_k_rows_per_k"  ... and for k > 128 only on shards holding at least this many rows per k (default 12288;
+ *                    batches below 128 queries: at least 256 rows per k and query); smaller shards run the f16 screen,
+ *                    whose rescoring does not grow with k; 0 = no such limit
  *   "f16_drop_bits_corpus" / "f16_drop_bits_queries"  low mantissa bits of the f16 image forced to zero
  *                    (0..8, default 3 / 0): sparser operands draw less tensor-core power, the screen margin
  *                    is computed from the actual rounding error so exactness is unaffected; corpus: empty index only

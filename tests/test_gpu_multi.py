@@ -162,6 +162,7 @@ def test_threshold_exchange_and_peer_merge_two_shards_one_device(nq, n, k, concu
     for r, sh in enumerate(shards):
         sh.set_threshold_exchange(words[r].data_ptr(), [words[1 - r].data_ptr()], cap)
         sh.set_option("i8_warm_rows", warm)      # > 0: the shard's first rows go through the f16 screen first
+        sh.set_option("i8_large_k_rows_per_k", 0)   # k > 128 on the int8 screen too (shards this small default to f16)
     qd = torch.from_numpy(q).to(dev)
     D64, I64 = brute_force_fp64(q, x, k)
     x64 = x.astype(np.float64)

@@ -533,25 +533,29 @@ def test_careful_mode_is_sticky_until_reset():
     assert idx.stats()["retries"] == 0
 
 
-@pytest.mark.parametrize("nq,k", [(1, 100), (4, 100), (32, 10), (129, 128), (300, 100), (64, 129), (40, 1000)])
+@pytest.mark.parametrize("nq,k", [(1, 100), (4, 100), (32, 10), (129, 128), (300, 100), (64, 129), (40, 1000), (200, 300)])
 def test_auto_path_policy(nq, k):
-    """The int8 image is built by default; AUTO takes its screen at every batch size and every k (for k > 128 behind a
-    larger f16 warm slab), the f16 screen only above "i8_auto_max_k".  Same results either way."""
+    """The int8 image is built by default; AUTO takes its screen at every batch size for k <= 128, and for larger k on
+    shards of >= 12288 rows per k ("i8_large_k_rows_per_k"; smaller ones run the f16 screen).  Same results either way."""
     hb = _engine()
     rng = np.random.default_rng(80 + nq)
     x = rng.standard_normal((90000, 768), dtype=np.float32)
     q = rng.standard_normal((nq, 768), dtype=np.float32)
     idx = hb.FlatIPIndex(768)
     idx.add(x)
+    idx.set_option("i8_large_k_rows_per_k", 0)                 # no shard-size limit: the int8 screen at every k
     D, I = idx.search(q, k)
     st = idx.stats()
     assert st["path"] == hb.HAC_PATH_I8 and st["retries"] == 0, st
     assert st["bytes_i8"] >= 90000 * 768                       # the int8 image is built on add ...
     assert st["bytes_shadow"] == 0                             # ... the f16 image only when a search needs it
-    idx.set_option("i8_auto_max_k", 128)                       # the round-1 policy: larger k on the f16 screen
+    idx.set_option("i8_large_k_rows_per_k", 12288)             # the default: 90 000 rows are too few for k > 128
     Dp, Ip = idx.search(q, k)
     assert idx.stats()["path"] == (hb.HAC_PATH_I8 if k <= 128 else hb.HAC_PATH_MMA)
     assert np.array_equal(Ip, I) and np.array_equal(Dp, D)
+    idx.set_option("i8_large_k_rows_per_k", 90000 // k)        # exactly enough rows per k
+    idx.search(q, k)
+    assert idx.stats()["path"] == (hb.HAC_PATH_I8 if k <= 128 or nq >= 128 or 256 * nq <= 90000 // k else hb.HAC_PATH_MMA)
     Dm, Im = idx.search(q, k, path=hb.HAC_PATH_MMA)
     assert idx.stats()["bytes_shadow"] >= 90000 * 768 * 2
     assert np.array_equal(I, Im) and np.array_equal(D, Dm)
@@ -787,8 +791,8 @@ def test_f16_image_is_built_lazily_and_kept_up_to_date():
     Dm, Im = idx.search(q, 100, path=hb.HAC_PATH_MMA)
     assert np.array_equal(Im, I8) and np.array_equal(Dm, D8)
     _check(q, x, 100, Dm, Im, also_fp32_oracle=False)
-    Dk, Ik = idx.search(q[:40], 300)                           # AUTO with k > 128: still the int8 screen
-    assert idx.stats()["path"] == hb.HAC_PATH_I8
+    Dk, Ik = idx.search(q[:40], 300)                           # AUTO with k > 128 on a small shard: the f16 screen
+    assert idx.stats()["path"] == hb.HAC_PATH_MMA
     _check(q[:40], x, 300, Dk, Ik, also_fp32_oracle=False)
     idx.reset()
     idx.add(x[:5000])
@@ -811,6 +815,7 @@ def test_large_k_runs_the_int8_screen_behind_a_warm_slab_sized_by_k(nq, n, k):
     q = rng.standard_normal((nq, 768), dtype=np.float32)
     idx = hb.FlatIPIndex(768)
     idx.add(x)
+    idx.set_option("i8_large_k_rows_per_k", 0)                 # (the default keeps shards this small on the f16 screen)
     D, I = idx.search(q, k)
     st = idx.stats()
     assert st["path"] == hb.HAC_PATH_I8 and st["retries"] == 0 and st["bytes_shadow"] == 0, st
