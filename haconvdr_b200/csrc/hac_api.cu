@@ -166,7 +166,7 @@ struct hac_index {
     int i8_auto_max_k = HAC_MAX_K;
     // ... for k > 128 only on shards of at least this many rows per k.  The int8 scan saves (rows - slab) x one int8
     // row of tensor time, the price is ~k * A * ln(rows / slab) more rescored rows per query: break-even ~10^4 rows per
-    // k (k = 1000: 25.7M rows 70.7 vs 75.5 ms, 12.9M rows 37.7 vs ~37.6 ms, 3.2M rows 18.0 vs ~10.5 ms).  Batches below
+    // k (k = 1000: 25.7M rows 70.7 vs 75.5 ms, 12.9M rows 37.7 vs ~37.6 ms, 3.2M rows 18.0 vs 17.1 ms).  Batches below
     // 128 queries run no warm slab and stream at the HBM rate: they need 256 rows per k and query.
     int64_t i8_large_k_rows_per_k = 12288;
     int default_path = HAC_PATH_MMA;        // what HAC_PATH_AUTO resolves to
