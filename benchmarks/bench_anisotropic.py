@@ -39,10 +39,12 @@ def main():
     same = all(set(best_i[r].tolist()) == set(I[r].tolist()) for r in range(n_chk))
     print(json.dumps({"config": "anisotropic corpus x = mu + 0.3*eps, %d x 768, %d queries, k=%d" % (args.rows, args.queries, args.k),
                       "ms_per_search": st["total_ms"], "scan_ms": st["scan_ms"], "queries_per_s": args.queries / st["total_ms"] * 1e3,
-                      "retries": st["retries"], "n_chunks": st["n_chunks"], "candidates_emitted": st["candidates_emitted"],
+                      "path": st["path"], "warm_rows": st["warm_rows"], "retries": st["retries"], "n_chunks": st["n_chunks"], "candidates_emitted": st["candidates_emitted"],
                       "candidates_rescored": st["candidates_rescored"], "margin_max": st["margin_max"],
                       "screen_err_max": st["screen_err_max"], "score_top1_median": float(D[:, 0].median()),
-                      "score_rank_k_median": float(D[:, -1].median()), "fp64_check_recall": 1.0 if same else 0.0}), flush=True)
+                      "score_rank_k_median": float(D[:, -1].median()), "fp64_check_recall": 1.0 if same else 0.0,
+                      "hbm_f16_gb": st["bytes_shadow"] / 1e9}), flush=True)
+    assert same and st["retries"] == 0
 
 
 if __name__ == "__main__":
