@@ -270,6 +270,36 @@ def test_in_process_index_shards_on_one_device():
     index.close()
 
 
+@pytest.mark.parametrize("n_shards,n,nq,k", [(3, 20011, 130, 100), (5, 9000, 7, 10), (4, 3, 5, 4)])
+def test_in_process_index_with_more_shards_than_devices(n_shards, n, nq, k):
+    """The native shard group with 3-5 shards on cuda:0 (uneven splits, shards that stay empty, several peers per
+    shard in the threshold exchange): same results as one index over all rows."""
+    import haconvdr_b200 as hb
+    from haconvdr_b200 import faiss_compat as faiss
+    from oracle.compare import assert_parity
+    from oracle.flat_ip import brute_force_fp64
+    rng = np.random.default_rng(n_shards * 1000 + n)
+    x = rng.standard_normal((n, 768), dtype=np.float32)
+    q = rng.standard_normal((nq, 768), dtype=np.float32)
+    index = faiss.ShardedInProcessIndex(768, [0] * n_shards)
+    index.add(x[: n // 2])
+    index.add(x[n // 2:])
+    assert index.ntotal == n and sum(sh.ntotal for sh in index.shards) == n
+    D, I = index.search(q, k)
+    one = hb.FlatIPIndex(768, 0)
+    one.add(x)
+    D1, I1 = one.search(q, k)
+    assert np.array_equal(I, I1) and np.array_equal(D, D1)          # bitwise what a single shard returns
+    if n >= 4 * k:
+        x64 = x.astype(np.float64)
+        D64, I64 = brute_force_fp64(q, x, k)
+        assert_parity(D64, I64, D, I, rtol=1e-5, ref_scores_of=lambda qi, ids: x64[ids] @ q[qi].astype(np.float64))
+    else:                                                           # k > rows: faiss' unfilled slots behind the rows
+        assert (I[:, n:] == -1).all() and (np.sort(I[:, :n], axis=1) == np.arange(n)).all()
+    one.close()
+    index.close()
+
+
 def test_shard_group_through_the_raw_c_abi():
     """hac_shards_* called as a C host would: borrowed handles, mismatching dimensions refused, per-shard id bases and
     options respected, argument errors reported through hac_last_error()."""
