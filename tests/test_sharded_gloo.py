@@ -97,6 +97,66 @@ def test_sharded_index_world_size_2_gloo(tmp_path):
     assert all(os.path.exists(os.path.join(str(tmp_path), "ok_%d.npy" % r)) for r in range(2))
 
 
+class FlakyShard(OracleShard):
+    """Raises once, on the chosen rank only (stands in for an overflow / out-of-memory of one GPU's local search)."""
+
+    def __init__(self, d, fail_now):
+        super().__init__(d)
+        self.fail_now = fail_now
+
+    def search(self, q, k):
+        if self.fail_now():
+            raise RuntimeError("local search failed on this rank")
+        return super().search(q, k)
+
+
+def _worker_failure(rank, world, port, tmp):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from haconvdr_b200.sharded import ShardedFlatIPIndex
+        from oracle.flat_ip import brute_force_fp64
+        rng = np.random.default_rng(7)
+        x = rng.standard_normal((400, 64)).astype(np.float32)
+        q = rng.standard_normal((9, 64)).astype(np.float32)
+        calls = {"n": 0}
+
+        def fail_now():
+            calls["n"] += 1
+            return rank == 1 and calls["n"] == 2             # the second search fails, on rank 1 only
+        idx = ShardedFlatIPIndex(64, local_index=FlakyShard(64, fail_now), merge=numpy_merge)
+        idx.add(x)
+        D64, I64 = brute_force_fp64(q, x, 10)
+        D, I = idx.search(q, 10)
+        assert np.array_equal(np.asarray(I), I64)
+        # one rank fails: EVERY rank must raise (the failing one its own error), none may hang in a collective
+        try:
+            idx.search(q, 10)
+            raised = None
+        except RuntimeError as e:
+            raised = str(e)
+        assert raised is not None, "rank %d returned a result although rank 1 failed" % rank
+        assert ("this rank" in raised) == (rank == 1), (rank, raised)
+        # and the protocol is still aligned afterwards: the next search works on all ranks
+        D, I = idx.search(q, 10)
+        assert np.array_equal(np.asarray(I), I64)
+        np.save(os.path.join(tmp, "fail_ok_%d.npy" % rank), np.asarray([1]))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(180)
+def test_a_failure_on_one_rank_raises_on_every_rank_gloo(tmp_path):
+    """ADVICE (round 1): a local failure on one rank must not leave the others waiting in a collective."""
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    mp.spawn(_worker_failure, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    assert all(os.path.exists(os.path.join(str(tmp_path), "fail_ok_%d.npy" % r)) for r in range(2))
+
+
 def test_shard_bounds_cover_rows_exactly():
     from haconvdr_b200.sharded import shard_bounds
     for n in (0, 1, 7, 25_700_592, 54_573_064):
