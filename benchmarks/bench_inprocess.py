@@ -26,6 +26,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--no-exchange", action="store_true")
+    ap.add_argument("--pinned", action="store_true", help="page-locked query / result arrays (what bench.py's e2e leg uses)")
     args = ap.parse_args()
     import numpy as np
     import torch
@@ -58,12 +59,19 @@ def main():
         torch.cuda.synchronize(g)
     setup_s = time.perf_counter() - t0
     q = synth_rows_device(args.queries, d, seed=4242, device=0).cpu().numpy()
+    out = {}
+    if args.pinned:
+        qp = torch.empty((args.queries, d), dtype=torch.float32).pin_memory()
+        qp.copy_(torch.from_numpy(q))
+        q = qp.numpy()
+        out = {"D": torch.empty((args.queries, args.k), dtype=torch.float32).pin_memory().numpy(),
+               "I": torch.empty((args.queries, args.k), dtype=torch.int64).pin_memory().numpy()}
     for _ in range(args.warmup):
-        D, I = index.search(q, args.k)
+        D, I = index.search(q, args.k, **out)
     times = []
     for _ in range(args.steps):
         t0 = time.perf_counter()
-        D, I = index.search(q, args.k)
+        D, I = index.search(q, args.k, **out)
         times.append(time.perf_counter() - t0)
     ms = 1e3 * sum(times) / len(times)
     # parity of 32 queries spread over the batch against an fp64 re-scoring of the WHOLE regenerated corpus (every device
@@ -101,7 +109,7 @@ def main():
         ok = ok and bool(np.all(got_s >= kth - 1e-5 * abs(kth)))               # nothing better than the k-th best was missed
         n_identical += int(np.array_equal(I[qi], ext_i[r, :args.k]))
     st = index.stats() if sharded else [index.stats()]
-    print(json.dumps({"what": "in-process drop-in (faiss_compat.index_cpu_to_gpu_multiple, co.shard)", "n_gpus": G,
+    print(json.dumps({"what": "in-process drop-in (faiss_compat.index_cpu_to_gpu_multiple, co.shard)", "n_gpus": G, "pinned_host_arrays": bool(args.pinned),
                       "rows": args.rows, "queries": args.queries, "k": args.k, "steps": args.steps,
                       "ms_per_search_host_to_host": ms, "best_ms": 1e3 * min(times),
                       "queries_per_s": args.queries / (ms * 1e-3), "spot_check_ok": bool(ok),

@@ -88,8 +88,8 @@ class IndexFlatIP:
     def add(self, x):
         self._get().add(x)
 
-    def search(self, q, k):
-        return self._get().search(q, k)
+    def search(self, q, k, D=None, I=None):
+        return self._get().search(q, k, D=D, I=I)
 
     def reset(self):
         if self._impl is not None:
