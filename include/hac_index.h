@@ -168,7 +168,7 @@ int hac_enable_peer_access(int device, int peer);
  *                       one per device (several on one device are allowed), enables peer access between their devices
  *                       and starts one host thread per shard - faiss' IndexShards keeps a C++ thread per sub-index too.
  *                       The handles are borrowed: add / reset / id bases stay per shard (hac_add, hac_set_id_base),
- *                       the group must be destroyed before them.
+ *                       the group must be destroyed before them.  Like a handle, a group is not re-entrant.
  * hac_shards_search  <- D, I = index.search(query_embeddings, topN) on that sharded index (:102): every shard thread
  *                       copies the host queries to its device and runs the single-shard search with the cross-shard
  *                       threshold exchange armed (peer-mapped buffers owned by the group), then ONE merge kernel on the
